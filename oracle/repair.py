@@ -1,0 +1,273 @@
+"""Oracle pipeline: ErrorModel.detect + RepairModel._run (TEST INFRASTRUCTURE -- see
+oracle/__init__.py).
+
+Restates ``errors.py:389-461,545-582`` (detection pipeline), ``RepairApi.scala:69-104``
+(current values), ``:171-211`` (NULL masking), ``model.py:533-555`` (split), ``:677-729``
+(features / encoders), ``:955-1052`` (model bookkeeping), ``:1062-1143`` (inference chain) and
+``:1398-1401`` (output shaping).  Model *training* is delegated to a ``model_provider`` callback
+(the reference delegates it to LightGBM, ``train.py:89-229``).
+"""
+import numpy as np
+
+from . import detect as D
+from . import domain as DM
+from . import stats as S
+from .forest import (encode_rows, encoder_kind, first_seen_categories, forest_predict)
+from .table import OTable, cast_to_string
+
+DEFAULT_OPTS = {  # errors.py:321-338, model.py:115-123
+    "error.attr_freq_ratio_threshold": 0.0,
+    "error.pairwise_freq_ratio_threshold": 0.05,
+    "error.max_attrs_to_compute_pairwise_stats": 3,
+    "error.max_attrs_to_compute_domains": 2,
+    "error.domain_threshold_alpha": 0.0,
+    "error.domain_threshold_beta": 0.70,
+    "model.max_training_row_num": 10000,
+    "model.max_training_column_num": 65536,
+    "model.small_domain_threshold": 12,
+}
+
+
+def _opt(opts, key):
+    v = (opts or {}).get(key, DEFAULT_OPTS[key])
+    return type(DEFAULT_OPTS[key])(v)
+
+
+def _detector_targets(det, pipeline_targets):
+    # ErrorDetector.setUp (errors.py:49-59)
+    own = det.get("targets") or []
+    if own:
+        return [t for t in pipeline_targets if t in set(own)]
+    return list(pipeline_targets)
+
+
+def run_detectors(tbl, row_id, targets, detectors, continuous):
+    """_detect_error_cells (errors.py:405-421): union + distinct of all detector outputs."""
+    target_attrs = [c for c in tbl.names if c != row_id]
+    if targets:
+        target_attrs = [c for c in target_attrs if c in set(targets)]  # errors.py:398-402
+    if not detectors:  # errors.py:389-396
+        detectors = [{"type": "null"}]
+        for c in (targets if targets else [c for c in tbl.names if c != row_id]):
+            detectors.append({"type": "domain", "attr": c, "values": [], "autofill": True, "min_count_thres": 4})
+    cells = set()
+    for det in detectors:
+        tg = _detector_targets(det, target_attrs)
+        t = det["type"]
+        if t == "null":
+            cells |= D.null_cells(tbl, row_id, tg)
+        elif t == "regex":
+            cells |= D.regex_cells(tbl, row_id, tg, det["attr"], det["regex"])
+        elif t == "domain":
+            rx = D.domain_values_regex(tbl, det["attr"], det.get("values", []), det.get("autofill", False),
+                                       det.get("min_count_thres", 12), continuous)
+            if rx is not None and det["attr"] in tbl.cols:
+                cells |= D.regex_cells(tbl, row_id, tg, det["attr"], rx)
+        elif t == "constraint":
+            cells |= D.constraint_cells(tbl, row_id, tg, det.get("path", ""), det.get("constraints", ""))
+        elif t == "outlier":
+            cells |= D.outlier_cells(tbl, row_id, continuous, tg, det.get("approx", False))
+        else:
+            raise ValueError(t)
+    return cells
+
+
+def with_current_values(tbl, cells):
+    """RepairApi.withCurrentValues (:69-104): current_value = CAST(cell AS STRING)."""
+    col_pos = {n: i for i, n in enumerate(tbl.names)}
+    out = []
+    for (r, a) in sorted(cells, key=lambda c: (c[0], col_pos[c[1]])):
+        out.append((r, a, cast_to_string(tbl.kinds[a], tbl.value(a, r))))
+    return out
+
+
+def error_model_detect(tbl, row_id, targets, discrete_thres, detectors, given_error_cells, continuous, opts=None):
+    """ErrorModel.detect (errors.py:545-582).
+
+    -> (error cells [(row_pos, attr, current_value)], target_columns, pairwise_stats, domain_stats)
+    ``given_error_cells``: optional list of (row_id_value, attribute)."""
+    if given_error_cells is not None:  # errors.py:434-446
+        idpos = {cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r)): r for r in range(tbl.n_rows)}
+        keep = set(targets) if targets else set(tbl.names)
+        cells = set()
+        for rid, a in given_error_cells:
+            if a in keep and a in tbl.cols and str(rid) in idpos:
+                cells.add((idpos[str(rid)], a))
+    else:
+        cells = run_detectors(tbl, row_id, targets, detectors, continuous)
+    if not cells:
+        return [], [], {}, {}
+    noisy_columns = [c for c in tbl.names if c in {a for _, a in cells}]
+    noisy = with_current_values(tbl, cells)
+    disc, domain_stats = S.convert_to_discretized_table(tbl, row_id, discrete_thres)
+    disc_cols = disc.names
+    if len(disc_cols) == 0:
+        return noisy, [], {}, {}
+    target_columns = [c for c in noisy_columns if c in disc_cols]
+    if len(target_columns) == 0 or len(disc_cols) <= 1:
+        return noisy, target_columns, {}, domain_stats
+    fs, pairwise, _ = S.compute_attr_stats(
+        disc, row_id, target_columns, domain_stats,
+        _opt(opts, "error.attr_freq_ratio_threshold"),
+        _opt(opts, "error.pairwise_freq_ratio_threshold"),
+        _opt(opts, "error.max_attrs_to_compute_pairwise_stats"))
+    error_cells = noisy
+    if given_error_cells is None:  # errors.py:569-576
+        doms = DM.compute_domain_in_error_cells(
+            disc, row_id, noisy, continuous, target_columns, fs, pairwise, domain_stats,
+            _opt(opts, "error.max_attrs_to_compute_domains"),
+            _opt(opts, "error.domain_threshold_alpha"),
+            _opt(opts, "error.domain_threshold_beta"))
+        weak = DM.weak_labeled_cells(disc, doms)
+        error_cells = [c for c in noisy if (c[0], c[1]) not in weak]
+    return error_cells, target_columns, pairwise, domain_stats
+
+
+def convert_error_cells_to_null(tbl, cells, target_columns):
+    """RepairApi.convertErrorCellsToNull (:171-211) on the ORIGINAL table (model.py:1323)."""
+    out = tbl.copy()
+    for (r, a, _) in cells:
+        if a in target_columns:
+            if out.cols[a].dtype == object:
+                out.cols[a][r] = None
+            elif out.kinds[a] == "str":
+                out.cols[a][r] = -1
+            else:
+                out.cols[a][r] = np.nan
+    return out
+
+
+def sample_training_rows(candidates, max_rows, seed=42):
+    """Deterministic stand-in for the unseeded ``df.sample(ratio)`` (model.py:755-766): exactly
+    ``max_rows`` rows without replacement when there are more, in table order."""
+    candidates = np.asarray(candidates, dtype=np.int64)
+    if len(candidates) <= max_rows:
+        return candidates
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(len(candidates), size=max_rows, replace=False))
+    return candidates[idx]
+
+
+def select_features(pairwise_stats, y, features, max_training_column_num):
+    """RepairModel._select_features (model.py:677-699)."""
+    if max_training_column_num < len(features) and y in pairwise_stats:
+        fts = sorted([(float(corr), f) for f, corr in pairwise_stats[y] if f in features])
+        top = []
+        for corr, f in fts:
+            if len(top) <= 1 or (corr >= 0.0 and len(top) < max_training_column_num):
+                top.append((corr, f))
+        features = [f for _, f in top]
+    return features
+
+
+def column_values(tbl, name, rows=None):
+    idx = range(tbl.n_rows) if rows is None else rows
+    return [tbl.value(name, int(r)) for r in idx]
+
+
+def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stats, continuous, opts,
+           model_provider, repair_data=False):
+    """RepairModel._run phases 2-3 (model.py:1311-1408), default mode.
+
+    ``model_provider(ctx) -> spec`` is called once per target that needs a statistical model with
+    ctx = {y, features, encoders (fitted categories), X (encoded training matrix), y_values,
+    is_discrete, num_class, train_rows};  spec = {"forest": flat forest, "classes": [labels
+    ascending] or None}  or  {"const": value}.
+    -> list of (row_id_string, attribute, current_value, repaired)."""
+    if not error_cells:
+        return []
+    if len(target_columns) == 0:
+        raise ValueError("At least one valid discretizable feature is needed to repair error cells, "
+                         "but no such feature found")
+    error_cells = [c for c in error_cells if c[1] in target_columns]  # model.py:1316
+    base = convert_error_cells_to_null(tbl, error_cells, target_columns)
+    dirty_pos = sorted({c[0] for c in error_cells})
+    columns = [c for c in base.names if c != row_id]  # train_df.drop(row_id) (model.py:985)
+    integral = {c for c in base.names if base.kinds[c] == "int"}
+    models = []
+    for y in target_columns:  # model.py:1001-1052
+        is_discrete = y not in continuous
+        y_all = column_values(base, y)
+        input_columns = [c for c in columns if c != y]
+        num_class = len({v for v in y_all if v is not None}) if is_discrete else 0
+        if is_discrete and num_class <= 1:
+            v = next((v for v in y_all if v is not None), None) if num_class == 1 else None
+            models.append((y, {"const": v}, input_columns, None))
+            continue
+        features = select_features(pairwise_stats, y, input_columns, _opt(opts, "model.max_training_column_num"))
+        cand = [r for r in range(base.n_rows) if y_all[r] is not None]
+        if len(cand) == 0:
+            models.append((y, {"const": None}, features, None))
+            continue
+        rows = sample_training_rows(cand, _opt(opts, "model.max_training_row_num"))
+        train_cols = {f: column_values(base, f, rows) for f in features}
+        encoders = []
+        for f in features:
+            kind = encoder_kind(f, continuous, domain_stats, _opt(opts, "model.small_domain_threshold"))
+            e = {"attr": f, "type": kind}
+            if kind != "cont":
+                e["categories"] = first_seen_categories(train_cols[f])
+            encoders.append(e)
+        X = encode_rows(encoders, train_cols)
+        ctx = {"y": y, "features": features, "encoders": encoders, "X": X,
+               "y_values": [y_all[int(r)] for r in rows], "is_discrete": is_discrete,
+               "num_class": num_class, "train_rows": rows}
+        spec = model_provider(ctx)
+        models.append((y, spec, features, encoders))
+    # ---- repair UDF (model.py:1096-1135): sequential chain over targets on the dirty rows ----
+    dirty = base.take(np.array(dirty_pos, dtype=np.int64))
+    for (y, spec, features, encoders) in models:
+        ycol = dirty.cols[y]
+        n = dirty.n_rows
+        if "const" in spec:
+            pred = [spec["const"]] * n
+        else:
+            X = encode_rows(encoders, {f: column_values(dirty, f) for f in features})
+            p = forest_predict(spec["forest"], X)
+            if spec.get("classes") is not None:
+                pred = [spec["classes"][int(i)] for i in p]
+            elif y in integral:
+                pred = [int(v) for v in np.round(p)]  # model.py:1131-1132
+            else:
+                pred = [float(v) for v in p]
+        for i in range(n):  # pdf[y].where(pdf[y].notna(), predicted)
+            if dirty.value(y, i) is None:
+                v = pred[i]
+                if ycol.dtype == object:
+                    ycol[i] = v
+                elif dirty.kinds[y] == "str":
+                    ycol[i] = -1 if v is None else int(v)
+                else:
+                    ycol[i] = np.nan if v is None else float(v)
+    if repair_data:
+        out = base.copy()
+        for i, r in enumerate(dirty_pos):
+            for c in columns:
+                out.cols[c][r] = dirty.cols[c][i]
+        return out
+    # ---- flatten + join + filter (model.py:1398-1401) ----
+    dpos = {r: i for i, r in enumerate(dirty_pos)}
+    out = []
+    for (r, a, cur) in error_cells:
+        rep = cast_to_string(dirty.kinds[a], dirty.value(a, dpos[r]))
+        if rep is None or cur is None or str(cur) != str(rep):  # repaired IS NULL OR NOT(cur <=> repaired)
+            rid = cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r))
+            out.append((rid, a, cur, rep))
+    return out
+
+
+def run(tbl, row_id, detectors=None, targets=None, discrete_thres=80, given_error_cells=None, opts=None,
+        model_provider=None, detect_errors_only=False, repair_data=False):
+    """RepairModel.run, default / detect_errors_only / repair_data modes."""
+    continuous = S.check_input_table(tbl, row_id)
+    targets = targets or []
+    if targets and not (set(targets) & set(tbl.names)):
+        raise ValueError("Target attributes not found in input: {}".format(",".join(targets)))
+    cells, target_columns, pairwise, domain_stats = error_model_detect(
+        tbl, row_id, targets, discrete_thres, detectors or [], given_error_cells, continuous, opts)
+    if detect_errors_only:
+        return [(cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r)), a, cur) for (r, a, cur) in cells]
+    if not cells:
+        return tbl if repair_data else []
+    return repair(tbl, row_id, cells, target_columns, pairwise, domain_stats, continuous, opts,
+                  model_provider, repair_data=repair_data)

@@ -1,0 +1,500 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Each test names the reference suite (file:line) whose inline table / expectation it transcribes.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import detect as D
+from oracle import domain as DM
+from oracle import repair as R
+from oracle import stats as S
+from oracle.table import AnalysisException, from_csv, from_rows
+
+
+def adult(infer=True):
+    return from_csv(os.path.join(GOLDEN, "adult.csv"), infer_schema=infer)
+
+
+def tids(tbl, cells, row_id="tid"):
+    out = []
+    for (r, a) in cells:
+        v = tbl.value(row_id, r)
+        out.append((v, a))
+    return sorted(out, key=lambda t: (t[0], t[1]))
+
+
+# ------------------------------------------------------------------ detectors
+def test_null_detector_scala_kat():
+    # ErrorDetectorSuite.scala:51-73
+    t = from_rows(["tid", "v1", "v2", "v3"], [
+        ("1", 100000, 3.0, "test-1"), ("2", None, 8.0, "test-2"),
+        ("3", 300000, 1.0, None), ("4", 400000, None, "test-4")])
+    assert tids(t, D.null_cells(t, "tid", ["v1", "v2", "v3"])) == [("2", "v1"), ("3", "v3"), ("4", "v2")]
+    assert tids(t, D.null_cells(t, "tid", ["v1"])) == [("2", "v1")]
+    assert tids(t, D.null_cells(t, "tid", ["v2", "v3"])) == [("3", "v3"), ("4", "v2")]
+    assert tids(t, D.null_cells(t, "tid", ["v3", "v1"])) == [("2", "v1"), ("3", "v3")]
+    assert tids(t, D.null_cells(t, "tid", ["v3", "v2", "v5"])) == [("3", "v3"), ("4", "v2")]
+
+
+def test_null_detector_adult():
+    # tests/test_errors.py:50-82
+    t = adult()
+    exp = [(3, "Sex"), (5, "Age"), (5, "Income"), (7, "Sex"), (12, "Age"), (12, "Sex"), (16, "Income")]
+    assert tids(t, D.null_cells(t, "tid", ["Sex", "Age", "Income"])) == exp
+    assert tids(t, D.null_cells(t, "tid", ["Sex"])) == [(3, "Sex"), (7, "Sex"), (12, "Sex")]
+    assert tids(t, D.null_cells(t, "tid", ["Income", "Unknown"])) == [(5, "Income"), (16, "Income")]
+    assert D.null_cells(t, "tid", ["Non-existent"]) == set()
+
+
+def test_regex_detector_scala_kat():
+    # ErrorDetectorSuite.scala:75-116
+    t = from_rows(["tid", "v1", "v2", "v3"], [
+        ("1", 123, 53.0, "123-abc"), ("2", 123456, 123.0, "456-efg"),
+        ("3", 123000, 456.0, None), ("4", 987654321, None, "123-hij")])
+    tg = ["v1", "v2", "v3"]
+    assert tids(t, D.regex_cells(t, "tid", tg, "v3", "123-hij")) == [("1", "v3"), ("2", "v3"), ("3", "v3")]
+    assert tids(t, D.regex_cells(t, "tid", tg, "v3", "123.*")) == [("2", "v3"), ("3", "v3")]
+    assert tids(t, D.regex_cells(t, "tid", tg, "v1", "123.*")) == [("4", "v1")]
+    assert tids(t, D.regex_cells(t, "tid", ["v3"], "v3", "123.*")) == [("2", "v3"), ("3", "v3")]
+    assert tids(t, D.regex_cells(t, "tid", ["v2", "v3"], "v2", "123.*")) == [("1", "v2"), ("3", "v2"), ("4", "v2")]
+    for rx in (None, "", "    "):
+        assert D.regex_cells(t, "tid", tg, "v1", rx) == set()
+
+
+def test_regex_and_domain_values_adult():
+    # tests/test_errors.py:84-153
+    t = adult()
+    rx = D.domain_values_regex(t, "Country", [], False, 12, [])
+    assert rx == "$^"
+    assert tids(t, D.regex_cells(t, "tid", ["Country"], "Country", rx)) == [(i, "Country") for i in range(20)]
+    rx = D.domain_values_regex(t, "Country", ["United-States"], False, 12, [])
+    assert tids(t, D.regex_cells(t, "tid", ["Country"], "Country", rx)) == [(7, "Country"), (19, "Country")]
+    rx = D.domain_values_regex(t, "Income", ["LessThan50K", "MoreThan50K"], False, 12, [])
+    assert tids(t, D.regex_cells(t, "tid", ["Income"], "Income", rx)) == [(5, "Income"), (16, "Income")]
+    rx = D.domain_values_regex(t, "Country", [], True, 4, [])
+    assert tids(t, D.regex_cells(t, "tid", ["Country"], "Country", rx)) == [(7, "Country"), (19, "Country")]
+    rx = D.domain_values_regex(t, "Income", [], True, 1, [])
+    assert tids(t, D.regex_cells(t, "tid", ["Income"], "Income", rx)) == [(5, "Income"), (16, "Income")]
+    assert D.regex_cells(t, "tid", ["Non-existent"], "Country", "$^") == set()
+    assert tids(t, D.regex_cells(t, "tid", ["Unknown", "Country"], "Country", "United-States")) == \
+        [(7, "Country"), (19, "Country")]
+    t2 = from_rows(["tid", "v"], [(1, 12), (2, 123), (3, 1234), (4, 12345)])
+    assert tids(t2, D.regex_cells(t2, "tid", ["v"], "v", "123.+")) == [(1, "v"), (2, "v")]
+
+
+def _fd_table():
+    return from_rows(["tid", "v1", "v2"], [
+        ("1", 1, "test-1"), ("2", 1, "test-1"), ("3", 1, None), ("4", 2, "test-2"),
+        ("5", 2, "test-X"), ("6", 3, "test-3"), ("7", 4, "test-4"), ("8", 4, "test-4")])
+
+
+@pytest.mark.parametrize("brute", [False, True])
+def test_constraint_detector_scala_kat(brute, tmp_path):
+    # ErrorDetectorSuite.scala:118-186 (NULL counts as a distinct value in the v1=1 group)
+    t = _fd_table()
+    p = tmp_path / "constraints.txt"
+    p.write_text("t1&t2&EQ(t1.v1,t2.v1)&IQ(t1.v2,t2.v2)")
+
+    def run(targets):
+        return tids(t, D.constraint_cells(t, "tid", targets, str(p), "", force_bruteforce=brute))
+    rows = ["1", "2", "3", "4", "5"]
+    assert run(["v1", "v2"]) == sorted([(r, a) for r in rows for a in ("v1", "v2")])
+    assert run(["v1"]) == [(r, "v1") for r in rows]
+    assert run(["v2", "v1"]) == sorted([(r, a) for r in rows for a in ("v1", "v2")])
+    assert run(["v2", "v3"]) == [(r, "v2") for r in rows]
+
+
+@pytest.mark.parametrize("brute", [False, True])
+def test_constraint_detector_adult(brute):
+    # ErrorDetectorSuite.scala:188-201 ; tests/test_errors.py:155-204
+    t = adult()
+    path = os.path.join(GOLDEN, "adult_constraints.txt")
+
+    def run(targets, det_targets=None):
+        tg = [x for x in targets if x in det_targets] if det_targets else targets
+        return tids(t, D.constraint_cells(t, "tid", tg, path, "", force_bruteforce=brute))
+    exp = [(4, "Relationship"), (4, "Sex"), (11, "Relationship"), (11, "Sex")]
+    assert run(["Relationship", "Sex"]) == exp
+    assert run(["Sex", "Relationship"]) == exp
+    assert run(["Relationship", "Sex"], ["Relationship"]) == [(4, "Relationship"), (11, "Relationship")]
+    assert run(["Relationship"]) == [(4, "Relationship"), (11, "Relationship")]
+    assert run(["Unknown", "Sex"]) == [(4, "Sex"), (11, "Sex")]
+    assert run(["Non-existent"]) == []
+    assert run(["Income"]) == []
+
+
+def test_constraint_detector_invalid_path():
+    # ErrorDetectorSuite.scala:204-215
+    t = from_rows(["tid", "value"], [(0, 1)])
+    for path in (None, "", "     "):
+        assert D.constraint_cells(t, "tid", [], path, "") == set()
+
+
+def test_constraint_grouped_matches_bruteforce_random():
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n = int(rng.integers(1, 60))
+        rows = []
+        for i in range(n):
+            def val(d):
+                v = int(rng.integers(0, d + 1))
+                return None if v == d else "x%d" % v
+            rows.append((i, val(3), val(2), val(4)))
+        t = from_rows(["tid", "a", "b", "c"], rows, kinds=["int", "str", "str", "str"])
+        for cons in ("a->c", "t1&t2&EQ(t1.a,t2.a)&EQ(t1.b,t2.b)&IQ(t1.c,t2.c)",
+                     "t1&t2&EQ(t1.a,t2.a)&EQ(t1.b,t2.b)", 't1&EQ(t1.a,"x1")&IQ(t1.b,"x0")',
+                     't1&LT(t1.a,"x2")&GT(t1.c,"x1")'):
+            g = D.constraint_cells(t, "tid", ["a", "b", "c"], "", cons)
+            b = D.constraint_cells(t, "tid", ["a", "b", "c"], "", cons, force_bruteforce=True)
+            assert g == b, (cons, rows)
+
+
+def test_outlier_detector_kats():
+    # ErrorDetectorSuite.scala:217-231
+    t = from_rows(["tid", "value"], [(i, 100.0) for i in range(1000)] + [(1000, 0.0)])
+    for approx in (False, True):
+        assert tids(t, D.outlier_cells(t, "tid", ["value"], ["value"], approx)) == [(1000, "value")]
+        assert tids(t, D.outlier_cells(t, "tid", ["value"], ["v", "value"], approx)) == [(1000, "value")]
+    # tests/test_errors.py:206-234
+    t = from_rows(["tid", "v"], [(1, 1.0), (2, 1.0), (3, 1.0), (4, 1000.0), (5, None)])
+    assert tids(t, D.outlier_cells(t, "tid", ["v"], ["v"])) == [(4, "v")]
+    assert tids(t, D.outlier_cells(t, "tid", ["v"], ["Unknown", "v"])) == [(4, "v")]
+    assert D.outlier_cells(t, "tid", ["v"], ["Non-existent"]) == set()
+
+
+def test_spark_percentile():
+    assert D.spark_percentile([1.0, 2.0, 3.0, 4.0], 0.25) == 1.75
+    assert D.spark_percentile([1.0, 2.0, 3.0, 4.0, 5.0], 0.75) == 4.0
+    assert D.spark_percentile([5.0], 0.25) == 5.0
+
+
+# ------------------------------------------------------------------ DC parser
+def _s(preds):
+    def one(p):
+        l = "L." + p.left
+        r = ("R." + p.right) if p.right_kind == "attr" else p.right
+        return {"EQ": "{} <=> {}", "IQ": "NOT({} <=> {})", "LT": "{} < {}", "GT": "{} > {}"}[p.sign].format(l, r)
+    return {one(p) for p in preds}
+
+
+def test_dc_parse_valid():
+    # DenialConstraintsSuite.scala:27-52
+    assert _s(D.parse('t1&EQ(t1.v1,"abc")&EQ(t1.v2,"def")')) == {'L.v1 <=> "abc"', 'L.v2 <=> "def"'}
+    assert _s(D.parse("t1&t2&EQ(t1.v1,t2.v1)&IQ(t1.v2,t2.v2)")) == {"L.v1 <=> R.v1", "NOT(L.v2 <=> R.v2)"}
+    assert _s(D.parse("t1&t2&LT(t1.v1,t2.v1)&GT(t1.v2,t2.v2)&EQ(t1.v1,t2.v1)")) == \
+        {"L.v1 < R.v1", "L.v2 > R.v2", "L.v1 <=> R.v1"}
+    assert _s(D.parse(' t1 & EQ ( t1.v1 , "abc") & EQ ( t1.v2 , "def" ) ')) == {'L.v1 <=> "abc"', 'L.v2 <=> "def"'}
+    assert _s(D.parse("t1 & t2 & EQ ( t1.v1 , t2.v1 ) & IQ ( t1.v2 , t2.v2 ) ")) == \
+        {"L.v1 <=> R.v1", "NOT(L.v2 <=> R.v2)"}
+
+
+@pytest.mark.parametrize("dc", [
+    'EQ(t1.v1,"abc")', '1a&IQ(1a.v,"abc")', 'key&EQ(noexistent.v1,"abc")&EQ(key,"def")',
+    't1&1a&EQ(t1.v,"abc")&IQ(1a.v,"def")', 't1&EQ(t1.v1,"abc")&IL(t1.v1, "def")&EQ(t1.v2,"ghi")',
+    't1&t2&GT(t3.v0,"abc")&EQ(t1.v1,t2.v1)&IQ(t1.v2,t2.v2)',
+    't1&t2&GT(t3.v0,"abc")&EQ(t1.v1,t2.v1)&IL(t1.v2,t2.v2)', 't1&EQ(t1.v1,"abc")', "t1&", "t1", "a&b&", "k1&k2"])
+def test_dc_parse_invalid(dc):
+    # DenialConstraintsSuite.scala:54-98
+    with pytest.raises(ValueError) as e:
+        D.parse(dc)
+    assert any(m in str(e.value) for m in ("Failed to parse an input string", "Illegal predicates found",
+                                           "At least two predicate candidates should be given"))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        preds, refs = D.parse_and_verify_constraints([dc], ["v1", "v2"])
+    assert preds == [] and refs == []
+    assert sum("Illegal constraint format found: " + dc in str(x.message) for x in w) == 1
+
+
+def test_dc_parse_alt_and_verify():
+    # DenialConstraintsSuite.scala:175-257
+    def alt(cs):
+        return [_s(D.parse_alt(c)) for c in [x.strip() for x in cs.split(";")] if c]
+    exp = [{"L.X <=> R.X", "NOT(L.Y <=> R.Y)"}, {"L.Y <=> R.Y", "NOT(L.Z <=> R.Z)"}]
+    assert alt("X->Y;Y->Z") == exp and alt("X->Y;Y->Z;") == exp and alt(";X ->  Y; Y-> Z   ") == exp
+    assert alt("") == []
+
+    def verify(cs, attrs):
+        preds, refs = D.parse_and_verify_constraints(D.load_constraint_stmts("", cs), attrs)
+        return [_s(p) for p in preds], set(refs)
+    assert verify("X->Y;Y->Z", ["X", "Y", "Z"]) == (exp, {"X", "Y", "Z"})
+    assert verify("X->Y;Y->Z", ["X", "Y"]) == ([exp[0]], {"X", "Y"})
+    assert verify("X->Y;Y->Z", ["Y", "Z"]) == ([exp[1]], {"Y", "Z"})
+    assert verify("X->Y;Y->Z", ["Y"]) == ([], set())
+    for bad in ("X=>Y", "A", "X- >Y", "X -<  Y"):
+        with pytest.raises(ValueError):
+            D.parse_alt(bad)
+
+
+def test_dc_parse_hospital_file():
+    # DenialConstraintsSuite.scala:111-173
+    lines = D.load_constraint_stmts(os.path.join(GOLDEN, "hospital_constraints.txt"), "")
+    t = from_csv(os.path.join(GOLDEN, "hospital.csv"))
+    preds, refs = D.parse_and_verify_constraints(lines, t.names)
+    assert len(preds) == 15
+    assert set(refs) == {"HospitalOwner", "MeasureName", "Condition", "PhoneNumber", "CountyName",
+                         "ProviderNumber", "HospitalName", "HospitalType", "EmergencyService", "City",
+                         "ZipCode", "Address1", "State", "Stateavg", "MeasureCode"}
+    assert {"L.HospitalName <=> R.HospitalName", "L.PhoneNumber <=> R.PhoneNumber",
+            "L.HospitalOwner <=> R.HospitalOwner", "NOT(L.State <=> R.State)"} in [_s(p) for p in preds]
+
+
+# ------------------------------------------------------------------ input check / stats
+def test_check_input_table():
+    # RepairSuite.scala:51-87 ; tests/test_model.py:762-795
+    with pytest.raises(AnalysisException, match="A least three columns"):
+        S.check_input_table(from_rows(["tid", "c1"], [("a", 1)]), "tid")
+    with pytest.raises(AnalysisException, match=r"Uniqueness does not hold in column 'tid' of table 'inputView' "
+                                                r"\(# of distinct 'tid': 1, # of rows: 3\)"):
+        S.check_input_table(from_rows(["tid", "x", "y"], [(1, 1, None), (1, 1, "test-1"), (1, 2, "test-1")]),
+                            "tid", "inputView")
+    t = from_rows(["tid", "v0", "v1", "v2"], [(0, 0, 0.0, "0")])
+    assert S.check_input_table(t, "tid") == ["v0", "v1"]
+
+
+def test_with_current_values():
+    # RepairSuite.scala:89-113
+    t = from_rows(["tid", "c0", "c1", "c2"], [(1, 100, "abc", 1.2), (2, 200, "def", 3.2), (3, 300, "ghi", 2.1),
+                                              (4, 400, "jkl", 1.9), (5, 500, "mno", 0.5)])
+    cells = {(1, "c1"), (1, "c2"), (2, "c0"), (4, "c2")}
+    got = [(t.value("tid", r), a, cur) for r, a, cur in R.with_current_values(t, cells)]
+    assert got == [(2, "c1", "def"), (2, "c2", "3.2"), (3, "c0", "300"), (5, "c2", "0.5")]
+
+
+def test_table_stats_and_domain_sizes():
+    # RepairSuite.scala:115-142
+    t = from_rows(["v1", "v2", "v3"], [(i % 3, float(i % 8), str(i % 6)) for i in range(30)])
+    assert [S.column_stats(t, c)[0] for c in t.names] == [3, 8, 6]
+
+
+def test_discretize_hospital():
+    # RepairSuite.scala:144-177 -- kept columns at thres=20; Address2/3 have ndv 0.
+    t = from_csv(os.path.join(GOLDEN, "hospital.csv"))
+    disc, stats = S.convert_to_discretized_table(t, "tid", 20)
+    assert set(disc.names) == {"tid", "HospitalType", "EmergencyService", "State"}
+    # values the reference pins that HLL++ reports exactly at this size
+    for k, v in {"Address2": 0, "Address3": 0, "Condition": 28, "CountyName": 65, "HospitalType": 13,
+                 "EmergencyService": 6, "City": 72, "State": 4, "Stateavg": 74}.items():
+        assert stats[k] == v, k
+    # HLL++-approximate in the reference; exact here
+    assert stats["Sample"] == 333 and stats["ZipCode"] == 71
+
+
+def test_discretize_escaped_names():
+    # RepairSuite.scala:179-203
+    t = from_rows(["t i d", "c 0", "c 1", "c 2"], [(1, 100, "abc", 1.2), (2, 200, "def", 3.2), (3, 100, "def", 2.1),
+                                                   (4, 100, "abc", 1.9), (5, 200, "abc", 0.5)])
+    disc, stats = S.convert_to_discretized_table(t, "t i d", 2)
+    assert set(disc.names) == {"t i d", "c 0", "c 1", "c 2"}
+    assert stats == {"c 0": 2, "c 1": 2, "c 2": 5}
+    assert disc.cols["c 0"].tolist() == [0, 2, 0, 0, 2]
+    # int((v - 0.5) / (3.2 - 0.5) * 2)
+    assert disc.cols["c 2"].tolist() == [0, 2, 1, 1, 0]
+
+
+def test_convert_error_cells_to_null():
+    # RepairSuite.scala:205-235
+    t = from_rows(["tid", "c0", "c1", "c2"], [(1, 100, "abc", 1.2), (2, 200, "def", 3.2), (3, 300, "ghi", 2.1),
+                                              (4, 400, "jkl", 1.9), (5, 500, "mno", 0.5)])
+    cells = [(1, "c1", "def"), (1, "c2", "3.2"), (2, "c0", "300"), (4, "c2", "0.5")]
+    out = R.convert_error_cells_to_null(t, cells, ["c0", "c1", "c2"])
+    rows = [tuple(out.value(c, r) for c in out.names) for r in range(5)]
+    assert rows == [(1, 100, "abc", 1.2), (2, 200, None, None), (3, None, "ghi", 2.1),
+                    (4, 400, "jkl", 1.9), (5, 500, "mno", None)]
+
+
+_FREQ_VIEW = [(1, "1", "test-1"), (2, "2", "test-2"), (3, "3", "test-3"), (4, "2", "test-2"), (5, "1", "test-1"),
+              (6, "1", "test-1"), (7, "3", "test-3"), (8, "3", "test-3"), (9, "2", "test-2a")]
+
+
+@pytest.mark.parametrize("names", [("tid", "xx", "yy"), ("t i d", "x x", "y y")])
+def test_compute_freq_stats(names):
+    # RepairSuite.scala:237-286
+    tid, x, y = names
+    t = from_rows([tid, x, y], _FREQ_VIEW)
+    fs = S.compute_freq_stats(t, [[x], [y], [x, y]], 0.0)
+    assert fs.attrs == [x, y]
+    assert sorted(fs.as_tuples(), key=str) == sorted([
+        ("1", 0, "test-1", 0, 3), ("2", 0, "test-2a", 0, 1), (None, 1, "test-2a", 0, 1), ("2", 0, "test-2", 0, 2),
+        (None, 1, "test-2", 0, 2), ("3", 0, None, 1, 3), ("3", 0, "test-3", 0, 3), (None, 1, "test-1", 0, 3),
+        ("2", 0, None, 1, 3), (None, 1, "test-3", 0, 3), ("1", 0, None, 1, 3)], key=str)
+    fs = S.compute_freq_stats(t, [[x], [y], [x, y]], 0.3)
+    assert sorted(fs.as_tuples(), key=str) == sorted([
+        ("1", 0, "test-1", 0, 3), ("3", 0, None, 1, 3), ("3", 0, "test-3", 0, 3), (None, 1, "test-1", 0, 3),
+        ("2", 0, None, 1, 3), (None, 1, "test-3", 0, 3), ("1", 0, None, 1, 3)], key=str)
+    with pytest.raises(RuntimeError, match="Cannot handle more than two entries: {},{},{}".format(tid, x, y)):
+        S.compute_freq_stats(t, [[tid, x, y]], 0.0)
+
+
+def test_freq_stats_64_attr_limit():
+    # RepairSuite.scala:288-310
+    def run(k):
+        names = ["c%d" % i for i in range(k)]
+        t = from_rows(names, [tuple(0 for _ in names)])
+        sets = [[names[i], names[j]] for i in range(k) for j in range(i + 1, k)]
+        return S.compute_freq_stats(t, sets, 0.0)
+    fs = run(64)
+    assert len(fs.rows) == 2016 and {r[2] for r in fs.rows} == {1}
+    with pytest.raises(AnalysisException, match="Cannot handle the target attributes whose length is more than 64"):
+        run(65)
+
+
+def test_pairwise_stats_no_freq_stat():
+    # RepairSuite.scala:312-332: worst-case values 1.0 / 2.0
+    fs = S.FreqStats(["x", "y"], [])
+    m = S.compute_pairwise_stats(1000, fs, [("x", "y"), ("y", "x")], {"tid": 9, "x": 2, "y": 4})
+    assert set(m) == {"x", "y"}
+    assert m["x"] == [("y", 1.0)]
+    assert m["y"] == [("x", 2.0)]
+
+
+_PAIR_VIEW = [("2", 0, "test-2", 0, 2), ("2", 0, "test-1", 0, 2), ("3", 0, "test-1", 0, 1), ("1", 0, "test-1", 0, 1),
+              ("2", 0, "test-2a", 0, 1), ("3", 0, "test-3", 0, 2), (None, 1, "test-2", 0, 2), ("3", 0, None, 1, 3),
+              ("2", 0, None, 1, 5), (None, 1, "test-1", 0, 4), (None, 1, "test-2a", 0, 1), (None, 1, "test-3", 0, 2),
+              ("1", 0, None, 1, 1)]
+
+
+def _fs_from(attrs, tuples):
+    rows = []
+    for t in tuples:
+        vals = tuple(t[2 * i] for i in range(len(attrs)))
+        flags = tuple(t[2 * i + 1] for i in range(len(attrs)))
+        rows.append((vals, flags, t[-1]))
+    return S.FreqStats(attrs, rows)
+
+
+def test_pairwise_stats():
+    # RepairSuite.scala:334-365 (sign only in the reference; exact values re-derived by hand)
+    fs = _fs_from(["x", "y"], _PAIR_VIEW)
+    m = S.compute_pairwise_stats(9, fs, [("x", "y"), ("y", "x")], {"tid": 9, "x": 3, "y": 4})
+    assert [a for a, _ in m["x"]] == ["y"] and m["x"][0][1] > 0.0
+    assert [a for a, _ in m["y"]] == ["x"] and m["y"][0][1] > 0.0
+    # independent re-derivation: H(a|b) = H(a,b) - H(b) with scipy's entropy (base 2)
+    from scipy.stats import entropy
+    hxy = entropy([2, 2, 1, 1, 1, 2], base=2)
+    assert abs(m["x"][0][1] - (hxy - entropy([2, 4, 1, 2], base=2))) < 1e-12
+    assert abs(m["y"][0][1] - (hxy - entropy([3, 5, 1], base=2))) < 1e-12
+
+
+def test_compute_attr_stats():
+    # RepairSuite.scala:367-427
+    t = from_rows(["tid", "x", "y"], _FREQ_VIEW)
+    dom = {"tid": 9, "x": 3, "y": 4}
+    fs1, m1, _ = S.compute_attr_stats(t, "tid", ["x", "y"], dom, 0.0, 1.0, 256)
+    assert len(fs1.rows) == 11
+    assert m1["x"][0][0] == "y" and m1["x"][0][1] <= 1.0
+    assert m1["y"][0][0] == "x" and m1["y"][0][1] <= 1.0
+    fs2, m2, _ = S.compute_attr_stats(t, "tid", ["x", "y"], dom, 1.0, 1.0, 256)
+    assert fs2.rows == []
+    assert m1["x"][0][1] < m2["x"][0][1] and m1["y"][0][1] < m2["x"][0][1]
+
+
+# ------------------------------------------------------------------ domain analysis
+_DOMAIN_INPUT = [(1, "2", "test-1", 1), (2, "2", "test-2", 1), (3, "3", "test-1", 3), (4, "2", "test-2", 2),
+                 (5, "1", "test-1", 1), (6, "2", "test-1", 1), (7, "3", "test-3", 2), (8, "3", "test-3", 3),
+                 (9, "2", "test-2a", 2)]
+_DOMAIN_FREQ = [
+    ("2", 0, None, 1, 1, 0, 3), (None, 1, "test-1", 0, 1, 0, 3), ("2", 0, None, 1, 2, 0, 2),
+    ("2", 0, None, 1, None, 1, 5), (None, 1, "test-1", 0, None, 1, 4), ("2", 0, "test-2", 0, None, 1, 2),
+    (None, 1, None, 1, 3, 0, 2), (None, 1, "test-1", 0, 3, 0, 1), (None, 1, "test-2", 0, 1, 0, 1),
+    ("3", 0, None, 1, None, 1, 3), (None, 1, "test-2", 0, 2, 0, 1), (None, 1, None, 1, 0, 0, 4),
+    ("2", 0, "test-1", 0, None, 1, 2), (None, 1, "test-2", 0, None, 1, 2), ("3", 0, "test-1", 0, None, 1, 1),
+    (None, 1, None, 1, 2, 0, 3), ("3", 0, None, 1, 3, 0, 2), ("1", 0, "test-1", 0, None, 0, 1),
+    (None, 1, "test-3", 0, 2, 0, 1), (None, 1, "test-3", 0, 3, 0, 1), (None, 1, "test-2a", 0, 2, 0, 1),
+    ("1", 0, None, 1, None, 1, 1), ("3", 0, "test-3", 0, None, 1, 2), (None, 1, "test-2a", 0, None, 1, 1),
+    ("2", 0, "test-2a", 0, None, 1, 1), (None, 1, "test-3", 0, None, 1, 2), ("3", 0, None, 1, 2, 0, 1),
+    ("1", 0, None, 1, 1, 0, 1)]
+
+
+@pytest.mark.parametrize("names", [("tid", "xx", "yy", "zz"), ("t i d", "x x", "y y", "z z")])
+def test_compute_domain_in_error_cells(names):
+    # RepairSuite.scala:429-512 -- the 8 expected (tid, attribute, current_value, n) rows
+    tid, x, y, z = names
+    t = from_rows([tid, x, y, z], _DOMAIN_INPUT)
+    fs = _fs_from([x, y, z], _DOMAIN_FREQ)
+    cells = [(0, x, "2"), (2, y, "test-3"), (5, y, "test-2")]
+    pairwise = {x: [(y, 1.0)], y: [(x, 0.846950694324252)]}
+    dom = {tid: 9, x: 3, y: 4, z: 3}
+    out = DM.compute_domain_in_error_cells(t, tid, cells, [z], [x, y], fs, pairwise, dom, 4, 0.0, 0.01)
+    got = sorted((t.value(tid, r), a, cur, n) for r, a, cur, d in out for n, _ in d)
+    assert got == sorted([(1, x, "2", "1"), (1, x, "2", "2"), (1, x, "2", "3"), (3, y, "test-3", "test-1"),
+                          (3, y, "test-3", "test-3"), (6, y, "test-2", "test-1"), (6, y, "test-2", "test-2"),
+                          (6, y, "test-2", "test-2a")])
+    for _, _, _, d in out:
+        assert abs(sum(p for _, p in d) - 1.0) < 1e-9
+        assert [p for _, p in d] == sorted([p for _, p in d], reverse=True)
+
+
+# ------------------------------------------------------------------ pipeline: detect_errors_only
+def _cells(rows):
+    return sorted(rows, key=lambda r: (int(r[0]), r[1]))
+
+
+def test_detect_errors_only_adult():
+    # tests/test_model.py:510-646
+    t = adult()
+    null = [{"type": "null"}]
+    exp = [("3", "Sex", None), ("5", "Age", None), ("5", "Income", None), ("7", "Sex", None), ("12", "Age", None),
+           ("12", "Sex", None), ("16", "Income", None)]
+    assert _cells(R.run(t, "tid", null, detect_errors_only=True)) == exp
+    assert _cells(R.run(t, "tid", null, targets=["Sex", "Age", "Income"], detect_errors_only=True)) == exp
+    assert _cells(R.run(t, "tid", null, targets=["Sex"], detect_errors_only=True)) == \
+        [("3", "Sex", None), ("7", "Sex", None), ("12", "Sex", None)]
+    assert _cells(R.run(t, "tid", null, targets=["Unknown", "Age"], detect_errors_only=True)) == \
+        [("5", "Age", None), ("12", "Age", None)]
+    dets = [{"type": "domain", "attr": "Country", "values": ["United-States"]},
+            {"type": "domain", "attr": "Income", "values": ["LessThan50K", "MoreThan50K"]}]
+    assert _cells(R.run(t, "tid", dets, detect_errors_only=True)) == \
+        [("5", "Income", None), ("7", "Country", "India"), ("16", "Income", None), ("19", "Country", "Iran")]
+    dets = [{"type": "regex", "attr": "Country", "regex": "United-States"},
+            {"type": "regex", "attr": "Relationship", "regex": "(Husband|Own-child|Not-in-family)"}]
+    assert _cells(R.run(t, "tid", dets, targets=["Country", "Relationship"], detect_errors_only=True)) == \
+        [("7", "Country", "India"), ("14", "Relationship", "Unmarried"), ("16", "Relationship", "Unmarried"),
+         ("19", "Country", "Iran")]
+    path = os.path.join(GOLDEN, "adult_constraints.txt")
+    assert _cells(R.run(t, "tid", [{"type": "constraint", "path": path}], targets=["Sex", "Relationship"],
+                        detect_errors_only=True)) == \
+        [("4", "Relationship", "Husband"), ("4", "Sex", "Female"), ("11", "Relationship", "Husband"),
+         ("11", "Sex", "Female")]
+    assert _cells(R.run(t, "tid", [{"type": "constraint", "path": path, "targets": ["Sex"]}],
+                        targets=["Sex", "Relationship"], detect_errors_only=True)) == \
+        [("4", "Sex", "Female"), ("11", "Sex", "Female")]
+
+
+def test_detect_errors_only_given_cells():
+    # tests/test_model.py:470-483
+    t = adult()
+    given = [(12, "Age"), (12, "Sex"), (16, "Income"), (3, "Sex"), (5, "Age"), (5, "Income"), (7, "Sex")]
+    assert _cells(R.run(t, "tid", [{"type": "null"}], given_error_cells=given, detect_errors_only=True)) == \
+        [("3", "Sex", None), ("5", "Age", None), ("5", "Income", None), ("7", "Sex", None), ("12", "Age", None),
+         ("12", "Sex", None), ("16", "Income", None)]
+
+
+def test_domain_values_against_continuous_values():
+    # tests/test_model.py:648-675
+    t = from_rows(["tid", "x", "y", "z"], [(1, 1.0, 1.0, 1.0), (2, 1.1, 1.1, 1.1), (3, 1.0, 1.0, None),
+                                           (4, 1.1, 1.0, 1.0), (5, 1.1, 1.1, 1.1), (6, 1.0, 1.0, None)])
+    dets = [{"type": "domain", "attr": c, "autofill": True, "min_count_thres": 2} for c in "xyz"] + [{"type": "null"}]
+    assert _cells(R.run(t, "tid", dets, detect_errors_only=True)) == [("3", "z", None), ("6", "z", None)]
+
+
+def test_no_valid_discrete_feature():
+    # tests/test_model.py:817-839
+    t = from_rows(["tid", "x", "y"], [(1, "1", None)] + [(i, str(i), "test-%d" % i) for i in range(2, 7)])
+    assert R.run(t, "tid", [{"type": "null"}], discrete_thres=3, detect_errors_only=True) == [("1", "y", None)]
+    with pytest.raises(ValueError, match="At least one valid discretizable feature is needed to repair error cells"):
+        R.run(t, "tid", [{"type": "null"}], discrete_thres=3)
+
+
+def test_hospital_constraint_cell_count():
+    # the 15 FD-type DCs flag 11 038 distinct cells before pruning
+    t = from_csv(os.path.join(GOLDEN, "hospital.csv"))
+    cells = D.constraint_cells(t, "tid", [c for c in t.names if c != "tid"],
+                               os.path.join(GOLDEN, "hospital_constraints.txt"), "")
+    assert len(cells) == 11038
+    assert len(D.null_cells(t, "tid", t.names)) == 2227
