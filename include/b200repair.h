@@ -1,0 +1,242 @@
+/*
+ * b200repair.h -- C ABI of libb200repair.so (hand-written sm_100a CUDA behind the
+ * `delphi.repair` API).
+ *
+ * This is the drop-in boundary for the hot path: each entry point replaces one Py4J static call
+ * the reference's Python driver makes into its Scala side.  Reference
+ * paths below are relative to maropu/spark-data-repair-plugin @ 7701550d.
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success, non-zero on failure; dr_last_error(ctx) explains.
+ *     Nothing throws across the boundary, nothing aborts.
+ *   - "device" pointers are caller-owned device memory (the Python host passes
+ *     torch.Tensor.data_ptr()); the library never allocates long-lived device memory except a
+ *     small per-context scratch buffer.  "host" pointers are caller-owned host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls that return a
+ *     host value (counts, quartiles) synchronise that stream; all others are asynchronous.
+ *   - table layout: one device array of int32 codes per column, NULL = -1 (column-major,
+ *     label-encoded; numeric columns additionally as float64 with NaN = NULL).
+ *   - a cell set is a bitmap per column: uint32 words, bit (r & 31) of word (r >> 5) = row r.
+ *   - one dr_ctx per GPU; a ctx is not thread-safe; independent ctxs may run concurrently.
+ */
+#ifndef B200REPAIR_H
+#define B200REPAIR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_MAX_COLS 64 /* computeFreqStats' own limit, RepairApi.scala:241-244 */
+#define DR_OK 0
+#define DR_ERR_INVALID 1
+#define DR_ERR_CUDA 2
+#define DR_ERR_UNSUPPORTED 3
+
+typedef struct dr_ctx dr_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int dr_ctx_create(int device, dr_ctx** out);
+int dr_ctx_destroy(dr_ctx* ctx);
+const char* dr_last_error(const dr_ctx* ctx);
+int dr_abi_version(void);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+int64_t dr_launch_count(const dr_ctx* ctx);
+
+/* ---- a2 + a7/a8: NULL scan fused with per-column histograms ------------------------------------
+ * Replaces ErrorDetectorApi.detectNullCells (ErrorDetectorApi.scala:30-34,128-157: K_t UNION-ALL
+ * scans) and the single-attribute GROUPING SETS of RepairApi.computeFreqStats
+ * (RepairApi.scala:231-273) plus the NULL/ndv part of computeAndGetTableStats (:108-118).
+ *   cols[i]      device int32[n_rows]
+ *   dom[i]       domain size of column i (codes are in [-1, dom[i]))
+ *   bitmaps[i]   device uint32[ceil(n_rows/32)] or NULL; NULL cells are OR-ed in
+ *   hist         device int64[sum(dom[i] + 1)], ACCUMULATED (caller zeroes); column i occupies
+ *                slots [off_i, off_i + dom[i] + 1), slot 0 = NULL, slot c + 1 = code c
+ * One pass over the n_cols columns: 4 * n_cols algorithmic bytes per row. */
+int dr_scan_hist(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, int64_t n_rows,
+                 uint32_t* const* bitmaps, int64_t* hist, void* stream);
+
+/* ---- a5: RegExErrorDetector / DomainValues ----------------------------------------------------
+ * Replaces ErrorDetectorApi.detectErrorCellsFromRegEx (ErrorDetectorApi.scala:36-46,159-187).
+ * The regex is evaluated once per dictionary entry on the host; lut[c] = 1 iff entry c does NOT
+ * match.  Flags  code < 0 (NULL)  or  lut[code] != 0. */
+int dr_lut_scan(dr_ctx* ctx, const int32_t* col, int64_t n_rows, const uint8_t* lut, int32_t dict_size,
+                uint32_t* bitmap, void* stream);
+
+/* ---- a4: GaussianOutlierErrorDetector ---------------------------------------------------------
+ * Replaces ErrorDetectorApi.detectErrorCellsFromOutliers (ErrorDetectorApi.scala:60-70,249-300).
+ * dr_quartiles: exact Spark `percentile(col, [0.25, 0.75])` over non-NaN values (linear
+ * interpolation at p*(n-1)); out_q host double[2]; out_n host int64 = number of non-NaN values.
+ * dr_range_flag: flags  v < lower || v > upper  (NaN never flagged). */
+int dr_quartiles(dr_ctx* ctx, const double* col, int64_t n_rows, double* out_q, int64_t* out_n, void* stream);
+int dr_range_flag(dr_ctx* ctx, const double* col, int64_t n_rows, double lower, double upper, uint32_t* bitmap,
+                  void* stream);
+
+/* ---- a3: ConstraintErrorDetector --------------------------------------------------------------
+ * Replaces ErrorDetectorApi.detectErrorCellsFromConstraints (ErrorDetectorApi.scala:48-58,
+ * 189-244); the constraint text is parsed on the host (DenialConstraints.scala:82-225).
+ *
+ * dr_dc_const: single-tuple DC  t1&OP(t1.A, const)&...  -> row_bitmap bit set iff ALL predicates
+ * hold.  Predicate p compares cols[p] (dictionary sorted, so order = code order) with a constant:
+ *   DR_OP_EQ   code == arg[p]                       (arg = code of the constant, -2 if absent)
+ *   DR_OP_IQ   code != arg[p]                       (NOT(<=>): NULL differs from a constant)
+ *   DR_OP_LT   code >= 0 && code <  arg[p]          (arg = lower_bound rank of the constant)
+ *   DR_OP_GT   code >= 0 && code >= arg[p]          (arg = upper_bound rank of the constant)
+ *
+ * dr_dc_fd_build / dr_dc_fd_flag: two-tuple DC  EQ(a_1)..EQ(a_m) & IQ(b).  A row violates iff its
+ * NULL-safe key group holds >= 2 distinct b (NULL counted as a value).  Keys are mixed-radix
+ * numbers  key = sum (code_i + 1) * stride_i  over [0, key_space); lo/hi are device
+ * int32[key_space] tables (caller initialises lo = INT32_MAX, hi = INT32_MIN) holding min/max of
+ * (b + 1) per key -- both are idempotent reductions, so per-GPU tables combine with one
+ * MIN / MAX all-reduce.  flag sets row_bitmap where lo[key] != hi[key]. */
+#define DR_OP_EQ 0
+#define DR_OP_IQ 1
+#define DR_OP_LT 2
+#define DR_OP_GT 3
+int dr_dc_const(dr_ctx* ctx, const int32_t* const* cols, const int32_t* ops, const int32_t* args, int n_preds,
+                int64_t n_rows, uint32_t* row_bitmap, void* stream);
+int dr_dc_fd_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                   const int32_t* b_col, int64_t n_rows, int64_t key_space, int32_t* lo, int32_t* hi,
+                   void* stream);
+int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                  int64_t n_rows, int64_t key_space, const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap,
+                  void* stream);
+
+/* ---- bitmap plumbing (a6: union + distinct of detector outputs, errors.py:405-421) ------------
+ * dr_bitmap_or:      dst |= src                                  (n_rows bits)
+ * dr_bitmap_andnot:  dst &= ~src
+ * dr_bitmap_count:   popcount -> host int64
+ * dr_bitmap_to_rows: ascending row indices of set bits -> device int32[capacity]; host count.
+ *                    Fails with DR_ERR_INVALID if count > capacity.
+ * dr_bitmap_gather:  out bit i = src bit rows[i]                 (n bits out)
+ * dr_bitmap_clear_rows: clears bit rows[i] for every i with flags[i] != 0 */
+int dr_bitmap_or(dr_ctx* ctx, uint32_t* dst, const uint32_t* src, int64_t n_rows, void* stream);
+int dr_bitmap_andnot(dr_ctx* ctx, uint32_t* dst, const uint32_t* src, int64_t n_rows, void* stream);
+int dr_bitmap_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int64_t* out_count, void* stream);
+int dr_bitmap_to_rows(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t capacity,
+                      int64_t* out_count, void* stream);
+int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int64_t n, uint32_t* out,
+                     void* stream);
+int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,
+                         void* stream);
+
+/* ---- a7: discretisation of continuous attributes ----------------------------------------------
+ * Replaces the projection of RepairApi.convertToDiscretizedTable (RepairApi.scala:126-169):
+ *   out = (int)((v - vmin) / denom * thres)   (truncation toward zero), NaN -> -1; denom == 0 -> -1 */
+int dr_discretize(dr_ctx* ctx, const double* vals, int64_t n_rows, double vmin, double denom, int32_t thres,
+                  int32_t* out, void* stream);
+
+/* ---- a8: attribute-pair statistics -------------------------------------------------------------
+ * Replaces the K_t*(K-1) approx_count_distinct(struct(x, y)) scans (RepairApi.scala:430-448) and
+ * the pair GROUPING SETS of computeFreqStats (:231-273).
+ *
+ * dr_pair_presence: for every pair p = (px[p], py[p]) sets bit  (cx+1)*(dom[y]+1) + (cy+1)  of
+ * the pair's bit table for the rows of `n_blocks` row blocks of `block_rows` rows spread evenly
+ * over the table (block_rows * n_blocks >= n_rows -> every row).  bits: device uint32, pair p at
+ * word offset bit_off[p] (host int64[n_pairs+1], in words), OR-accumulated.  A sample gives lower
+ * bounds of the distinct-pair counts, the full table gives them exactly.
+ *
+ * dr_cooc: exact co-occurrence counts.  out: device int64, pair p occupies
+ * [tab_off[p], tab_off[p+1]) with entry (cx+1)*(dom[y]+1) + (cy+1); ACCUMULATED (caller zeroes). */
+int dr_pair_presence(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+                     const int32_t* py, int n_pairs, const int64_t* bit_off, int64_t n_rows, int64_t block_rows,
+                     int64_t n_blocks, uint32_t* bits, void* stream);
+int dr_cooc(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+            const int32_t* py, int n_pairs, const int64_t* tab_off, int64_t n_rows, int64_t* out, void* stream);
+
+/* ---- a9: cell-domain analysis (weak labelling) -------------------------------------------------
+ * Replaces RepairApi.computeDomainInErrorCells (RepairApi.scala:479-675) + the weak-label test
+ * of errors.py:517-524 for ONE target attribute.
+ *   rows          device int32[n_cells]      noisy cells of the target (row indices)
+ *   target        device int32[n_rows]       discretised target column (dom_t values)
+ *   corr[j]       device int32[n_rows]       discretised correlated attribute j, j < n_corr <= 8
+ *   cooc[j]       device int64[(dom_c[j]+1)*(dom_t+1)]  counts, entry (c+1)*(dom_t+1)+(t+1), i.e. the
+ *                                            candidate (target) index varies fastest
+ *   hist_t        device int64[dom_t+1]      single-attribute counts of the target
+ *   tau[j]        co-occurrence threshold (cnt > tau[j]), RepairApi.scala:572-576
+ *   out_top1      device int32[n_cells]      candidate with the highest probability among those
+ *                                            with prob > beta, -1 if none (ties: lowest code)
+ *   out_prob      device double[n_cells]     its probability (0 if none)
+ *   out_weak      device uint8[n_cells]      1 iff the cell's current code == out_top1 (the cell is
+ *                                            weak-labelled clean), else 0 */
+int dr_domain_score(dr_ctx* ctx, const int32_t* rows, int64_t n_cells, const int32_t* target, int32_t dom_t,
+                    const int32_t* const* corr, const int32_t* dom_c, const int64_t* const* cooc, int n_corr,
+                    const int64_t* hist_t, const int64_t* tau, int64_t n_total_rows, double beta,
+                    int32_t* out_top1, double* out_prob, uint8_t* out_weak, void* stream);
+
+/* ---- a10: repair base = error cells masked to NULL, restricted to the rows that matter ---------
+ * Replaces RepairApi.convertErrorCellsToNull (RepairApi.scala:171-211) and the dirty/clean split
+ * (model.py:550-555) without materialising the N x K masked table: gathers the given rows into a
+ * ROW-MAJOR int32[n][n_cols] tile, writing -1 where bitmaps[c] has the row's bit set
+ * (bitmaps[c] may be NULL = column is not a target).  Also used to pull training samples. */
+int dr_gather_rows_masked(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
+                          const int32_t* rows, int64_t n, int32_t* out, void* stream);
+/* Same for float64 side arrays of continuous attributes (NaN where masked). */
+int dr_gather_rows_masked_f64(dr_ctx* ctx, const double* const* cols, uint32_t* const* bitmaps, int n_cols,
+                              const int32_t* rows, int64_t n, double* out, void* stream);
+/* out bit i = (tile[i][col] < 0): the cells model `col` has to fill (model.py:1128-1133). */
+int dr_tile_null_bitmap(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols, int col, uint32_t* out,
+                        void* stream);
+int dr_tile_null_bitmap_f64(dr_ctx* ctx, const double* tile, int64_t n, int n_cols, int col, uint32_t* out,
+                            void* stream);
+/* out[i] = col[rows[i]]  (current values of error cells, RepairApi.withCurrentValues :69-104). */
+int dr_gather_i32(dr_ctx* ctx, const int32_t* col, const int32_t* rows, int64_t n, int32_t* out, void* stream);
+int dr_gather_f64(dr_ctx* ctx, const double* col, const int32_t* rows, int64_t n, double* out, void* stream);
+/* out[i] = tile[drows[i]][col]  (repaired values read back from the dirty-row tile). */
+int dr_tile_gather_i32(dr_ctx* ctx, const int32_t* tile, int n_cols, int col, const int32_t* drows, int64_t n,
+                       int32_t* out, void* stream);
+int dr_tile_gather_f64(dr_ctx* ctx, const double* tile, int n_cols, int col, const int32_t* drows, int64_t n,
+                       double* out, void* stream);
+/* out[i] = position of keys[i] in the ascending array sorted[n_sorted] (binary search), -1 if
+ * absent: maps an error cell's row to its dirty-tile row. */
+int dr_lookup_sorted(dr_ctx* ctx, const int32_t* sorted, int64_t n_sorted, const int32_t* keys, int64_t n,
+                     int32_t* out, void* stream);
+
+/* ---- a13: repair-model inference ---------------------------------------------------------------
+ * Replaces the `repair` pandas UDF (model.py:1095-1135): transformer.transform + model.predict
+ * + fill-NULL-only, for ONE target attribute over the dirty-row tile, in place.
+ *
+ * Forest (device arrays, caller-owned; layout in DESIGN.md "flat forest"):
+ *   n_seq sequences (1 = regression or binary, C = multiclass), trees grouped by sequence:
+ *   seq_tree_off int32[n_seq+1]; tree_node_off int32[n_trees+1];
+ *   node_thr double[n_nodes] (threshold, or leaf value on leaves); node_meta uint32[n_nodes]:
+ *     bits 0..11  feature index, 0xFFF = leaf
+ *     bit  12     NaN goes left
+ *     bits 13..21 left child, bits 22..30 right child (node index relative to the tree root)
+ *   baseline double[n_seq].
+ * Features: encoded feature f of a row = enc_lut[f][ tile[row][feat_col[f]] + 1 ] when
+ *   feat_col[f] >= 0 refers to a discrete tile column (enc_lut_off int32[n_feat+1] into the
+ *   double LUT; entry 0 = NULL), or ctile[row][-feat_col[f]-1] for continuous columns
+ *   (passthrough, NaN = NULL).
+ * Margin of sequence s = baseline[s] + sum of its trees' leaves in tree order (sequential float64
+ * adds: bit-identical to the oracle).  Output per cell i (tile row cells[i]):
+ *   kind 0 (classifier)  code = class_code[argmax_s margin] (binary: margin > 0 ? class 1 : 0),
+ *                        ties -> lowest s; written to tile[row][target_col]
+ *   kind 1 (regressor)   value (rounded half-to-even like numpy.round when `integral`) written
+ *                        to ctile[row][target_ccol]
+ * out_margin (optional, device double[n_cells * n_seq]) receives the margins (pmf modes). */
+typedef struct dr_forest {
+    int32_t n_seq, n_trees, n_nodes, n_feat;
+    const int32_t* seq_tree_off;
+    const int32_t* tree_node_off;
+    const double* node_thr;
+    const uint32_t* node_meta;
+    const double* baseline;
+    const int32_t* feat_col;
+    const int32_t* enc_lut_off;
+    const double* enc_lut;
+    const int32_t* class_code; /* int32[n_classes], kind 0 only */
+    int32_t kind, integral, n_classes;
+} dr_forest;
+int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n_cols, double* ctile, int n_ccols,
+                      const int32_t* cells, int64_t n_cells, int target_col, double* out_margin, void* stream);
+/* PoorModel (model.py:44-61): constant fill of the listed tile rows. */
+int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int32_t* cells, int64_t n_cells,
+                     int32_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REPAIR_H */

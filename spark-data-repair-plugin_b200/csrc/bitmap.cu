@@ -1,0 +1,459 @@
+// Cell-set plumbing: bitmap algebra, ordered compaction (bitmap -> ascending row list), masked
+// row gathers into the row-major dirty tile, cell gathers and sorted lookup.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 8;
+
+__global__ void __launch_bounds__(kThreads) k_bitmap_or(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                                        int64_t n_words, int andnot) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride)
+        dst[i] = andnot ? (dst[i] & ~src[i]) : (dst[i] | src[i]);
+}
+
+__device__ __forceinline__ uint32_t tail_mask(int64_t word, int64_t n_rows) {
+    const int64_t first = word << 5;
+    if (first + 32 <= n_rows) return 0xffffffffu;
+    if (first >= n_rows) return 0u;
+    return (1u << (int)(n_rows - first)) - 1u;
+}
+
+// ---- ordered compaction -------------------------------------------------------------------------
+constexpr int kWordsPerBlock = 1024;  // 32 Ki rows per block
+
+__global__ void __launch_bounds__(kThreads) k_block_popc(const uint32_t* __restrict__ bm, int64_t n_rows,
+                                                         int64_t n_words, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int warp_sum[kThreads / 32];
+    const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock;
+    unsigned int c = 0;
+    for (int i = threadIdx.x; i < kWordsPerBlock; i += kThreads) {
+        const int64_t w = w0 + i;
+        if (w < n_words) c += __popc(bm[w] & tail_mask(w, n_rows));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int i = 0; i < kThreads / 32; ++i) t += warp_sum[i];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the per-block counts, one CTA; counts[n_blocks] receives the total
+__global__ void __launch_bounds__(1024) k_scan_counts(unsigned long long* __restrict__ counts, int n_blocks) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? counts[i] : 0ull;
+        unsigned long long x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            warp_tot[lane] = t;  // inclusive
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (warp ? warp_tot[warp - 1] : 0ull) + (x - v);
+        if (i < n_blocks) counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[n_blocks] = carry;
+}
+
+__global__ void __launch_bounds__(kThreads) k_write_rows(const uint32_t* __restrict__ bm, int64_t n_rows,
+                                                         int64_t n_words,
+                                                         const unsigned long long* __restrict__ offsets,
+                                                         int32_t* __restrict__ out, int64_t capacity) {
+    __shared__ unsigned int warp_sum[kThreads / 32];
+    __shared__ unsigned long long block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) block_base = offsets[blockIdx.x];
+    __syncthreads();
+    const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock;
+    for (int step = 0; step < kWordsPerBlock; step += kThreads) {
+        const int64_t w = w0 + step + threadIdx.x;
+        uint32_t bits = w < n_words ? (bm[w] & tail_mask(w, n_rows)) : 0u;
+        const unsigned int c = __popc(bits);
+        unsigned int x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        unsigned int before = x - c;
+        unsigned int total = 0;
+        for (int i = 0; i < kThreads / 32; ++i) {
+            if (i < warp) before += warp_sum[i];
+            total += warp_sum[i];
+        }
+        unsigned long long pos = block_base + before;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if ((int64_t)pos < capacity) out[pos] = (int32_t)((w << 5) + b);
+            ++pos;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) block_base += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bitmap_gather(const uint32_t* __restrict__ src,
+                                                            const int32_t* __restrict__ rows, int64_t n,
+                                                            uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool bit = false;
+        if (i < n) {
+            const int r = rows[i];
+            bit = (__ldg(src + (r >> 5)) >> (r & 31)) & 1u;
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) out[i >> 5] = w;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bitmap_clear_rows(uint32_t* __restrict__ bm,
+                                                                const int32_t* __restrict__ rows,
+                                                                const uint8_t* __restrict__ flags, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!flags[i]) continue;
+        const int r = rows[i];
+        atomicAnd(bm + (r >> 5), ~(1u << (r & 31)));  // several cleared rows may share a word
+    }
+}
+
+// ---- masked row gather into the row-major tile ---------------------------------------------------
+struct GatherParams {
+    const void* cols[DR_MAX_COLS];
+    const uint32_t* bitmaps[DR_MAX_COLS];
+    int n_cols;
+};
+
+// A warp gathers 32 rows: lane = row while reading (each column read is a 32-row gather from one
+// column array), then the 32 x K tile is written out contiguously (coalesced) through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_gather_rows_masked(const __grid_constant__ GatherParams p,
+                                                                 const int32_t* __restrict__ rows, int64_t n,
+                                                                 T* __restrict__ out, T null_value) {
+    extern __shared__ unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    const int K = p.n_cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* my = tile + (size_t)warp * 32 * (K + 1);
+    const int64_t n_groups = (n + 31) >> 5;
+    for (int64_t grp = (int64_t)blockIdx.x * (kThreads / 32) + warp; grp < n_groups;
+         grp += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t i = (grp << 5) + lane;
+        const int r = i < n ? rows[i] : -1;
+        for (int c = 0; c < K; ++c) {
+            T v = null_value;
+            if (r >= 0) {
+                const uint32_t* bm = p.bitmaps[c];
+                const bool masked = bm != nullptr && ((__ldg(bm + (r >> 5)) >> (r & 31)) & 1u);
+                if (!masked) v = reinterpret_cast<const T*>(p.cols[c])[r];
+            }
+            my[lane * (K + 1) + c] = v;
+        }
+        __syncwarp();
+        const int64_t first = grp << 5;
+        const int64_t cnt = (n - first < 32 ? n - first : 32) * K;
+        for (int64_t j = lane; j < cnt; j += 32) out[first * K + j] = my[(j / K) * (K + 1) + (j % K)];
+        __syncwarp();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_tile_null_bitmap(const T* __restrict__ tile, int64_t n, int K,
+                                                               int col, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool bit = false;
+        if (i < n) {
+            const T v = tile[i * K + col];
+            if constexpr (sizeof(T) == 8) bit = v != v; else bit = v < 0;
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) out[i >> 5] = w;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_gather(const T* __restrict__ col, const int32_t* __restrict__ rows,
+                                                     int64_t n, int64_t row_stride, int64_t col_off,
+                                                     T* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = col[(int64_t)rows[i] * row_stride + col_off];
+}
+
+__global__ void __launch_bounds__(kThreads) k_lookup_sorted(const int32_t* __restrict__ sorted, int64_t n_sorted,
+                                                            const int32_t* __restrict__ keys, int64_t n,
+                                                            int32_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int key = keys[i];
+        int64_t lo = 0, hi = n_sorted;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(sorted + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        out[i] = (lo < n_sorted && __ldg(sorted + lo) == key) ? (int32_t)lo : -1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_tile_fill(int32_t* __restrict__ tile, int K, int col,
+                                                        const int32_t* __restrict__ cells, int64_t n, int32_t value) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        tile[(int64_t)cells[i] * K + col] = value;
+}
+
+inline int grid_rows(const dr_ctx* ctx, int64_t n) { return dr_grid_for(ctx, n, kThreads, kCtasPerSm); }
+
+}  // namespace
+
+extern "C" {
+
+int dr_bitmap_or(dr_ctx* ctx, uint32_t* dst, const uint32_t* src, int64_t n_rows, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, dst && src, "null pointer");
+    const int64_t n_words = (n_rows + 31) >> 5;
+    if (n_words <= 0) return DR_OK;
+    k_bitmap_or<<<grid_rows(ctx, n_words), kThreads, 0, (cudaStream_t)stream>>>(dst, src, n_words, 0);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_bitmap_andnot(dr_ctx* ctx, uint32_t* dst, const uint32_t* src, int64_t n_rows, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, dst && src, "null pointer");
+    const int64_t n_words = (n_rows + 31) >> 5;
+    if (n_words <= 0) return DR_OK;
+    k_bitmap_or<<<grid_rows(ctx, n_words), kThreads, 0, (cudaStream_t)stream>>>(dst, src, n_words, 1);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+static int compaction_counts(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int* n_blocks_out,
+                             cudaStream_t st) {
+    const int64_t n_words = (n_rows + 31) >> 5;
+    const int64_t n_blocks = (n_words + kWordsPerBlock - 1) / kWordsPerBlock;
+    DR_REQUIRE(ctx, n_blocks < (1 << 30), "bitmap too large");
+    int rc = dr_ensure_scratch(ctx, sizeof(unsigned long long) * (size_t)(n_blocks + 1));
+    if (rc) return rc;
+    unsigned long long* counts = (unsigned long long*)ctx->scratch;
+    k_block_popc<<<(int)n_blocks, kThreads, 0, st>>>(bitmap, n_rows, n_words, counts);
+    DR_LAUNCHED(ctx);
+    k_scan_counts<<<1, 1024, 0, st>>>(counts, (int)n_blocks);
+    DR_LAUNCHED(ctx);
+    *n_blocks_out = (int)n_blocks;
+    return DR_OK;
+}
+
+int dr_bitmap_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int64_t* out_count, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, bitmap && out_count, "null pointer");
+    *out_count = 0;
+    if (n_rows <= 0) return DR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_blocks = 0;
+    int rc = compaction_counts(ctx, bitmap, n_rows, &n_blocks, st);
+    if (rc) return rc;
+    unsigned long long* counts = (unsigned long long*)ctx->scratch;
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, counts + n_blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 st));
+    DR_CUDA(ctx, cudaStreamSynchronize(st));
+    *out_count = (int64_t) * (unsigned long long*)ctx->pinned;
+    return DR_OK;
+}
+
+int dr_bitmap_to_rows(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t capacity,
+                      int64_t* out_count, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, bitmap && out_count && (out_rows || capacity == 0), "null pointer");
+    *out_count = 0;
+    if (n_rows <= 0) return DR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_blocks = 0;
+    int rc = compaction_counts(ctx, bitmap, n_rows, &n_blocks, st);
+    if (rc) return rc;
+    unsigned long long* counts = (unsigned long long*)ctx->scratch;
+    const int64_t n_words = (n_rows + 31) >> 5;
+    if (capacity > 0) {
+        k_write_rows<<<n_blocks, kThreads, 0, st>>>(bitmap, n_rows, n_words, counts, out_rows, capacity);
+        DR_LAUNCHED(ctx);
+    }
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, counts + n_blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 st));
+    DR_CUDA(ctx, cudaStreamSynchronize(st));
+    *out_count = (int64_t) * (unsigned long long*)ctx->pinned;
+    if (*out_count > capacity) return dr_fail(ctx, DR_ERR_INVALID, "dr_bitmap_to_rows: capacity too small");
+    return DR_OK;
+}
+
+int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int64_t n, uint32_t* out,
+                     void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, src && rows && out, "null pointer");
+    k_bitmap_gather<<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(src, rows, n, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,
+                         void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, bitmap && rows && flags, "null pointer");
+    k_bitmap_clear_rows<<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(bitmap, rows, flags, n);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int gather_rows_masked(dr_ctx* ctx, const T* const* cols, uint32_t* const* bitmaps, int n_cols,
+                              const int32_t* rows, int64_t n, T* out, T null_value, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0 || n_cols == 0) return DR_OK;
+    DR_REQUIRE(ctx, cols && rows && out, "null pointer");
+    DR_REQUIRE(ctx, n_cols >= 1 && n_cols <= DR_MAX_COLS, "n_cols must be in [1, 64]");
+    GatherParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_cols = n_cols;
+    for (int c = 0; c < n_cols; ++c) {
+        DR_REQUIRE(ctx, cols[c] != nullptr, "null column pointer");
+        p.cols[c] = cols[c];
+        p.bitmaps[c] = bitmaps ? bitmaps[c] : nullptr;
+    }
+    const size_t smem = (size_t)(kThreads / 32) * 32 * (n_cols + 1) * sizeof(T);
+    DR_CUDA(ctx, cudaFuncSetAttribute(k_gather_rows_masked<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    const int grid = dr_grid_for(ctx, (n + 31) / 32, kThreads / 32, 2);
+    k_gather_rows_masked<T><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p, rows, n, out, null_value);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+extern "C" {
+
+int dr_gather_rows_masked(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
+                          const int32_t* rows, int64_t n, int32_t* out, void* stream) {
+    return gather_rows_masked<int32_t>(ctx, cols, bitmaps, n_cols, rows, n, out, -1, stream);
+}
+
+int dr_gather_rows_masked_f64(dr_ctx* ctx, const double* const* cols, uint32_t* const* bitmaps, int n_cols,
+                              const int32_t* rows, int64_t n, double* out, void* stream) {
+    return gather_rows_masked<double>(ctx, cols, bitmaps, n_cols, rows, n, out, (double)NAN, stream);
+}
+
+int dr_tile_null_bitmap(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols, int col, uint32_t* out,
+                        void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && out && col >= 0 && col < n_cols, "bad tile column");
+    k_tile_null_bitmap<int32_t><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(tile, n, n_cols, col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_null_bitmap_f64(dr_ctx* ctx, const double* tile, int64_t n, int n_cols, int col, uint32_t* out,
+                            void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && out && col >= 0 && col < n_cols, "bad tile column");
+    k_tile_null_bitmap<double><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(tile, n, n_cols, col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_gather_i32(dr_ctx* ctx, const int32_t* col, const int32_t* rows, int64_t n, int32_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, col && rows && out, "null pointer");
+    k_gather<int32_t><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(col, rows, n, 1, 0, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_gather_f64(dr_ctx* ctx, const double* col, const int32_t* rows, int64_t n, double* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, col && rows && out, "null pointer");
+    k_gather<double><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(col, rows, n, 1, 0, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_gather_i32(dr_ctx* ctx, const int32_t* tile, int n_cols, int col, const int32_t* drows, int64_t n,
+                       int32_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && drows && out && col >= 0 && col < n_cols, "bad tile column");
+    k_gather<int32_t><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(tile, drows, n, n_cols, col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_gather_f64(dr_ctx* ctx, const double* tile, int n_cols, int col, const int32_t* drows, int64_t n,
+                       double* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && drows && out && col >= 0 && col < n_cols, "bad tile column");
+    k_gather<double><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(tile, drows, n, n_cols, col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_lookup_sorted(dr_ctx* ctx, const int32_t* sorted, int64_t n_sorted, const int32_t* keys, int64_t n,
+                     int32_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, (sorted || n_sorted == 0) && keys && out, "null pointer");
+    k_lookup_sorted<<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(sorted, n_sorted, keys, n, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int32_t* cells, int64_t n_cells,
+                     int32_t value, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n_cells <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && cells && col >= 0 && col < n_cols, "bad tile column");
+    k_tile_fill<<<grid_rows(ctx, n_cells), kThreads, 0, (cudaStream_t)stream>>>(tile, n_cols, col, cells, n_cells,
+                                                                               value);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// Detector scans other than the NULL scan: LUT (regex / domain values), IQR range, exact
+// quartiles, denial constraints, discretisation.  All are single streaming passes over 1..m
+// columns (HBM-bound, 4 or 8 bytes per row and column in, 1 bit per row out).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 8;
+
+// Evaluate `pred(row)` for every row and OR the resulting bits into `bm`.  Each 32-row word is
+// produced by exactly one warp (ballot), so the read-modify-write needs no atomics.
+template <class Pred>
+__device__ __forceinline__ void rows_to_bitmap(int64_t n_rows, uint32_t* __restrict__ bm, Pred pred) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n_rows + 31) & ~(int64_t)31;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+        const bool bit = r < n_rows ? pred(r) : false;
+        const unsigned w = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0 && w != 0) bm[r >> 5] |= w;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_lut_scan(const int32_t* __restrict__ col, int64_t n_rows,
+                                                       const uint8_t* __restrict__ lut, int dict_size,
+                                                       uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        const int c = __ldcs(col + r);
+        return c < 0 || (c < dict_size && __ldg(lut + c) != 0);
+    });
+}
+
+__global__ void __launch_bounds__(kThreads) k_range_flag(const double* __restrict__ col, int64_t n_rows,
+                                                         double lower, double upper, uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        const double v = __ldcs(col + r);
+        return v < lower || v > upper;  // NaN compares false: NULLs are never outliers
+    });
+}
+
+struct ConstParams {
+    const int32_t* cols[DR_MAX_COLS];
+    int32_t ops[DR_MAX_COLS];
+    int32_t args[DR_MAX_COLS];
+    int n_preds;
+};
+
+__global__ void __launch_bounds__(kThreads) k_dc_const(const __grid_constant__ ConstParams p, int64_t n_rows,
+                                                       uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        bool ok = true;
+        for (int i = 0; i < p.n_preds && ok; ++i) {
+            const int c = __ldcs(p.cols[i] + r);
+            const int a = p.args[i];
+            switch (p.ops[i]) {
+                case DR_OP_EQ: ok = c == a; break;
+                case DR_OP_IQ: ok = c != a; break;
+                case DR_OP_LT: ok = c >= 0 && c < a; break;
+                default: ok = c >= 0 && c >= a; break;
+            }
+        }
+        return ok;
+    });
+}
+
+struct KeyParams {
+    const int32_t* cols[DR_MAX_COLS];
+    int64_t strides[DR_MAX_COLS];
+    int n_keys;
+};
+
+__device__ __forceinline__ int64_t row_key(const KeyParams& k, int64_t r) {
+    int64_t key = 0;
+    for (int i = 0; i < k.n_keys; ++i) key += (int64_t)(__ldcs(k.cols[i] + r) + 1) * k.strides[i];
+    return key;
+}
+
+// min / max of (b + 1) per NULL-safe key.  The tables are read first through L2 (ld.cg) so that the
+// common case -- the value is already inside [lo, hi] -- costs no atomic at all.
+__global__ void __launch_bounds__(kThreads) k_dc_fd_build(const __grid_constant__ KeyParams k,
+                                                          const int32_t* __restrict__ b_col, int64_t n_rows,
+                                                          int64_t key_space, int32_t* lo, int32_t* hi) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const int64_t key = row_key(k, r);
+        if (key < 0 || key >= key_space) continue;
+        const int v = __ldcs(b_col + r) + 1;
+        if (v < __ldcg(lo + key)) atomicMin(lo + key, v);
+        if (v > __ldcg(hi + key)) atomicMax(hi + key, v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_dc_fd_flag(const __grid_constant__ KeyParams k, int64_t n_rows,
+                                                         int64_t key_space, const int32_t* __restrict__ lo,
+                                                         const int32_t* __restrict__ hi, uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        const int64_t key = row_key(k, r);
+        if (key < 0 || key >= key_space) return false;
+        return __ldg(lo + key) != __ldg(hi + key);
+    });
+}
+
+__global__ void __launch_bounds__(kThreads) k_discretize(const double* __restrict__ vals, int64_t n_rows,
+                                                         double vmin, double denom, int thres,
+                                                         int32_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const double v = __ldcs(vals + r);
+        int o = -1;
+        if (v == v && denom != 0.0) {
+            // (v - min) / (max - min) * thres, evaluated in this order in IEEE double, then int()
+            const double q = __dmul_rn(__ddiv_rn(__dsub_rn(v, vmin), denom), (double)thres);
+            o = (int)trunc(q);
+        }
+        out[r] = o;
+    }
+}
+
+// ---- exact quartiles: MSD radix select over order-preserving 64-bit keys ----------------------
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+constexpr int kDigitBits = 11;
+constexpr int kBuckets = 1 << kDigitBits;
+constexpr int kMaxStates = 4;
+
+struct SelectParams {
+    unsigned long long prefix[kMaxStates];
+    unsigned long long mask;  // bits already fixed
+    int shift;                // position of the digit examined in this pass
+    int digit_mask;
+    int n_states;
+};
+
+__global__ void __launch_bounds__(kThreads) k_radix_hist(const double* __restrict__ col, int64_t n_rows,
+                                                         const __grid_constant__ SelectParams p,
+                                                         unsigned long long* __restrict__ out) {
+    __shared__ unsigned int h[kMaxStates * kBuckets];
+    for (int i = threadIdx.x; i < p.n_states * kBuckets; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const double v = __ldcs(col + r);
+        if (v != v) continue;
+        const double vz = v == 0.0 ? 0.0 : v;  // -0.0 and 0.0 are one value
+        const unsigned long long key = f64_key(vz);
+        const int d = (int)((key >> p.shift) & (unsigned long long)p.digit_mask);
+        for (int s = 0; s < p.n_states; ++s)
+            if ((key & p.mask) == p.prefix[s]) atomicAdd(&h[s * kBuckets + d], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_states * kBuckets; i += blockDim.x)
+        if (h[i]) atomicAdd(out + i, (unsigned long long)h[i]);
+}
+
+double key_to_f64(unsigned long long k) {
+    unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    memcpy(&d, &u, sizeof(d));
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dr_lut_scan(dr_ctx* ctx, const int32_t* col, int64_t n_rows, const uint8_t* lut, int32_t dict_size,
+                uint32_t* bitmap, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, col && bitmap && (lut || dict_size == 0), "null pointer");
+    if (n_rows <= 0) return DR_OK;
+    k_lut_scan<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        col, n_rows, lut, dict_size, bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_range_flag(dr_ctx* ctx, const double* col, int64_t n_rows, double lower, double upper, uint32_t* bitmap,
+                  void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, col && bitmap, "null pointer");
+    if (n_rows <= 0) return DR_OK;
+    k_range_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        col, n_rows, lower, upper, bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_dc_const(dr_ctx* ctx, const int32_t* const* cols, const int32_t* ops, const int32_t* args, int n_preds,
+                int64_t n_rows, uint32_t* row_bitmap, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, cols && ops && args && row_bitmap, "null pointer");
+    DR_REQUIRE(ctx, n_preds >= 1 && n_preds <= DR_MAX_COLS, "n_preds must be in [1, 64]");
+    if (n_rows <= 0) return DR_OK;
+    ConstParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_preds = n_preds;
+    for (int i = 0; i < n_preds; ++i) {
+        DR_REQUIRE(ctx, cols[i] != nullptr, "null column pointer");
+        DR_REQUIRE(ctx, ops[i] >= DR_OP_EQ && ops[i] <= DR_OP_GT, "unknown predicate op");
+        p.cols[i] = cols[i];
+        p.ops[i] = ops[i];
+        p.args[i] = args[i];
+    }
+    k_dc_const<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(p, n_rows,
+                                                                                                      row_bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+static int fill_keys(dr_ctx* ctx, KeyParams* k, const int32_t* const* key_cols, const int64_t* strides,
+                     int n_keys) {
+    DR_REQUIRE(ctx, key_cols && strides, "null pointer");
+    DR_REQUIRE(ctx, n_keys >= 1 && n_keys <= DR_MAX_COLS, "n_keys must be in [1, 64]");
+    memset(k, 0, sizeof(*k));
+    k->n_keys = n_keys;
+    for (int i = 0; i < n_keys; ++i) {
+        DR_REQUIRE(ctx, key_cols[i] != nullptr, "null key column");
+        k->cols[i] = key_cols[i];
+        k->strides[i] = strides[i];
+    }
+    return DR_OK;
+}
+
+int dr_dc_fd_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                   const int32_t* b_col, int64_t n_rows, int64_t key_space, int32_t* lo, int32_t* hi,
+                   void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, b_col && lo && hi && key_space > 0, "null pointer / empty key space");
+    KeyParams k;
+    int rc = fill_keys(ctx, &k, key_cols, strides, n_keys);
+    if (rc) return rc;
+    if (n_rows <= 0) return DR_OK;
+    k_dc_fd_build<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        k, b_col, n_rows, key_space, lo, hi);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                  int64_t n_rows, int64_t key_space, const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap,
+                  void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, lo && hi && row_bitmap && key_space > 0, "null pointer / empty key space");
+    KeyParams k;
+    int rc = fill_keys(ctx, &k, key_cols, strides, n_keys);
+    if (rc) return rc;
+    if (n_rows <= 0) return DR_OK;
+    k_dc_fd_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        k, n_rows, key_space, lo, hi, row_bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_discretize(dr_ctx* ctx, const double* vals, int64_t n_rows, double vmin, double denom, int32_t thres,
+                  int32_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, vals && out, "null pointer");
+    if (n_rows <= 0) return DR_OK;
+    k_discretize<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        vals, n_rows, vmin, denom, thres, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+// Exact Spark `percentile` at 0.25 / 0.75: needs the order statistics floor(p(n-1)) and ceil(p(n-1)).
+// Six histogram passes (11+11+11+11+10+10 bits) narrow up to four prefixes at once.
+int dr_quartiles(dr_ctx* ctx, const double* col, int64_t n_rows, double* out_q, int64_t* out_n, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, col && out_q && out_n, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    out_q[0] = out_q[1] = NAN;
+    *out_n = 0;
+    if (n_rows <= 0) return DR_OK;
+    int rc = dr_ensure_scratch(ctx, sizeof(unsigned long long) * kMaxStates * kBuckets);
+    if (rc) return rc;
+    unsigned long long* d_hist = (unsigned long long*)ctx->scratch;
+    static thread_local unsigned long long h_hist[kMaxStates * kBuckets];
+    const int grid = dr_grid_for(ctx, n_rows, kThreads, 4);
+
+    // state = (prefix, remaining rank); several target ranks may share a state
+    unsigned long long prefix[kMaxStates] = {0, 0, 0, 0};
+    int64_t rank[kMaxStates] = {0, 0, 0, 0};  // rank inside the state's prefix bucket
+    int state_of[4] = {0, 0, 0, 0};
+    int n_states = 1;
+    int64_t n = -1;
+    double pos[2];
+    int64_t want[4];
+    unsigned long long mask = 0;
+    const int widths[6] = {11, 11, 11, 11, 10, 10};
+    int shift = 64;
+    for (int pass = 0; pass < 6; ++pass) {
+        shift -= widths[pass];
+        SelectParams p;
+        memset(&p, 0, sizeof(p));
+        p.mask = mask;
+        p.shift = shift;
+        p.digit_mask = (1 << widths[pass]) - 1;
+        p.n_states = n_states;
+        for (int s = 0; s < n_states; ++s) p.prefix[s] = prefix[s];
+        DR_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * n_states * kBuckets, st));
+        k_radix_hist<<<grid, kThreads, 0, st>>>(col, n_rows, p, d_hist);
+        DR_LAUNCHED(ctx);
+        DR_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * n_states * kBuckets,
+                                     cudaMemcpyDeviceToHost, st));
+        DR_CUDA(ctx, cudaStreamSynchronize(st));
+        if (pass == 0) {
+            n = 0;
+            for (int b = 0; b < kBuckets; ++b) n += (int64_t)h_hist[b];
+            *out_n = n;
+            if (n == 0) return DR_OK;
+            pos[0] = (double)(n - 1) * 0.25;
+            pos[1] = (double)(n - 1) * 0.75;
+            want[0] = (int64_t)floor(pos[0]);
+            want[1] = (int64_t)ceil(pos[0]);
+            want[2] = (int64_t)floor(pos[1]);
+            want[3] = (int64_t)ceil(pos[1]);
+        }
+        // advance every target rank into its digit bucket, then rebuild the distinct states
+        unsigned long long new_prefix[4];
+        int64_t new_rank[4];
+        for (int t = 0; t < 4; ++t) {
+            const int s = state_of[t];
+            int64_t k = pass == 0 ? want[t] : rank[t];
+            const unsigned long long* hh = h_hist + (size_t)s * kBuckets;
+            int b = 0;
+            for (; b < (1 << widths[pass]); ++b) {
+                if (k < (int64_t)hh[b]) break;
+                k -= (int64_t)hh[b];
+            }
+            if (b == (1 << widths[pass])) return dr_fail(ctx, DR_ERR_CUDA, "radix select lost its rank");
+            new_prefix[t] = prefix[s] | ((unsigned long long)b << shift);
+            new_rank[t] = k;
+        }
+        mask |= ((unsigned long long)p.digit_mask) << shift;
+        // rebuild the distinct states (several ranks may share a prefix)
+        unsigned long long uniq[4];
+        int nu = 0;
+        for (int t = 0; t < 4; ++t) {
+            int s = 0;
+            for (; s < nu; ++s)
+                if (uniq[s] == new_prefix[t]) break;
+            if (s == nu) uniq[nu++] = new_prefix[t];
+            state_of[t] = s;
+            rank[t] = new_rank[t];
+        }
+        for (int s = 0; s < nu; ++s) prefix[s] = uniq[s];
+        n_states = nu;
+    }
+    double v[4];
+    for (int t = 0; t < 4; ++t) v[t] = key_to_f64(prefix[state_of[t]]);
+    for (int q = 0; q < 2; ++q) {
+        const double lo = floor(pos[q]), hi = ceil(pos[q]);
+        // (higher - position) * v[lower] + (position - lower) * v[higher]
+        out_q[q] = lo == hi ? v[2 * q] : (hi - pos[q]) * v[2 * q] + (pos[q] - lo) * v[2 * q + 1];
+    }
+    return DR_OK;
+}
+
+}  // extern "C"

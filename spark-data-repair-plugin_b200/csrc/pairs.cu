@@ -1,0 +1,190 @@
+// Attribute-pair statistics: distinct-pair presence bits and exact
+// co-occurrence counts.  Both stage a 256-row tile of the referenced columns in shared memory as
+// 16-bit slots (code + 1), then every thread walks the pair list for its row.
+//   presence: test-then-atomicOr on a bit table (after the first few tiles nearly every test hits)
+//   counts:   shared-memory int32 atomics per (CTA, table), flushed to global int64 at the end
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 256;
+
+struct PairParams {
+    const int32_t* cols[DR_MAX_COLS];
+    int32_t dom[DR_MAX_COLS];
+    int32_t used[DR_MAX_COLS];  // columns referenced by this launch's pairs (staged in this order)
+    int n_used;
+    const int32_t* px;  // device, indices into `used` order
+    const int32_t* py;
+    const int32_t* off;  // device int32[n_pairs + 1], word/entry offsets relative to the launch
+    int n_pairs;
+    int64_t n_rows;
+    int64_t block_rows;
+    int64_t n_blocks;
+};
+
+__device__ __forceinline__ int64_t block_start(const PairParams& p, int64_t j) {
+    if (p.block_rows * p.n_blocks >= p.n_rows || p.n_blocks <= 1) return j * p.block_rows;
+    return (j * (p.n_rows - p.block_rows)) / (p.n_blocks - 1);
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ PairParams p, int table_words,
+                                                    void* __restrict__ out_raw) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* tab = smem;                                                   // table_words
+    uint16_t* codes = reinterpret_cast<uint16_t*>(smem + table_words);      // n_used * kTile
+    for (int i = threadIdx.x; i < table_words; i += kThreads) tab[i] = 0;
+    __syncthreads();
+    const int64_t units_per_block = (p.block_rows + kTile - 1) / kTile;
+    const int64_t n_units = units_per_block * p.n_blocks;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int64_t j = u / units_per_block, k = u % units_per_block;
+        const int64_t first = block_start(p, j) + k * kTile;
+        int64_t last = block_start(p, j) + p.block_rows;
+        if (last > p.n_rows) last = p.n_rows;
+        const int64_t r = first + threadIdx.x;
+        const bool live = r < last;
+        for (int c = 0; c < p.n_used; ++c) {
+            const int col = p.used[c];
+            int s = 0;
+            if (live) {
+                const unsigned v = (unsigned)(__ldcs(p.cols[col] + r) + 1);
+                s = v > (unsigned)p.dom[col] ? p.dom[col] : (int)v;
+            }
+            codes[c * kTile + threadIdx.x] = (uint16_t)s;
+        }
+        // each thread only reads back its own column of `codes`: no barrier needed
+        if (live) {
+            for (int q = 0; q < p.n_pairs; ++q) {
+                const int x = __ldg(p.px + q), y = __ldg(p.py + q);
+                const int cx = codes[x * kTile + threadIdx.x], cy = codes[y * kTile + threadIdx.x];
+                const int idx = cx * (p.dom[p.used[y]] + 1) + cy;
+                const int base = __ldg(p.off + q);
+                if (kCount) {
+                    atomicAdd(&tab[base + idx], 1u);
+                } else {
+                    const uint32_t bit = 1u << (idx & 31);
+                    uint32_t* w = &tab[base + (idx >> 5)];
+                    if (!(*w & bit)) atomicOr(w, bit);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (kCount) {
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(out_raw);
+        for (int i = threadIdx.x; i < table_words; i += kThreads)
+            if (tab[i]) atomicAdd(out + i, (unsigned long long)tab[i]);
+    } else {
+        uint32_t* out = reinterpret_cast<uint32_t*>(out_raw);
+        for (int i = threadIdx.x; i < table_words; i += kThreads)
+            if (tab[i]) atomicOr(out + i, tab[i]);
+    }
+}
+
+// Launches k_pairs over consecutive pair ranges whose tables fit the shared-memory budget.
+template <bool kCount>
+int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+              const int32_t* py, int n_pairs, const int64_t* off, int64_t n_rows, int64_t block_rows,
+              int64_t n_blocks, void* out, cudaStream_t st) {
+    DR_REQUIRE(ctx, cols && dom && px && py && off && out, "null pointer");
+    DR_REQUIRE(ctx, n_cols >= 1 && n_cols <= DR_MAX_COLS, "n_cols must be in [1, 64]");
+    DR_REQUIRE(ctx, n_rows < (int64_t)INT32_MAX, "n_rows must be < 2^31 per shard");
+    if (n_pairs <= 0 || n_rows <= 0 || n_blocks <= 0 || block_rows <= 0) return DR_OK;
+    for (int q = 0; q < n_pairs; ++q) {
+        DR_REQUIRE(ctx, px[q] >= 0 && px[q] < n_cols && py[q] >= 0 && py[q] < n_cols && px[q] != py[q], "bad pair");
+        const int64_t need = kCount ? (int64_t)(dom[px[q]] + 1) * (dom[py[q]] + 1)
+                                    : ((int64_t)(dom[px[q]] + 1) * (dom[py[q]] + 1) + 31) / 32;
+        DR_REQUIRE(ctx, off[q + 1] - off[q] >= need, "pair table offsets too small");
+        DR_REQUIRE(ctx, dom[px[q]] < 65535 && dom[py[q]] < 65535, "domain too large for 16-bit staging");
+    }
+    // device copies of the per-launch pair lists live in the context scratch buffer
+    int rc = dr_ensure_scratch(ctx, sizeof(int32_t) * (size_t)(3 * n_pairs + 3) + 256);
+    if (rc) return rc;
+    static thread_local int32_t* h = nullptr;
+    static thread_local size_t h_cap = 0;
+    if (h_cap < (size_t)(3 * n_pairs + 3)) {
+        free(h);
+        h_cap = (size_t)(3 * n_pairs + 3);
+        h = (int32_t*)malloc(sizeof(int32_t) * h_cap);
+        if (!h) { h_cap = 0; return dr_fail(ctx, DR_ERR_INVALID, "out of host memory"); }
+    }
+    int q0 = 0;
+    while (q0 < n_pairs) {
+        PairParams p;
+        memset(&p, 0, sizeof(p));
+        int slot_of[DR_MAX_COLS];
+        for (int i = 0; i < n_cols; ++i) slot_of[i] = -1;
+        int q1 = q0;
+        int64_t words = 0;
+        while (q1 < n_pairs) {
+            const int extra = (slot_of[px[q1]] < 0) + (slot_of[py[q1]] < 0);
+            const int64_t words_after = off[q1 + 1] - off[q0];
+            const size_t bytes_after = (size_t)words_after * 4 + (size_t)(p.n_used + extra) * kTile * 2;
+            if (q1 > q0 && bytes_after > (size_t)200 * 1024) break;
+            if (slot_of[px[q1]] < 0) { slot_of[px[q1]] = p.n_used; p.used[p.n_used++] = px[q1]; }
+            if (slot_of[py[q1]] < 0) { slot_of[py[q1]] = p.n_used; p.used[p.n_used++] = py[q1]; }
+            words = words_after;
+            ++q1;
+        }
+        const size_t smem = (size_t)words * 4 + (size_t)p.n_used * kTile * 2;
+        if (smem > 220 * 1024)
+            return dr_fail(ctx, DR_ERR_UNSUPPORTED, "pair table of %lld words does not fit in shared memory",
+                           (long long)words);
+        const int np = q1 - q0;
+        for (int q = 0; q < np; ++q) {
+            h[q] = slot_of[px[q0 + q]];
+            h[np + q] = slot_of[py[q0 + q]];
+            h[2 * np + q] = (int32_t)(off[q0 + q] - off[q0]);
+        }
+        h[3 * np] = (int32_t)(off[q1] - off[q0]);
+        int32_t* d = (int32_t*)ctx->scratch;
+        // the scratch copy must be consumed before the next range overwrites it
+        DR_CUDA(ctx, cudaStreamSynchronize(st));
+        DR_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(int32_t) * (size_t)(3 * np + 1), cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < n_cols; ++i) { p.cols[i] = cols[i]; p.dom[i] = dom[i]; }
+        p.px = d;
+        p.py = d + np;
+        p.off = d + 2 * np;
+        p.n_pairs = np;
+        p.n_rows = n_rows;
+        p.block_rows = block_rows;
+        p.n_blocks = n_blocks;
+        DR_CUDA(ctx, cudaFuncSetAttribute(k_pairs<kCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t units = ((block_rows + kTile - 1) / kTile) * n_blocks;
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        int grid = ctx->sm_count * per_sm;
+        if ((int64_t)grid > units) grid = (int)units;
+        char* outp = (char*)out + (kCount ? sizeof(int64_t) : sizeof(uint32_t)) * (size_t)off[q0];
+        k_pairs<kCount><<<grid, kThreads, smem, st>>>(p, (int)words, outp);
+        DR_LAUNCHED(ctx);
+        DR_CUDA(ctx, cudaStreamSynchronize(st));  // h / scratch are reused by the next range
+        q0 = q1;
+    }
+    return DR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dr_pair_presence(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+                     const int32_t* py, int n_pairs, const int64_t* bit_off, int64_t n_rows, int64_t block_rows,
+                     int64_t n_blocks, uint32_t* bits, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    return run_pairs<false>(ctx, cols, dom, n_cols, px, py, n_pairs, bit_off, n_rows, block_rows, n_blocks, bits,
+                            (cudaStream_t)stream);
+}
+
+int dr_cooc(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+            const int32_t* py, int n_pairs, const int64_t* tab_off, int64_t n_rows, int64_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    const int64_t block_rows = 1 << 16;
+    const int64_t n_blocks = (n_rows + block_rows - 1) / block_rows;
+    return run_pairs<true>(ctx, cols, dom, n_cols, px, py, n_pairs, tab_off, n_rows, block_rows, n_blocks, out,
+                           (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// dr_scan_hist: NULL-cell scan fused with per-column histograms.
+//
+// One pass over the columns; HBM-bound: 4 bytes per cell in, 1 bit per cell out.
+//
+// Shared-memory atomics cost ~2 cycles per lane on this part, an order of magnitude more than
+// the HBM stream can afford at 32 columns.  The kernel therefore needs NO atomics in its hot loop:
+//   * every warp owns a disjoint subset of the columns of its CTA (column c -> warp c % 8), so
+//     bins are never shared between warps;
+//   * inside a warp every lane owns a private copy of each bin, laid out bin*32 + lane, i.e. lane
+//     L only ever touches shared-memory bank L: plain LDS/IADD/STS, conflict-free by construction.
+// A CTA holds sum(dom+1) * 128 bytes of bins; columns are packed into groups (gridDim.y) that fit
+// the shared-memory budget.  Each lane streams 4 consecutive rows per 128-bit load; the NULL bits
+// of 128 rows are assembled with three xor-shuffles and OR-ed into the column bitmap (each word is
+// owned by exactly one warp).  At the end the lane-private bins are reduced and added to the
+// global int64 histogram with one atomic per (CTA, bin).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTileRows = 128;             // rows per warp-wide 128-bit load
+constexpr int kTilesPerChunk = 8;          // independent loads in flight per lane and column
+constexpr int kChunkRows = kTileRows * kTilesPerChunk;
+
+struct ScanParams {
+    const int32_t* cols[DR_MAX_COLS];
+    uint32_t* bitmaps[DR_MAX_COLS];
+    int32_t dom[DR_MAX_COLS];
+    int32_t slot_off[DR_MAX_COLS];   // offset into the global histogram
+    int32_t local_off[DR_MAX_COLS];  // offset into the group's shared-memory bins
+    int32_t group_start[DR_MAX_COLS + 1];
+    int32_t group_slots[DR_MAX_COLS];
+    int64_t n_rows;
+    int64_t* hist;
+};
+
+__device__ __forceinline__ void count_one(int32_t* bins, int loc, int dom, int code, int lane) {
+    unsigned s = (unsigned)(code + 1);
+    s = s > (unsigned)dom ? (unsigned)dom : s;  // memory safety for out-of-range codes
+    bins[(loc + (int)s) * 32 + lane] += 1;
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_hist(const __grid_constant__ ScanParams p) {
+    extern __shared__ int32_t bins[];
+    const int g = blockIdx.y;
+    const int c_begin = p.group_start[g], c_end = p.group_start[g + 1];
+    const int n_slots = p.group_slots[g];
+    for (int i = threadIdx.x; i < n_slots * 32; i += kThreads) bins[i] = 0;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_rows = p.n_rows;
+    const int64_t n_chunks = (n_rows + kChunkRows - 1) / kChunkRows;
+
+    for (int c = c_begin + warp; c < c_end; c += kWarps) {
+        const int32_t* __restrict__ col = p.cols[c];
+        uint32_t* __restrict__ bm = p.bitmaps[c];
+        const int loc = p.local_off[c], dom = p.dom[c];
+        const bool vec_ok = ((uintptr_t)col & 15) == 0;
+        for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+            const int64_t base = chunk * kChunkRows;
+            int4 v[kTilesPerChunk];
+            if (vec_ok && base + kChunkRows <= n_rows) {
+#pragma unroll
+                for (int t = 0; t < kTilesPerChunk; ++t)
+                    v[t] = __ldcs(reinterpret_cast<const int4*>(col + base + t * kTileRows) + lane);
+            } else {
+#pragma unroll
+                for (int t = 0; t < kTilesPerChunk; ++t) {
+                    const int64_t r = base + t * kTileRows + lane * 4;
+                    // INT32_MIN marks "row does not exist": not counted, no bit
+                    v[t].x = r + 0 < n_rows ? col[r + 0] : INT32_MIN;
+                    v[t].y = r + 1 < n_rows ? col[r + 1] : INT32_MIN;
+                    v[t].z = r + 2 < n_rows ? col[r + 2] : INT32_MIN;
+                    v[t].w = r + 3 < n_rows ? col[r + 3] : INT32_MIN;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kTilesPerChunk; ++t) {
+                const int4 q = v[t];
+                unsigned nib = 0;
+                if (q.x != INT32_MIN) { count_one(bins, loc, dom, q.x, lane); nib |= (q.x < 0) << 0; }
+                if (q.y != INT32_MIN) { count_one(bins, loc, dom, q.y, lane); nib |= (q.y < 0) << 1; }
+                if (q.z != INT32_MIN) { count_one(bins, loc, dom, q.z, lane); nib |= (q.z < 0) << 2; }
+                if (q.w != INT32_MIN) { count_one(bins, loc, dom, q.w, lane); nib |= (q.w < 0) << 3; }
+                if (bm != nullptr) {
+                    unsigned w = nib << (4 * (lane & 7));
+                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                    if ((lane & 7) == 0 && w != 0) {
+                        const int64_t word = ((base + t * kTileRows) >> 5) + (lane >> 3);
+                        bm[word] |= w;  // this word belongs to this warp only
+                    }
+                }
+            }
+        }
+        // reduce the lane-private copies of this column's bins; lane L sums bin (s0 + L), reading
+        // the 32 copies in a rotated order so that the 32 lanes hit 32 different banks
+        __syncwarp();
+        for (int s0 = 0; s0 <= dom; s0 += 32) {
+            const int s = s0 + lane;
+            if (s <= dom) {
+                long long total = 0;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) total += bins[(loc + s) * 32 + ((j + lane) & 31)];
+                if (total != 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.hist + p.slot_off[c] + s),
+                              (unsigned long long)total);
+            }
+        }
+    }
+}
+
+// Fallback for domains too large for lane-private bins: global int64 atomics (low contention when
+// the domain is large) + the same bitmap logic, one thread per row.
+__global__ void k_scan_hist_global(const int32_t* __restrict__ col, uint32_t* __restrict__ bm, int dom,
+                                   int64_t n_rows, int64_t* __restrict__ hist) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n_rows + 31) & ~(int64_t)31;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+        bool is_null = false;
+        if (r < n_rows) {
+            const int code = col[r];
+            unsigned s = (unsigned)(code + 1);
+            s = s > (unsigned)dom ? (unsigned)dom : s;
+            atomicAdd(reinterpret_cast<unsigned long long*>(hist + s), 1ull);
+            is_null = code < 0;
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, is_null);
+        if (bm != nullptr && lane == 0 && w != 0) bm[r >> 5] |= w;
+    }
+}
+
+}  // namespace
+
+extern "C" int dr_scan_hist(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols,
+                            int64_t n_rows, uint32_t* const* bitmaps, int64_t* hist, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, cols && dom && hist, "null pointer");
+    DR_REQUIRE(ctx, n_cols >= 0 && n_cols <= DR_MAX_COLS, "n_cols must be in [0, 64]");
+    DR_REQUIRE(ctx, n_rows >= 0 && n_rows < (int64_t)INT32_MAX, "n_rows must be < 2^31 per shard");
+    if (n_cols == 0 || n_rows == 0) return DR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DR_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    constexpr int kBudgetSlots = 880;     // 880 * 128 B = 110 KB -> two CTAs per SM (2 * 111 KB <= 228 KB)
+    constexpr int kMaxGroupSlots = 1760;  // 220 KB, one CTA per SM
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_rows = n_rows;
+    p.hist = hist;
+    // columns small enough for lane-private bins; the rest take the global-atomic fallback
+    int total_slots = 0, n_small = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        DR_REQUIRE(ctx, dom[i] >= 0, "negative domain size");
+        DR_REQUIRE(ctx, cols[i] != nullptr, "null column pointer");
+        if (dom[i] + 1 <= kMaxGroupSlots) { total_slots += dom[i] + 1; ++n_small; }
+    }
+    // balanced packing: as few groups as the budget allows, about the same number of columns each
+    int want_groups = (total_slots + kBudgetSlots - 1) / kBudgetSlots;
+    if (want_groups < 1) want_groups = 1;
+    const int cols_per_group = (n_small + want_groups - 1) / want_groups;
+    int n_packed = 0, n_groups = 0, cur_slots = 0, cur_cols = 0, off = 0;
+    int max_group_slots = 0;
+    p.group_start[0] = 0;
+    for (int i = 0; i < n_cols; ++i) {
+        const int slots = dom[i] + 1;
+        if (slots > kMaxGroupSlots) {  // large-domain fallback, launched separately
+            const int threads = 256;
+            const int grid = dr_grid_for(ctx, n_rows, threads, 8);
+            k_scan_hist_global<<<grid, threads, 0, st>>>(cols[i], bitmaps ? bitmaps[i] : nullptr, dom[i], n_rows,
+                                                         hist + off);
+            DR_LAUNCHED(ctx);
+            off += slots;
+            continue;
+        }
+        const int limit = slots > kBudgetSlots ? kMaxGroupSlots : kBudgetSlots;
+        if (cur_cols > 0 && (cur_slots + slots > limit || cur_cols >= cols_per_group)) {
+            p.group_slots[n_groups] = cur_slots;
+            max_group_slots = cur_slots > max_group_slots ? cur_slots : max_group_slots;
+            p.group_start[++n_groups] = n_packed;
+            cur_slots = 0;
+            cur_cols = 0;
+        }
+        p.cols[n_packed] = cols[i];
+        p.bitmaps[n_packed] = bitmaps ? bitmaps[i] : nullptr;
+        p.dom[n_packed] = dom[i];
+        p.slot_off[n_packed] = off;
+        p.local_off[n_packed] = cur_slots;
+        cur_slots += slots;
+        ++cur_cols;
+        off += slots;
+        ++n_packed;
+    }
+    if (n_packed == 0) return DR_OK;
+    p.group_slots[n_groups] = cur_slots;
+    max_group_slots = cur_slots > max_group_slots ? cur_slots : max_group_slots;
+    p.group_start[++n_groups] = n_packed;
+
+    const size_t smem = (size_t)max_group_slots * 32 * sizeof(int32_t);
+    DR_CUDA(ctx, cudaFuncSetAttribute(k_scan_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int64_t n_chunks = (n_rows + kChunkRows - 1) / kChunkRows;
+    int grid_x = (ctx->sm_count * ctas_per_sm + n_groups - 1) / n_groups;
+    if ((int64_t)grid_x > n_chunks) grid_x = (int)n_chunks;
+    if (grid_x < 1) grid_x = 1;
+    dim3 grid(grid_x, n_groups);
+    k_scan_hist<<<grid, kThreads, smem, st>>>(p);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}

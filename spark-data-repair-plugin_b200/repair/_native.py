@@ -1,0 +1,268 @@
+"""ctypes binding of ``libb200repair.so`` (C ABI declared in ``include/b200repair.h``).
+
+This is the only door into the hand-written sm_100a kernels.  There is no CPU fallback: if the
+shared library is missing, or no CUDA device is usable, every engine entry point raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libb200repair.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+DR_OP = {"EQ": 0, "IQ": 1, "LT": 2, "GT": 3}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class dr_forest(ctypes.Structure):
+    _fields_ = [
+        ("n_seq", c_int32), ("n_trees", c_int32), ("n_nodes", c_int32), ("n_feat", c_int32),
+        ("seq_tree_off", c_void_p), ("tree_node_off", c_void_p), ("node_thr", c_void_p),
+        ("node_meta", c_void_p), ("baseline", c_void_p), ("feat_col", c_void_p),
+        ("enc_lut_off", c_void_p), ("enc_lut", c_void_p), ("class_code", c_void_p),
+        ("kind", c_int32), ("integral", c_int32), ("n_classes", c_int32),
+    ]
+
+
+_PP = POINTER(c_void_p)
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "dr_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "dr_ctx_destroy": (c_int, [c_void_p]),
+    "dr_last_error": (c_char_p, [c_void_p]),
+    "dr_abi_version": (c_int, []),
+    "dr_launch_count": (c_int64, [c_void_p]),
+    "dr_scan_hist": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, c_int64, _PP, c_void_p, c_void_p]),
+    "dr_lut_scan": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "dr_quartiles": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_int64), c_void_p]),
+    "dr_range_flag": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p]),
+    "dr_dc_const": (c_int, [c_void_p, _PP, POINTER(c_int32), POINTER(c_int32), c_int, c_int64, c_void_p, c_void_p]),
+    "dr_dc_fd_build": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_void_p, c_int64, c_int64, c_void_p,
+                               c_void_p, c_void_p]),
+    "dr_dc_fd_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
+    "dr_bitmap_or": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dr_bitmap_andnot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dr_bitmap_count": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
+    "dr_bitmap_to_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
+    "dr_bitmap_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_bitmap_clear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dr_discretize": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p, c_void_p]),
+    "dr_pair_presence": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, POINTER(c_int32), POINTER(c_int32), c_int,
+                                 POINTER(c_int64), c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "dr_cooc": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, POINTER(c_int32), POINTER(c_int32), c_int,
+                        POINTER(c_int64), c_int64, c_void_p, c_void_p]),
+    "dr_domain_score": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, _PP, POINTER(c_int32), _PP, c_int,
+                                c_void_p, POINTER(c_int64), c_int64, c_double, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "dr_gather_rows_masked": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_gather_rows_masked_f64": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_tile_null_bitmap": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "dr_tile_null_bitmap_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "dr_gather_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_tile_gather_i32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_tile_gather_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_lookup_sorted": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_forest_predict": (c_int, [c_void_p, POINTER(dr_forest), c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
+                                  c_int, c_void_p, c_void_p]),
+    "dr_tile_fill_i32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int32, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree shared library and bind every entry point; raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "{} not found next to {} -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)".format(LIB_NAME, __file__))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _ptr_array(ptrs):
+    arr = (c_void_p * max(len(ptrs), 1))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return ctypes.cast(arr, _PP), arr
+
+
+def _i32_array(vals):
+    return (c_int32 * max(len(vals), 1))(*[int(v) for v in vals])
+
+
+def _i64_array(vals):
+    return (c_int64 * max(len(vals), 1))(*[int(v) for v in vals])
+
+
+def _dp(t):
+    """device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+class Context:
+    """One ``dr_ctx`` (one GPU).  Methods take torch CUDA tensors purely as device-buffer carriers."""
+
+    def __init__(self, device_index):
+        import torch
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device is available; the repair engine has no CPU fallback")
+        self.lib = load_library()
+        self.device_index = int(device_index)
+        self._h = c_void_p()
+        rc = self.lib.dr_ctx_create(self.device_index, byref(self._h))
+        if rc != 0:
+            msg = self.lib.dr_last_error(self._h).decode() if self._h else "dr_ctx_create failed"
+            raise NativeError(msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError("libb200repair: " + self.lib.dr_last_error(self._h).decode())
+
+    @staticmethod
+    def _stream():
+        import torch
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.dr_launch_count(self._h))
+
+    # ---- detectors -------------------------------------------------------------------------------
+    def scan_hist(self, cols, dom, n_rows, bitmaps, hist):
+        cp, _k1 = _ptr_array([c.data_ptr() for c in cols])
+        bp, _k2 = _ptr_array([0 if b is None else b.data_ptr() for b in bitmaps])
+        self._check(self.lib.dr_scan_hist(self._h, cp, _i32_array(dom), len(cols), n_rows, bp, _dp(hist),
+                                          self._stream()))
+
+    def lut_scan(self, col, n_rows, lut, dict_size, bitmap):
+        self._check(self.lib.dr_lut_scan(self._h, _dp(col), n_rows, _dp(lut), dict_size, _dp(bitmap), self._stream()))
+
+    def quartiles(self, col, n_rows):
+        q = (c_double * 2)()
+        n = c_int64()
+        self._check(self.lib.dr_quartiles(self._h, _dp(col), n_rows, q, byref(n), self._stream()))
+        return float(q[0]), float(q[1]), int(n.value)
+
+    def range_flag(self, col, n_rows, lower, upper, bitmap):
+        self._check(self.lib.dr_range_flag(self._h, _dp(col), n_rows, lower, upper, _dp(bitmap), self._stream()))
+
+    def dc_const(self, cols, ops, args, n_rows, row_bitmap):
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_dc_const(self._h, cp, _i32_array(ops), _i32_array(args), len(cols), n_rows,
+                                         _dp(row_bitmap), self._stream()))
+
+    def dc_fd_build(self, key_cols, strides, b_col, n_rows, key_space, lo, hi):
+        cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
+        self._check(self.lib.dr_dc_fd_build(self._h, cp, _i64_array(strides), len(key_cols), _dp(b_col), n_rows,
+                                            key_space, _dp(lo), _dp(hi), self._stream()))
+
+    def dc_fd_flag(self, key_cols, strides, n_rows, key_space, lo, hi, row_bitmap):
+        cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
+        self._check(self.lib.dr_dc_fd_flag(self._h, cp, _i64_array(strides), len(key_cols), n_rows, key_space,
+                                           _dp(lo), _dp(hi), _dp(row_bitmap), self._stream()))
+
+    # ---- bitmaps ---------------------------------------------------------------------------------
+    def bitmap_or(self, dst, src, n_rows):
+        self._check(self.lib.dr_bitmap_or(self._h, _dp(dst), _dp(src), n_rows, self._stream()))
+
+    def bitmap_andnot(self, dst, src, n_rows):
+        self._check(self.lib.dr_bitmap_andnot(self._h, _dp(dst), _dp(src), n_rows, self._stream()))
+
+    def bitmap_count(self, bitmap, n_rows):
+        n = c_int64()
+        self._check(self.lib.dr_bitmap_count(self._h, _dp(bitmap), n_rows, byref(n), self._stream()))
+        return int(n.value)
+
+    def bitmap_to_rows(self, bitmap, n_rows, out_rows, capacity):
+        n = c_int64()
+        self._check(self.lib.dr_bitmap_to_rows(self._h, _dp(bitmap), n_rows, _dp(out_rows), capacity, byref(n),
+                                               self._stream()))
+        return int(n.value)
+
+    def bitmap_gather(self, src, rows, n, out):
+        self._check(self.lib.dr_bitmap_gather(self._h, _dp(src), _dp(rows), n, _dp(out), self._stream()))
+
+    def bitmap_clear_rows(self, bitmap, rows, flags, n):
+        self._check(self.lib.dr_bitmap_clear_rows(self._h, _dp(bitmap), _dp(rows), _dp(flags), n, self._stream()))
+
+    # ---- statistics ------------------------------------------------------------------------------
+    def discretize(self, vals, n_rows, vmin, denom, thres, out):
+        self._check(self.lib.dr_discretize(self._h, _dp(vals), n_rows, vmin, denom, thres, _dp(out), self._stream()))
+
+    def pair_presence(self, cols, dom, px, py, bit_off, n_rows, block_rows, n_blocks, bits):
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_pair_presence(self._h, cp, _i32_array(dom), len(cols), _i32_array(px), _i32_array(py),
+                                              len(px), _i64_array(bit_off), n_rows, block_rows, n_blocks, _dp(bits),
+                                              self._stream()))
+
+    def cooc(self, cols, dom, px, py, tab_off, n_rows, out):
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_cooc(self._h, cp, _i32_array(dom), len(cols), _i32_array(px), _i32_array(py), len(px),
+                                     _i64_array(tab_off), n_rows, _dp(out), self._stream()))
+
+    def domain_score(self, rows, n_cells, target, dom_t, corr, dom_c, cooc, hist_t, tau, n_total, beta, out_top1,
+                     out_prob, out_weak):
+        cp, _k1 = _ptr_array([c.data_ptr() for c in corr])
+        tp, _k2 = _ptr_array([c.data_ptr() for c in cooc])
+        self._check(self.lib.dr_domain_score(self._h, _dp(rows), n_cells, _dp(target), dom_t, cp, _i32_array(dom_c),
+                                             tp, len(corr), _dp(hist_t), _i64_array(tau), n_total, beta,
+                                             _dp(out_top1), _dp(out_prob), _dp(out_weak), self._stream()))
+
+    # ---- repair base / tile ----------------------------------------------------------------------
+    def gather_rows_masked(self, cols, bitmaps, rows, n, out, f64=False):
+        cp, _k1 = _ptr_array([c.data_ptr() for c in cols])
+        bp, _k2 = _ptr_array([0 if b is None else b.data_ptr() for b in bitmaps])
+        fn = self.lib.dr_gather_rows_masked_f64 if f64 else self.lib.dr_gather_rows_masked
+        self._check(fn(self._h, cp, bp, len(cols), _dp(rows), n, _dp(out), self._stream()))
+
+    def tile_null_bitmap(self, tile, n, n_cols, col, out, f64=False):
+        fn = self.lib.dr_tile_null_bitmap_f64 if f64 else self.lib.dr_tile_null_bitmap
+        self._check(fn(self._h, _dp(tile), n, n_cols, col, _dp(out), self._stream()))
+
+    def gather(self, col, rows, n, out, f64=False):
+        fn = self.lib.dr_gather_f64 if f64 else self.lib.dr_gather_i32
+        self._check(fn(self._h, _dp(col), _dp(rows), n, _dp(out), self._stream()))
+
+    def tile_gather(self, tile, n_cols, col, drows, n, out, f64=False):
+        fn = self.lib.dr_tile_gather_f64 if f64 else self.lib.dr_tile_gather_i32
+        self._check(fn(self._h, _dp(tile), n_cols, col, _dp(drows), n, _dp(out), self._stream()))
+
+    def lookup_sorted(self, sorted_rows, n_sorted, keys, n, out):
+        self._check(self.lib.dr_lookup_sorted(self._h, _dp(sorted_rows), n_sorted, _dp(keys), n, _dp(out),
+                                              self._stream()))
+
+    def forest_predict(self, forest_struct, tile, n_cols, ctile, n_ccols, cells, n_cells, target_col, out_margin=None):
+        self._check(self.lib.dr_forest_predict(self._h, byref(forest_struct), _dp(tile), n_cols, _dp(ctile), n_ccols,
+                                               _dp(cells), n_cells, target_col, _dp(out_margin), self._stream()))
+
+    def tile_fill(self, tile, n_cols, col, cells, n_cells, value):
+        self._check(self.lib.dr_tile_fill_i32(self._h, _dp(tile), n_cols, col, _dp(cells), n_cells, value,
+                                              self._stream()))

@@ -1,0 +1,188 @@
+"""Flat forest exchange format, feature encoders and their device images.
+
+The reference hands its pandas UDF pickled LightGBM models plus ``category_encoders`` transformers
+(``model.py:1067-1073,1111-1133``); here a model is a handful of flat arrays the CUDA kernel
+walks directly (``dr_forest`` in ``include/b200repair.h``).
+
+Flat forest (host, NumPy):
+  n_classes      1 = regression, 2 = binary (one tree sequence), C > 2 = C sequences
+  baseline       float64[S]
+  tree_seq       int32[T]        sequence (class) of tree t, trees in boosting order
+  tree_offset    int64[T+1]      node range of tree t
+  feature        int32[M]  (-1 = leaf)   threshold float64[M]   missing_left uint8[M]
+  left, right    int32[M]  (relative to the tree root)          value float64[M] (leaf value)
+Encoders (one per feature column, in feature order):
+  {"attr", "type": "cont"}                          float passthrough, NaN = NULL
+  {"attr", "type": "ordinal", "categories": [...]}  first-seen order on the training sample ->
+                                                    1..k; NULL never seen -> -2; unseen value -> NaN
+  {"attr", "type": "sum", "categories": [...]}      deviation (sum) contrast, k-1 columns, last
+                                                    level = -1 row; NULL never seen -> zeros; unseen -> NaN
+  categories hold dictionary CODES (-1 = the NULL category).
+"""
+import numpy as np
+
+LEAF = 0xFFF
+MAX_TREE_NODES = 511
+
+
+def first_seen(codes):
+    """Distinct values of a code array in order of first appearance (pandas ``unique`` order)."""
+    codes = np.asarray(codes)
+    _, idx = np.unique(codes, return_index=True)
+    return [int(c) for c in codes[np.sort(idx)]]
+
+
+def encoder_type(attr, continuous, domain_stats, small_domain_threshold):
+    # model.py:701-729: SumEncoder for ndv < small_domain_threshold, OrdinalEncoder otherwise
+    if attr in continuous:
+        return "cont"
+    return "sum" if int(domain_stats[attr]) < small_domain_threshold else "ordinal"
+
+
+def encoder_width(enc):
+    if enc["type"] == "sum":
+        k = len(enc["categories"])
+        return k - 1 if k >= 2 else 0
+    return 1
+
+
+def encoder_lut(enc, dict_size):
+    """float64 [dict_size + 1, width]: row (code + 1) = encoded feature values of that code."""
+    w = encoder_width(enc)
+    lut = np.full((dict_size + 1, w), np.nan, dtype=np.float64)
+    cats = enc["categories"]
+    null_seen = -1 in cats
+    if enc["type"] == "ordinal":
+        for pos, c in enumerate(cats):
+            lut[c + 1, 0] = float(pos + 1)
+        if not null_seen:
+            lut[0, 0] = -2.0
+        return lut
+    k = len(cats)
+    if k < 2:
+        return lut
+    for pos, c in enumerate(cats):
+        row = np.zeros(k - 1)
+        if pos == k - 1:
+            row[:] = -1.0
+        else:
+            row[pos] = 1.0
+        lut[c + 1] = row
+    if not null_seen:
+        lut[0] = 0.0
+    return lut
+
+
+def encode_matrix(encoders, code_cols, value_cols, dict_sizes):
+    """Host-side encoding of a sample: code_cols / value_cols are {attr: array}.  -> float64 [n, F']"""
+    n = 0
+    for e in encoders:
+        src = value_cols if e["type"] == "cont" else code_cols
+        n = len(src[e["attr"]])
+        break
+    blocks = []
+    for e in encoders:
+        if e["type"] == "cont":
+            blocks.append(np.asarray(value_cols[e["attr"]], dtype=np.float64).reshape(-1, 1))
+        else:
+            lut = encoder_lut(e, dict_sizes[e["attr"]])
+            blocks.append(lut[np.asarray(code_cols[e["attr"]], dtype=np.int64) + 1])
+    if not blocks:
+        return np.zeros((n, 0))
+    return np.concatenate(blocks, axis=1)
+
+
+def pack_nodes(forest):
+    """-> (node_thr float64[M], node_meta uint32[M]) in the kernel's packed layout."""
+    feat = np.asarray(forest["feature"], dtype=np.int64)
+    if feat.size and feat.max() >= LEAF:
+        raise ValueError("too many encoded features for the packed node format")
+    left = np.asarray(forest["left"], dtype=np.int64)
+    right = np.asarray(forest["right"], dtype=np.int64)
+    if left.size and (left.max() > MAX_TREE_NODES or right.max() > MAX_TREE_NODES):
+        raise ValueError("a tree has more than {} nodes".format(MAX_TREE_NODES))
+    is_leaf = feat < 0
+    meta = np.where(is_leaf, LEAF, feat).astype(np.uint32)
+    meta |= (np.asarray(forest["missing_left"], dtype=np.uint32) & 1) << 12
+    meta |= (np.where(is_leaf, 0, left).astype(np.uint32) & 0x1FF) << 13
+    meta |= (np.where(is_leaf, 0, right).astype(np.uint32) & 0x1FF) << 22
+    thr = np.where(is_leaf, forest["value"], forest["threshold"]).astype(np.float64)
+    return thr, meta
+
+
+def group_by_sequence(forest):
+    """Reorders trees so that each sequence is contiguous (boosting order kept inside a sequence).
+    -> (seq_tree_off int32[S+1], tree order int array)"""
+    seq = np.asarray(forest["tree_seq"], dtype=np.int64)
+    S = len(forest["baseline"])
+    order = np.argsort(seq, kind="stable")
+    counts = np.bincount(seq, minlength=S)
+    off = np.zeros(S + 1, dtype=np.int32)
+    off[1:] = np.cumsum(counts)
+    return off, order
+
+
+class DeviceModel:
+    """Device image of one repair model (forest + encoder LUTs) ready for dr_forest_predict."""
+
+    def __init__(self, spec, feature_tile_cols, dict_sizes, cont_tile_cols, device):
+        """spec: {"forest", "encoders", "class_codes" or None, "integral"}.
+        feature_tile_cols: {attr: column index in the code tile};  cont_tile_cols: {attr: index in
+        the float64 tile}."""
+        import torch
+        from ._native import dr_forest
+        f = spec["forest"]
+        off, order = group_by_sequence(f)
+        thr, meta = pack_nodes(f)
+        toff = np.asarray(f["tree_offset"], dtype=np.int64)
+        sizes = (toff[1:] - toff[:-1])[order]
+        new_off = np.zeros(len(order) + 1, dtype=np.int64)
+        new_off[1:] = np.cumsum(sizes)
+        idx = np.concatenate([np.arange(toff[t], toff[t + 1]) for t in order]) if len(order) else \
+            np.zeros(0, dtype=np.int64)
+        thr, meta = thr[idx], meta[idx]
+        feat_col, lut_off, luts = [], [0], []
+        for e in spec["encoders"]:
+            w = encoder_width(e)
+            if e["type"] == "cont":
+                feat_col.append(-cont_tile_cols[e["attr"]] - 1)
+                lut_off.append(lut_off[-1])
+                continue
+            lut = encoder_lut(e, dict_sizes[e["attr"]])
+            for j in range(w):
+                feat_col.append(feature_tile_cols[e["attr"]])
+                luts.append(lut[:, j])
+                lut_off.append(lut_off[-1] + lut.shape[0])
+        n_feat = len(feat_col)
+        if n_feat != int(f["n_features"]):
+            raise ValueError("encoder layout ({} features) does not match the forest ({})".format(
+                n_feat, int(f["n_features"])))
+
+        def dev(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+
+        self._keep = {
+            "seq_tree_off": dev(off, np.int32),
+            "tree_node_off": dev(new_off, np.int32),
+            "node_thr": dev(thr if len(thr) else np.zeros(1), np.float64),
+            "node_meta": dev((meta if len(meta) else np.zeros(1, dtype=np.uint32)).view(np.int32), np.int32),
+            "baseline": dev(f["baseline"], np.float64),
+            "feat_col": dev(feat_col if feat_col else [0], np.int32),
+            "enc_lut_off": dev(lut_off, np.int32),
+            "enc_lut": dev(np.concatenate(luts) if luts else np.zeros(1), np.float64),
+        }
+        cc = spec.get("class_codes")
+        self.kind = 0 if cc is not None else 1
+        self._keep["class_code"] = dev(cc if cc is not None else [0], np.int32)
+        s = dr_forest()
+        s.n_seq, s.n_trees, s.n_nodes, s.n_feat = len(f["baseline"]), len(order), len(thr), n_feat
+        for k in ("seq_tree_off", "tree_node_off", "node_thr", "node_meta", "baseline", "feat_col", "enc_lut_off",
+                  "enc_lut", "class_code"):
+            setattr(s, k, self._keep[k].data_ptr())
+        s.kind = self.kind
+        s.integral = 1 if spec.get("integral") else 0
+        s.n_classes = len(cc) if cc is not None else 0
+        self.struct = s
+        self.n_seq = s.n_seq
+        self.n_trees = s.n_trees
+        self.n_nodes = s.n_nodes

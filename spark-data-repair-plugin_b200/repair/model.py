@@ -1,0 +1,521 @@
+"""``RepairModel``: the reference's builder-style API (``python/repair/model.py:103-1537``) in front of
+the B200 pipeline.  Setter names, argument checks, option keys, error messages, running modes and
+the output schema ``(row_id, attribute, current_value, repaired)`` are the reference's; the work
+behind ``run()`` is ``engine.Engine`` (CUDA) instead of Spark SQL + pandas UDFs.
+
+Inputs: a pandas ``DataFrame`` (a pyspark ``DataFrame`` is collected once with ``toPandas()``), the
+name of a table registered in ``repair.catalog``, or a pre-encoded ``EncodedTable``.
+Modes implemented in this version: default, ``detect_errors_only``, ``repair_data``; the pmf /
+score / maximal-likelihood modes validate their arguments like the reference and then raise
+``NotImplementedError`` ("next").
+"""
+import logging
+import time
+from typing import Any, Dict, List, Optional, Union
+
+import numpy as np
+import pandas as pd
+from pandas import DataFrame
+
+from . import catalog
+from .costs import UpdateCostFunction
+from .errors import ErrorDetector, ErrorModelOptions, default_detectors
+from .forest import DeviceModel, encode_matrix, encoder_type, first_seen
+from .table import EncodedTable
+from .train import build_model, train_option_keys, validate_options
+from .utils import AnalysisException, argtype_check, cell_to_string, get_option_value, to_list_str
+
+_logger = logging.getLogger("repair")
+
+_MODEL_OPTS = [
+    ("model.max_training_row_num", 10000, int, lambda v: v >= 10, "`{}` should be greater than and equal to 10"),
+    ("model.max_training_column_num", 65536, int, lambda v: v >= 2, "`{}` should be greater than 1"),
+    ("model.small_domain_threshold", 12, int, lambda v: v >= 3, "`{}` should be greater than 2"),
+    ("model.rule.repair_by_regex.disabled", True, bool, None, None),
+    ("model.rule.repair_by_nearest_values.disabled", True, bool, None, None),
+    ("model.rule.merge_threshold", 2.0, float, None, None),
+    ("model.rule.repair_by_functional_deps.disabled", False, bool, None, None),
+    ("model.rule.max_domain_size", 1000, int, lambda v: v > 10, "`{}` should be greater than 10"),
+    ("repair.pmf.cost_weight", 0.1, float, lambda v: v > 0.0, "`{}` should be positive"),
+    ("repair.pmf.prob_threshold", 0.0, float, None, None),
+    ("repair.pmf.prob_top_k", 32, int, lambda v: v >= 3, "`{}` should be greater than 2"),
+]
+_MODEL_OPT = {o[0]: o for o in _MODEL_OPTS}
+
+
+def _is_spark_df(obj):
+    return type(obj).__module__.startswith("pyspark.") and type(obj).__name__ == "DataFrame"
+
+
+def _as_encoded(obj, row_id, name="input"):
+    if isinstance(obj, EncodedTable):
+        return obj
+    if _is_spark_df(obj):
+        obj = obj.toPandas()
+    return EncodedTable.from_pandas(obj, row_id, name)
+
+
+def select_features(pairwise_stats, y, features, max_training_column_num):
+    """Keeps the features most correlated with y when there are too many (model.py:677-699)."""
+    if max_training_column_num < len(features) and y in pairwise_stats:
+        ranked = sorted((float(h), f) for f, h in pairwise_stats[y] if f in features)
+        kept = []
+        for h, f in ranked:
+            if len(kept) <= 1 or (h >= 0.0 and len(kept) < max_training_column_num):
+                kept.append(f)
+        return kept
+    return features
+
+
+class RepairModel():
+    """Interface to detect error cells in given input data and repair them (drop-in for
+    ``repair.model.RepairModel``)."""
+
+    option_keys = set([o[0] for o in _MODEL_OPTS]) | set(ErrorModelOptions.option_keys) | set(train_option_keys)
+
+    def __init__(self) -> None:
+        self.db_name: str = ""
+        self.input: Optional[Union[str, DataFrame, EncodedTable]] = None
+        self.row_id: Optional[str] = None
+        self.targets: List[str] = []
+        self.error_cells: Optional[Union[str, DataFrame]] = None
+        self.error_detectors: List[ErrorDetector] = []
+        self.discrete_thres: int = 80
+        self.parallel_stat_training_enabled: bool = False
+        self.training_data_rebalancing_enabled: bool = False
+        self.repair_by_rules: bool = False
+        self.repair_delta: Optional[int] = None
+        self.cf: Optional[UpdateCostFunction] = None
+        self.opts: Dict[str, str] = {}
+        # engine knobs (not part of the reference API)
+        self.device_index: int = 0
+        self.model_provider = None   # callable(ctx) -> model spec; default trains with train.build_model
+        self.last_run: Dict[str, Any] = {}
+
+    # ---- setters (same names / checks / messages as the reference) -------------------------------
+    @argtype_check
+    def setDbName(self, db_name: str) -> "RepairModel":
+        if isinstance(self.input, DataFrame) or _is_spark_df(self.input):
+            raise ValueError("Can not specify a database name when input is `DataFrame`")
+        self.db_name = db_name
+        return self
+
+    @argtype_check
+    def setTableName(self, table_name: str) -> "RepairModel":
+        if not table_name:
+            raise ValueError("`table_name` should have at least character")
+        self.input = table_name
+        return self
+
+    @argtype_check
+    def setInput(self, input: Union[str, DataFrame]) -> "RepairModel":
+        if type(input) is str:
+            self.setTableName(input)
+        else:
+            self.db_name = ""
+            self.input = input
+        return self
+
+    def setEncodedInput(self, table: EncodedTable) -> "RepairModel":
+        """Pre-encoded input (label-encoded int32 columns + dictionaries); sets the row id too."""
+        if not isinstance(table, EncodedTable):
+            raise TypeError("`table` should be provided as EncodedTable, got {}".format(type(table).__name__))
+        self.db_name = ""
+        self.input = table
+        self.row_id = table.row_id
+        return self
+
+    @argtype_check
+    def setRowId(self, row_id: str) -> "RepairModel":
+        if not row_id:
+            raise ValueError("`row_id` should have at least character")
+        self.row_id = row_id
+        return self
+
+    @argtype_check
+    def setTargets(self, attrs: List[str]) -> "RepairModel":
+        if len(attrs) == 0:
+            raise ValueError("`attrs` should have at least one attribute")
+        self.targets = attrs
+        return self
+
+    @argtype_check
+    def setErrorCells(self, error_cells: Union[str, DataFrame]) -> "RepairModel":
+        if type(error_cells) is str and not error_cells:
+            raise ValueError("`error_cells` should have at least character")
+        if self.row_id is None:
+            raise ValueError("`setRowId` should be called before specifying error cells")
+        df = error_cells if isinstance(error_cells, DataFrame) else catalog.table(str(error_cells))
+        if not all(c in df.columns for c in [str(self.row_id), "attribute"]):
+            raise ValueError("Error cells should have `{}` and `attribute` in columns".format(self.row_id))
+        self.error_cells = error_cells
+        return self
+
+    @argtype_check
+    def setErrorDetectors(self, detectors: List[ErrorDetector]) -> "RepairModel":
+        self.error_detectors = detectors
+        return self
+
+    @argtype_check
+    def setDiscreteThreshold(self, thres: int) -> "RepairModel":
+        if int(thres) < 2:
+            raise ValueError("`thres` should be bigger than 1, got {}".format(thres))
+        self.discrete_thres = thres
+        return self
+
+    @argtype_check
+    def setParallelStatTrainingEnabled(self, enabled: bool) -> "RepairModel":
+        self.parallel_stat_training_enabled = enabled
+        return self
+
+    @argtype_check
+    def setTrainingDataRebalancingEnabled(self, enabled: bool) -> "RepairModel":
+        self.training_data_rebalancing_enabled = enabled
+        return self
+
+    @argtype_check
+    def setRepairByRules(self, enabled: bool) -> "RepairModel":
+        self.repair_by_rules = enabled
+        return self
+
+    @argtype_check
+    def setRepairDelta(self, delta: int) -> "RepairModel":
+        if delta <= 0:
+            raise ValueError("Repair delta should be positive, got {}".format(delta))
+        self.repair_delta = int(delta)
+        return self
+
+    @argtype_check
+    def setUpdateCostFunction(self, cf: UpdateCostFunction) -> "RepairModel":
+        self.cf = cf
+        return self
+
+    @argtype_check
+    def option(self, key: str, value: str) -> "RepairModel":
+        if key not in self.option_keys:
+            raise ValueError("Non-existent key specified: key={}".format(key))
+        self.opts[key] = value
+        return self
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _opt(self, key):
+        return get_option_value(self.opts, *_MODEL_OPT[key])
+
+    @property
+    def _repair_by_nearest_values_enabled(self) -> bool:
+        return not bool(self._opt("model.rule.repair_by_nearest_values.disabled")) \
+            and self.repair_by_rules and self.cf is not None
+
+    def _resolve_input(self):
+        if isinstance(self.input, str):
+            name = "{}.{}".format(self.db_name, self.input) if self.db_name else self.input
+            return _as_encoded(catalog.table(name), str(self.row_id), name), name
+        return _as_encoded(self.input, str(self.row_id)), "input"
+
+    def _given_cells(self, table):
+        """setErrorCells frame -> (row positions, attrs) restricted like errors.py:434-446."""
+        if self.error_cells is None:
+            return None
+        df = self.error_cells if isinstance(self.error_cells, DataFrame) else catalog.table(str(self.error_cells))
+        keep = set(self.targets) if self.targets else set(table.names) | {table.row_id}
+        pos_of = {str(v): i for i, v in enumerate(table.row_ids.tolist())}
+        positions, attrs = [], []
+        for rid, a in zip(df[str(self.row_id)].tolist(), df["attribute"].tolist()):
+            if a in keep and a in table.by_name and str(rid) in pos_of:
+                positions.append(pos_of[str(rid)])
+                attrs.append(a)
+        return positions, attrs
+
+    # ---- run -------------------------------------------------------------------------------------
+    def run(self, detect_errors_only: bool = False, compute_repair_candidate_prob: bool = False,
+            compute_repair_prob: bool = False, compute_repair_score: bool = False,
+            repair_data: bool = False, maximal_likelihood_repair: bool = False) -> DataFrame:
+        if self.input is None or self.row_id is None:
+            raise ValueError("`setInput` and `setRowId` should be called before repairing")
+        if maximal_likelihood_repair and self.repair_delta is None:
+            raise ValueError("`setRepairDelta` should be called when enabling maximal likelihood repairing")
+        if maximal_likelihood_repair and self.cf is None:
+            raise ValueError("`setUpdateCostFunction` should be called when enabling maximal likelihood repairing")
+        if maximal_likelihood_repair and len(self.cf.targets) > 0:  # type: ignore
+            raise ValueError("`UpdateCostFunction.targets` cannot be used when enabling "
+                             "maximal likelihood repairing")
+        exclusive = [("detect_errors_only", detect_errors_only),
+                     ("compute_repair_candidate_prob", compute_repair_candidate_prob),
+                     ("compute_repair_prob", compute_repair_prob),
+                     ("compute_repair_score", compute_repair_score),
+                     ("repair_data", repair_data)]
+        chosen = [n for n, v in exclusive if v]
+        if len(chosen) > 1:
+            raise ValueError("{} cannot be set to true simultaneously".format(to_list_str(chosen, sep="/", quote=True)))
+        if self._repair_by_nearest_values_enabled and \
+                (maximal_likelihood_repair or compute_repair_candidate_prob or compute_repair_prob
+                 or compute_repair_score):
+            raise ValueError("Cannot repair data by nearest values when enabling "
+                             "`maximal_likelihood_repair`, `compute_repair_candidate_prob`, "
+                             "`compute_repair_prob`, or `compute_repair_score`")
+        if compute_repair_prob or compute_repair_score:
+            compute_repair_candidate_prob = True
+        if compute_repair_score:
+            maximal_likelihood_repair = True
+
+        t0 = time.time()
+        table, input_name = self._resolve_input()
+        continuous = table.continuous_attrs
+        _logger.info("input_table: {} ({} rows x {} columns)".format(input_name, table.n_rows, len(table.columns)))
+        if maximal_likelihood_repair and len(continuous) != 0:
+            raise ValueError("Cannot enable the maximal likelihood repair mode when continous attributes found")
+        if self.targets and len(set(self.targets) & (set(table.names) | {table.row_id})) == 0:
+            raise ValueError("Target attributes not found in {}: {}".format(input_name, to_list_str(self.targets)))
+        err_opts = ErrorModelOptions.resolve(self.opts)
+        validate_options(self.opts)
+        for key in _MODEL_OPT:
+            self._opt(key)
+        if compute_repair_candidate_prob or maximal_likelihood_repair:
+            raise NotImplementedError("pmf / score / maximal-likelihood modes are not built yet (SURVEY.md 8f)")
+        if self.repair_by_rules:
+            raise NotImplementedError("rule-based repairs are not built yet (SURVEY.md 8f)")
+
+        from .engine import Engine
+        engine = Engine(table, self.device_index)
+        try:
+            detectors = self.error_detectors or default_detectors(self.targets, table.names)
+            _logger.info("[Error Detection Phase] Used error detectors: {}".format(to_list_str(detectors)))
+            res = engine.detect([d.spec() for d in detectors], self.targets, self.discrete_thres, err_opts,
+                                self._given_cells(table))
+            self.last_run = {"detect": res, "elapsed_detect": time.time() - t0}
+            if detect_errors_only:
+                return self._cells_frame(engine, table, res)
+            if sum(res.n_cells.values()) == 0:
+                _logger.info("Any error cell not found, so the input data is already clean")
+                return self._input_frame(table) if repair_data else self._empty_frame(table, repaired=True)
+            if len(res.target_columns) == 0:
+                raise ValueError("At least one valid discretizable feature is needed to repair error cells, "
+                                 "but no such feature found")
+            out = repair_cells(self, engine, table, res, continuous, repair_data)
+            _logger.info("!!!Total Processing time is {}(s)!!!".format(time.time() - t0))
+            return out
+        finally:
+            self.last_run["gpu_launches"] = engine.ctx.launch_count
+            engine.close()
+
+    # ---- frames ----------------------------------------------------------------------------------
+    def _empty_frame(self, table, repaired=False):
+        cols = [table.row_id, "attribute", "current_value"] + (["repaired"] if repaired else [])
+        return DataFrame({c: [] for c in cols})
+
+    def _input_frame(self, table):
+        data = {table.row_id: table.row_ids}
+        for c in table.columns:
+            if c.continuous:
+                data[c.name] = c.values if c.kind == "float" else pd.array(
+                    [None if v != v else int(v) for v in c.values], dtype="Int64")
+            else:
+                data[c.name] = c.decode(c.codes)
+        return DataFrame(data)
+
+    def _cells_frame(self, engine, table, res):
+        ids, attrs, curs = [], [], []
+        for a, rows, cur in engine.cells_of(res):
+            ids.append(table.row_ids[rows])
+            attrs += [a] * len(rows)
+            curs += table.by_name[a].decode(cur)
+        if not ids:
+            return self._empty_frame(table)
+        return DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs,
+                          "current_value": pd.array(curs, dtype=object)})
+
+
+def _train_model(rm, engine, table, res, y, continuous, tile_col):
+    """Bookkeeping of _build_repair_models for one target (model.py:1001-1052, 768-815).
+    -> ("const", code or None) | ("forest", DeviceModel, info)"""
+    col = table.by_name[y]
+    is_discrete = not col.continuous
+    input_columns = [c for c in table.names if c != y]
+    if is_discrete:
+        counts = np.asarray(engine.raw_value_counts(y), dtype=np.int64).copy()
+        if y in res.bitmaps and res.n_cells.get(y, 0):
+            rows = engine.bitmap_rows(res.bitmaps[y])
+            cur = engine.torch.empty(int(rows.numel()), dtype=engine.torch.int32, device=engine.device)
+            engine.ctx.gather(engine.dt.col(y), rows, int(rows.numel()), cur)
+            masked = np.bincount(cur.cpu().numpy().astype(np.int64) + 1, minlength=len(counts))
+            counts -= masked
+        present = np.nonzero(counts[1:] > 0)[0]
+        num_class = len(present)
+        if num_class <= 1:
+            return ("const", int(present[0]) if num_class == 1 else None)
+    else:
+        num_class = 0
+    features = select_features(res.pairwise_stats, y, input_columns, rm._opt("model.max_training_column_num"))
+    rows, n_valid = engine.valid_training_rows(res, y, rm._opt("model.max_training_row_num"))
+    if n_valid == 0:
+        return ("const", None)
+    codes, vals = engine.sample_rows_masked(res, res.target_columns, rows)
+    cont_idx = engine.dt.cont_index
+    encoders = []
+    dict_sizes = {c.name: c.dict_size for c in table.columns}
+    for f in features:
+        kind = encoder_type(f, continuous, res.domain_stats, rm._opt("model.small_domain_threshold"))
+        e = {"attr": f, "type": kind}
+        if kind != "cont":
+            e["categories"] = first_seen(codes[:, tile_col[f]])
+        encoders.append(e)
+    X = encode_matrix(encoders, {f: codes[:, tile_col[f]] for f in features},
+                      {f: vals[:, cont_idx[f]] for f in features if f in cont_idx} if vals is not None else {},
+                      dict_sizes)
+    y_values = codes[:, tile_col[y]] if is_discrete else vals[:, cont_idx[y]]
+    ctx = {"y": y, "features": features, "encoders": encoders, "X": X, "y_values": y_values,
+           "is_discrete": is_discrete, "num_class": num_class, "train_rows": rows, "opts": rm.opts}
+    _logger.info("Building model... type={} y={} features={} #rows={}".format(
+        "classfier" if is_discrete else "regressor", y, to_list_str(features), len(rows)))
+    if rm.model_provider is not None:
+        spec = rm.model_provider(ctx)
+    else:
+        forest, classes = build_model(X, y_values, is_discrete, num_class, rm.opts)
+        spec = None if forest is None else {"forest": forest, "class_codes": classes}
+    if spec is None:
+        return ("const", None)
+    if "const" in spec:
+        return ("const", spec["const"])
+    full = {"forest": spec["forest"], "encoders": encoders,
+            "class_codes": [int(c) for c in spec["class_codes"]] if is_discrete else None,
+            "integral": (not is_discrete) and col.kind == "int"}
+    dm = DeviceModel(full, tile_col, dict_sizes, cont_idx, engine.device)
+    return ("forest", dm, {"spec": full, "ctx": ctx})
+
+
+def repair_cells(rm, engine, table, res, continuous, repair_data=False):
+    """Phases 2-3 of RepairModel._run (model.py:1311-1408) on the device."""
+    torch = engine.torch
+    targets = res.target_columns
+    K = len(table.columns)
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    cont_idx = engine.dt.cont_index
+    cells = engine.cells_of(res, targets)           # (attr, rows, current codes), table order
+    if not cells:
+        return rm._input_frame(table) if repair_data else rm._empty_frame(table, repaired=True)
+    # models (training phase)
+    t0 = time.time()
+    models = [(y, _train_model(rm, engine, table, res, y, continuous, tile_col)) for y in targets]
+    rm.last_run["models"] = models
+    rm.last_run["elapsed_training"] = time.time() - t0
+    # repair phase: sequential chain over the targets on the dirty-row tile
+    t0 = time.time()
+    drows, tile, ctile = engine.build_dirty_tile(res, targets)
+    D = int(drows.numel())
+    n_cc = len(cont_idx)
+    nullbits = torch.zeros((D + 31) // 32 + 1, dtype=torch.int32, device=engine.device)
+    for y, m in models:
+        ycol = table.by_name[y]
+        if ycol.continuous:
+            engine.ctx.tile_null_bitmap(ctile, D, n_cc, cont_idx[y], nullbits, f64=True)
+        else:
+            engine.ctx.tile_null_bitmap(tile, D, K, tile_col[y], nullbits)
+        todo = engine.bitmap_rows(nullbits, D)
+        n = int(todo.numel())
+        if n == 0:
+            continue
+        if m[0] == "const":
+            if m[1] is not None and not ycol.continuous:
+                engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, int(m[1]))
+            continue
+        dm = m[1]
+        engine.ctx.forest_predict(dm.struct, tile, K, ctile, n_cc, todo, n,
+                                  cont_idx[y] if ycol.continuous else tile_col[y])
+    # output: (row id, attribute, current_value, repaired) for the error cells
+    ids, attrs, curs, reps = [], [], [], []
+    repaired_cells = []
+    for a, rows, cur in cells:
+        col = table.by_name[a]
+        d_rows = torch.from_numpy(rows.astype(np.int32)).to(engine.device)
+        dpos = torch.empty(len(rows), dtype=torch.int32, device=engine.device)
+        engine.ctx.lookup_sorted(drows, D, d_rows, len(rows), dpos)
+        cur_s = col.decode(cur)
+        if col.continuous:
+            out = torch.empty(len(rows), dtype=torch.float64, device=engine.device)
+            engine.ctx.tile_gather(ctile, n_cc, cont_idx[a], dpos, len(rows), out, f64=True)
+            vals = out.cpu().numpy()
+            rep_s = [cell_to_string(col.kind, v) for v in vals.tolist()]
+            repaired_cells.append((a, rows, vals))
+        else:
+            out = torch.empty(len(rows), dtype=torch.int32, device=engine.device)
+            engine.ctx.tile_gather(tile, K, tile_col[a], dpos, len(rows), out)
+            codes = out.cpu().numpy()
+            rep_s = col.decode(codes)
+            repaired_cells.append((a, rows, codes))
+        ids.append(table.row_ids[rows])
+        attrs += [a] * len(rows)
+        curs += cur_s
+        reps += rep_s
+    rm.last_run["elapsed_repair"] = time.time() - t0
+    rm.last_run["n_error_cells"] = len(attrs)
+    rm.last_run["n_dirty_rows"] = D
+    if repair_data:
+        return _apply_repairs(rm, table, repaired_cells)
+    frame = DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs,
+                       "current_value": pd.array(curs, dtype=object), "repaired": pd.array(reps, dtype=object)})
+    # repaired IS NULL OR NOT(current_value <=> repaired)   (model.py:1401)
+    cur_a, rep_a = frame["current_value"].to_numpy(dtype=object), frame["repaired"].to_numpy(dtype=object)
+    keep = np.array([r is None or c is None or c != r for c, r in zip(cur_a, rep_a)], dtype=bool)
+    return frame[keep].reset_index(drop=True)
+
+
+def _apply_repairs(rm, table, repaired_cells):
+    """repair_data=True: the input table with every error cell replaced by its repair."""
+    frame = rm._input_frame(table)
+    for a, rows, vals in repaired_cells:
+        col = table.by_name[a]
+        series = frame[a].to_numpy(dtype=object, copy=True) if not col.continuous or col.kind == "int" \
+            else frame[a].to_numpy(copy=True)
+        if col.continuous:
+            for r, v in zip(rows.tolist(), vals.tolist()):
+                series[r] = (None if v != v else int(v)) if col.kind == "int" else v
+        else:
+            dec = col.decode(vals)
+            for r, v in zip(rows.tolist(), dec):
+                series[r] = v
+        frame[a] = pd.array(series, dtype="Int64") if col.continuous and col.kind == "int" else series
+    return frame
+
+
+def detect_with(detector):
+    """``ErrorDetector.setUp(...).detect()`` standalone (errors.py:78-82): -> (row_id, attribute)."""
+    from .engine import Engine
+    src = detector.qualified_input_name
+    df = catalog.table(src) if isinstance(src, str) else src
+    table = _as_encoded(df, detector.row_id)
+    engine = Engine(table, 0)
+    try:
+        spec = dict(detector.spec())
+        spec.pop("targets", None)  # already folded into _targets by setUp
+        targets = [t for t in detector._targets if t in table.by_name]
+        if not targets:
+            return DataFrame({table.row_id: [], "attribute": []})
+        engine.discretize(80)
+        bitmaps, fused = {}, {}
+        kind = spec["type"]
+        if kind == "null":
+            engine.detect_null(targets, bitmaps, fused)
+            engine.scan_hist(list(fused.keys()), fused)
+        elif kind == "regex":
+            engine.detect_regex(spec["attr"], spec["regex"], targets, bitmaps)
+        elif kind == "domain":
+            if spec["attr"] in targets:
+                rx = engine.domain_values_regex(spec["attr"], spec["values"], spec["autofill"],
+                                                spec["min_count_thres"])
+                if rx is not None:
+                    engine.detect_regex(spec["attr"], rx, targets, bitmaps)
+        elif kind == "constraint":
+            engine.detect_constraints(spec["path"], spec["constraints"], targets, bitmaps)
+        elif kind == "outlier":
+            engine.detect_outliers(targets, bitmaps, spec.get("approx", False))
+        ids, attrs = [], []
+        for a in table.names:
+            if a in bitmaps:
+                rows = engine.bitmap_rows(bitmaps[a]).cpu().numpy().astype(np.int64)
+                ids.append(table.row_ids[rows])
+                attrs += [a] * len(rows)
+        if not attrs:
+            return DataFrame({table.row_id: [], "attribute": []})
+        return DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs})
+    finally:
+        engine.close()

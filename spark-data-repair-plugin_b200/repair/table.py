@@ -1,0 +1,233 @@
+"""Host-side table ingest: a DataFrame is collected ONCE into label-encoded int32 column-major
+arrays (sorted dictionaries, NULL = -1) plus float64 side arrays for numeric columns, then copied
+to the GPU through pinned staging buffers.  This replaces the Spark views the reference passes by
+name between Python and Scala ("Data hand-off").
+"""
+import numpy as np
+
+from .utils import AnalysisException, cell_to_string
+
+_SUPPORTED_MSG = "tinyint,float,smallint,string,double,int,bigint"  # RepairBase.scala:41-44 order as Spark prints it
+ROW_ALIGN = 128  # rows are padded so that every column starts 512-byte aligned (128-bit loads)
+
+
+class Column:
+    """kind: 'str' (discrete) | 'int' | 'float' (both continuous, RepairBase.scala:41-44).
+    ``dictionary``: sorted distinct non-NULL values (str objects, or float64 for numerics);
+    ``codes``: int32 index into it, -1 = NULL;  ``values``: float64 (NaN = NULL) for numerics."""
+
+    def __init__(self, name, kind, dictionary, codes, values=None):
+        self.name, self.kind, self.dictionary, self.codes, self.values = name, kind, dictionary, codes, values
+
+    @property
+    def dict_size(self):
+        return len(self.dictionary)
+
+    @property
+    def continuous(self):
+        return self.kind in ("int", "float")
+
+    def code_of(self, value):
+        """Dictionary code of a python value, or -2 if it does not occur."""
+        if len(self.dictionary) == 0:
+            return -2
+        if self.kind == "str":
+            i = int(np.searchsorted(self.dictionary.astype(str) if self.dictionary.dtype != object else
+                                    np.array(self.dictionary, dtype=object).astype(str), str(value)))
+            return i if i < len(self.dictionary) and str(self.dictionary[i]) == str(value) else -2
+        try:
+            x = float(value)
+        except (TypeError, ValueError):
+            return -2
+        i = int(np.searchsorted(self.dictionary, x))
+        return i if i < len(self.dictionary) and self.dictionary[i] == x else -2
+
+    def rank_bounds(self, value):
+        """(lower_bound, upper_bound) ranks of a constant in the sorted dictionary: ``col < c`` is
+        ``code < lower`` and ``col > c`` is ``code >= upper``."""
+        if self.kind == "str":
+            keys = [str(v) for v in self.dictionary]
+            import bisect
+            return bisect.bisect_left(keys, str(value)), bisect.bisect_right(keys, str(value))
+        x = float(value)
+        return int(np.searchsorted(self.dictionary, x, "left")), int(np.searchsorted(self.dictionary, x, "right"))
+
+    def strings(self):
+        """CAST(dictionary entry AS STRING) for every entry (regex LUTs, output frames)."""
+        if self.kind == "str":
+            return [str(v) for v in self.dictionary]
+        return [cell_to_string(self.kind, float(v)) for v in self.dictionary]
+
+    def decode(self, codes):
+        """codes -> list of CAST(.. AS STRING) python values (None for NULL)."""
+        strs = self.strings()
+        return [None if c < 0 else strs[c] for c in np.asarray(codes).tolist()]
+
+
+def _encode_numeric(name, kind, arr):
+    vals = np.asarray(arr, dtype=np.float64)
+    nul = np.isnan(vals)
+    uniq = np.unique(vals[~nul])
+    codes = np.full(len(vals), -1, dtype=np.int32)
+    codes[~nul] = np.searchsorted(uniq, vals[~nul]).astype(np.int32)
+    return Column(name, kind, uniq, codes, vals)
+
+
+def _encode_strings(name, series):
+    import pandas as pd
+    obj = series.astype(object)
+    isn = pd.isna(obj).to_numpy()
+    strs = np.array([None if n else str(v) for v, n in zip(obj.tolist(), isn.tolist())], dtype=object)
+    present = strs[~isn]
+    uniq = np.array(sorted(set(present.tolist())), dtype=object)
+    lut = {v: i for i, v in enumerate(uniq.tolist())}
+    codes = np.full(len(strs), -1, dtype=np.int32)
+    if len(present):
+        codes[~isn] = np.fromiter((lut[v] for v in present.tolist()), dtype=np.int32, count=len(present))
+    return Column(name, "str", uniq, codes, None)
+
+
+class EncodedTable:
+    """The collected input: row ids + encoded columns (row id excluded)."""
+
+    def __init__(self, row_id, row_ids, row_id_kind, columns, name="input"):
+        self.row_id, self.row_ids, self.row_id_kind = row_id, row_ids, row_id_kind
+        self.columns = list(columns)
+        self.name = name
+        self.n_rows = len(row_ids)
+        self.by_name = {c.name: c for c in self.columns}
+        self.row_offset = 0      # first global row of this shard
+        self.n_rows_global = self.n_rows
+
+    @property
+    def names(self):
+        return [c.name for c in self.columns]
+
+    @property
+    def continuous_attrs(self):
+        return [c.name for c in self.columns if c.continuous]
+
+    # ---- constructors --------------------------------------------------------------------------
+    @classmethod
+    def from_pandas(cls, df, row_id, name="input"):
+        """checkInputTable (RepairApi.scala:34-67): type gate, >= 3 columns, unique row id."""
+        import pandas as pd
+        if row_id not in df.columns:
+            raise AnalysisException("Column '{}' does not exist in table '{}'".format(row_id, name))
+        kinds, bad = {}, []
+        for c in df.columns:
+            k = df[c].dtype.kind
+            if k == "b":
+                bad.append("boolean")
+            elif k in "iu":
+                kinds[c] = "int"
+            elif k == "f":
+                kinds[c] = "float"
+            elif k in "OUS" or str(df[c].dtype) in ("string", "str", "category"):
+                kinds[c] = "str"
+            elif k == "M":
+                bad.append("timestamp")
+            else:
+                bad.append(str(df[c].dtype))
+        if bad:
+            raise AnalysisException("Supported types are {}, but unsupported ones found: {}".format(
+                _SUPPORTED_MSG, ",".join(bad)))
+        # object columns holding only numbers (e.g. nullable ints collected from Spark) are numeric
+        for c, k in list(kinds.items()):
+            if k == "str" and df[c].dtype == object:
+                non_null = [v for v in df[c].tolist() if v is not None and not (isinstance(v, float) and v != v)]
+                if non_null and all(isinstance(v, (int, np.integer)) and not isinstance(v, bool) for v in non_null):
+                    kinds[c] = "int"
+                elif non_null and all(isinstance(v, (int, float, np.integer, np.floating)) and
+                                      not isinstance(v, bool) for v in non_null):
+                    kinds[c] = "float"
+        if not len(df.columns) >= 3:
+            raise AnalysisException("A least three columns (`{}` columns + two more ones) in table '{}'".format(
+                row_id, name))
+        n_distinct = int(df[row_id].nunique(dropna=False))
+        if n_distinct != len(df):
+            raise AnalysisException(
+                "Uniqueness does not hold in column '{}' of table '{}' (# of distinct '{}': {}, # of rows: {})".format(
+                    row_id, name, row_id, n_distinct, len(df)))
+        cols = []
+        for c in df.columns:
+            if c == row_id:
+                continue
+            if kinds[c] == "str":
+                cols.append(_encode_strings(c, df[c]))
+            else:
+                arr = pd.to_numeric(df[c], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+                cols.append(_encode_numeric(c, kinds[c], arr))
+        return cls(row_id, df[row_id].to_numpy(), kinds[row_id], cols, name)
+
+    @classmethod
+    def from_codes(cls, row_id, names, codes, dict_sizes, name="input", row_ids=None, dictionaries=None):
+        """Pre-encoded discrete table (already label-encoded upstream, e.g. Arrow dictionary pages
+        or the synthetic generator): ``codes[k]`` int32, -1 = NULL; value c of column k prints as
+        ``dictionaries[k][c]`` (default ``"v%03d" % c``)."""
+        n = len(codes[0]) if len(codes) else 0
+        cols = []
+        for i, nm in enumerate(names):
+            d = dictionaries[i] if dictionaries is not None else \
+                np.array(["v%03d" % c for c in range(int(dict_sizes[i]))], dtype=object)
+            cols.append(Column(nm, "str", d, np.ascontiguousarray(codes[i], dtype=np.int32), None))
+        if row_ids is None:
+            row_ids = np.arange(n, dtype=np.int64)
+        if len(names) + 1 < 3:
+            raise AnalysisException("A least three columns (`{}` columns + two more ones) in table '{}'".format(
+                row_id, name))
+        return cls(row_id, row_ids, "int", cols, name)
+
+    def row_id_strings(self, positions):
+        ids = self.row_ids[np.asarray(positions, dtype=np.int64)]
+        return ids
+
+    def shard(self, rank, world):
+        """Contiguous row shard [lo, hi) for rank `rank` of `world` (global dictionaries kept)."""
+        n = self.n_rows
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        cols = [Column(c.name, c.kind, c.dictionary, c.codes[lo:hi], None if c.values is None else c.values[lo:hi])
+                for c in self.columns]
+        t = EncodedTable(self.row_id, self.row_ids[lo:hi], self.row_id_kind, cols, self.name)
+        t.row_offset, t.n_rows_global = lo, n
+        return t
+
+
+class DeviceTable:
+    """The encoded table resident in HBM: ``codes`` int32 [K][n_pad] (one contiguous column per
+    attribute) and ``values`` float64 [Kc][n_pad] for the continuous attributes."""
+
+    def __init__(self, table, device, codes=None, values=None):
+        import torch
+        self.table = table
+        self.device = device
+        self.n_rows = table.n_rows
+        self.n_pad = (self.n_rows + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN or ROW_ALIGN
+        K = len(table.columns)
+        self.cont_index = {c.name: i for i, c in enumerate([c for c in table.columns if c.continuous])}
+        if codes is None:
+            codes = torch.empty((K, self.n_pad), dtype=torch.int32, device=device)
+            staging = torch.empty((self.n_pad,), dtype=torch.int32).pin_memory()
+            for i, c in enumerate(table.columns):
+                staging[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.codes)))
+                staging[self.n_rows:].fill_(-1)
+                codes[i].copy_(staging, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        self.codes = codes
+        if values is None and self.cont_index:
+            values = torch.empty((len(self.cont_index), self.n_pad), dtype=torch.float64, device=device)
+            staging = torch.empty((self.n_pad,), dtype=torch.float64).pin_memory()
+            for c in table.columns:
+                if c.continuous:
+                    staging[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.values)))
+                    staging[self.n_rows:].fill_(float("nan"))
+                    values[self.cont_index[c.name]].copy_(staging, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+        self.values = values
+        self.col_index = {c.name: i for i, c in enumerate(table.columns)}
+
+    def col(self, name):
+        return self.codes[self.col_index[name]]
+
+    def val(self, name):
+        return self.values[self.cont_index[name]]

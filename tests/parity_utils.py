@@ -1,0 +1,157 @@
+"""Shared helpers for the parity tests: run the CUDA path (through the public API and the C ABI) and
+the CPU oracle on the same input, feeding the oracle the very forests the product trained."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "spark-data-repair-plugin_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+
+def make_detectors(specs):
+    from repair.errors import (ConstraintErrorDetector, DomainValues, GaussianOutlierErrorDetector,
+                               NullErrorDetector, RegExErrorDetector)
+    out = []
+    for s in specs:
+        t = s["type"]
+        if t == "null":
+            out.append(NullErrorDetector())
+        elif t == "regex":
+            out.append(RegExErrorDetector(s["attr"], s["regex"]))
+        elif t == "domain":
+            out.append(DomainValues(s["attr"], s.get("values", []), s.get("autofill", False),
+                                    s.get("min_count_thres", 12)))
+        elif t == "constraint":
+            out.append(ConstraintErrorDetector(s.get("path", ""), s.get("constraints", ""), s.get("targets", [])))
+        elif t == "outlier":
+            out.append(GaussianOutlierErrorDetector(s.get("approx", False)))
+    return out
+
+
+def _nan_equal(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def provider_from_product(rm, table, value_of):
+    """Oracle model_provider that hands back the product's forests and cross-checks the training
+    bookkeeping both sides derived independently (features, encoders, encoded sample)."""
+    models = dict(rm.last_run["models"])
+
+    def provider(ctx):
+        m = models[ctx["y"]]
+        if m[0] == "const":
+            return {"const": None if m[1] is None else value_of(ctx["y"], m[1])}
+        info = m[2]
+        pctx, spec = info["ctx"], info["spec"]
+        assert pctx["features"] == ctx["features"], (pctx["features"], ctx["features"])
+        for pe, oe in zip(spec["encoders"], ctx["encoders"]):
+            assert pe["attr"] == oe["attr"] and pe["type"] == oe["type"]
+            if pe["type"] != "cont":
+                want = [None if c < 0 else value_of(pe["attr"], c) for c in pe["categories"]]
+                assert want == oe["categories"], (pe["attr"], want, oe["categories"])
+        assert _nan_equal(pctx["X"], ctx["X"]), "encoded training matrices differ for " + ctx["y"]
+        assert list(np.asarray(pctx["train_rows"])) == list(np.asarray(ctx["train_rows"]))
+        classes = None
+        if spec["class_codes"] is not None:
+            classes = [value_of(ctx["y"], c) for c in spec["class_codes"]]
+        return {"forest": spec["forest"], "classes": classes}
+
+    return provider
+
+
+def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=None, mode="repair", encoded=False):
+    from repair import RepairModel
+    rm = RepairModel()
+    if encoded:
+        rm.setEncodedInput(inp)
+    else:
+        rm.setInput(inp).setRowId(row_id)
+    if specs:
+        rm.setErrorDetectors(make_detectors(specs))
+    if targets:
+        rm.setTargets(targets)
+    if thres != 80:
+        rm.setDiscreteThreshold(thres)
+    if given is not None:
+        rm.setErrorCells(given)
+    for k, v in (opts or {}).items():
+        rm.option(k, str(v))
+    if mode == "detect":
+        out = rm.run(detect_errors_only=True)
+    elif mode == "repair_data":
+        out = rm.run(repair_data=True)
+    else:
+        out = rm.run()
+    return rm, out
+
+
+def frame_tuples(df, row_id):
+    cols = [c for c in df.columns]
+    out = []
+    for rec in df.itertuples(index=False):
+        d = dict(zip(cols, rec))
+        t = [str(d[row_id]), d["attribute"], d.get("current_value")]
+        if "repaired" in d:
+            t.append(d["repaired"])
+        out.append(tuple(None if (isinstance(x, float) and x != x) else x for x in t))
+    return sorted(out, key=lambda t: (t[0], t[1]))
+
+
+def run_both_frame(df, row_id, specs, targets=None, thres=80, opts=None, mode="repair", kinds=None):
+    """pandas input: product through RepairModel, oracle through oracle.repair.run."""
+    from oracle import repair as OR
+    from oracle.table import from_pandas
+    from repair.table import EncodedTable
+    rm, out = run_product(df, row_id, specs, targets, thres, opts, mode=mode)
+    got = frame_tuples(out, row_id)
+    otbl = from_pandas(df)
+    enc = EncodedTable.from_pandas(df, row_id)
+
+    def value_of(attr, code):
+        col = enc.by_name[attr]
+        v = col.dictionary[code]
+        if col.kind == "str":
+            return str(v)
+        return int(v) if col.kind == "int" else float(v)
+
+    provider = provider_from_product(rm, enc, value_of) if mode == "repair" else None
+    o_opts = {k: v for k, v in (opts or {}).items() if k.startswith("error.") or k in OR.DEFAULT_OPTS}
+    want = OR.run(otbl, row_id, specs, targets, thres, None, o_opts, provider, detect_errors_only=(mode == "detect"))
+    want = sorted([tuple(w) for w in want], key=lambda t: (t[0], t[1]))
+    return got, want, {"gpu_launches": rm.last_run.get("gpu_launches", 0), "rm": rm}
+
+
+def synth_inputs(n_rows, n_cols, seed=0, c4=True):
+    from repair import synth
+    from repair.table import EncodedTable
+    spec = synth.SynthSpec.c4(n_rows, n_cols, seed) if c4 else synth.SynthSpec.c3(n_rows, n_cols, seed)
+    codes = synth.generate_numpy(spec)
+    names = synth.column_names(n_cols)
+    enc = EncodedTable.from_codes("tid", names, codes, spec.dom)
+    specs = [{"type": "null"}]
+    if c4 and synth.fd_constraints(n_cols):
+        specs.append({"type": "constraint", "constraints": synth.fd_constraints(n_cols)})
+    return spec, names, codes, enc, specs
+
+
+def run_both_synth(n_rows, n_cols, seed=0, n_estimators=20, c4=True, mode="repair", max_training_rows=2000):
+    """Label-encoded synthetic table (configs C3 / C4 at test size)."""
+    from oracle import repair as OR
+    from oracle.table import OTable
+    spec, names, codes, enc, specs = synth_inputs(n_rows, n_cols, seed, c4)
+    opts = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": n_estimators,
+            "model.max_training_row_num": max_training_rows}
+    rm, out = run_product(enc, "tid", specs, None, 80, opts, mode=mode, encoded=True)
+    got = frame_tuples(out, "tid")
+    otbl = OTable(["tid"] + names, ["int"] + ["str"] * n_cols,
+                  [np.arange(n_rows, dtype=np.float64)] + [c.astype(np.int64) for c in codes])
+    provider = provider_from_product(rm, enc, lambda attr, code: int(code)) if mode == "repair" else None
+    o_opts = {"error.pairwise_freq_ratio_threshold": 1.0, "model.max_training_row_num": max_training_rows}
+    want = OR.run(otbl, "tid", specs, None, 80, None, o_opts, provider, detect_errors_only=(mode == "detect"))
+    fmt = (lambda v: None if v is None else "v%03d" % int(v))
+    want = sorted([tuple([w[0], w[1]] + [fmt(x) for x in w[2:]]) for w in want], key=lambda t: (t[0], t[1]))
+    return got, want, {"gpu_launches": rm.last_run.get("gpu_launches", 0), "rm": rm}

@@ -1,0 +1,184 @@
+"""End-to-end parity: the public API (RepairModel -> C ABI -> CUDA) against the CPU oracle on the
+reference's fixtures and on seeded synthetic tables, plus the reference's own goldens."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import parity_utils as PU
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+FAST = {"model.lgb.n_estimators": 30}
+
+
+def read_csv(name, infer=True):
+    df = pd.read_csv(os.path.join(GOLDEN, name), dtype=None if infer else str, keep_default_na=True)
+    return df
+
+
+def adult():
+    df = pd.read_csv(os.path.join(GOLDEN, "adult.csv"))
+    return df
+
+
+def test_adult_detect_errors_only_golden():
+    # tests/test_model.py:510-518 + bin/testdata/adult_repair.csv (error-cell set)
+    rm, out = PU.run_product(adult(), "tid", [{"type": "null"}], mode="detect")
+    got = PU.frame_tuples(out, "tid")
+    exp = sorted([("3", "Sex", None), ("5", "Age", None), ("5", "Income", None), ("7", "Sex", None),
+                  ("12", "Age", None), ("12", "Sex", None), ("16", "Income", None)], key=lambda t: (t[0], t[1]))
+    assert got == exp
+
+
+@pytest.mark.parametrize("specs,targets", [
+    ([{"type": "null"}], None),
+    ([{"type": "null"}], ["Sex"]),
+    ([{"type": "domain", "attr": "Country", "values": ["United-States"]},
+      {"type": "domain", "attr": "Income", "values": ["LessThan50K", "MoreThan50K"]}], None),
+    ([{"type": "regex", "attr": "Country", "regex": "United-States"},
+      {"type": "regex", "attr": "Relationship", "regex": "(Husband|Own-child|Not-in-family)"}],
+     ["Country", "Relationship"]),
+    ([{"type": "constraint", "path": os.path.join(GOLDEN, "adult_constraints.txt")}], ["Sex", "Relationship"]),
+    ([{"type": "constraint", "path": os.path.join(GOLDEN, "adult_constraints.txt"), "targets": ["Sex"]}],
+     ["Sex", "Relationship"]),
+    ([], None),  # default detectors: NULL + DomainValues(autofill, 4) per attribute
+])
+def test_adult_detect_parity(specs, targets):
+    got, want, _ = PU.run_both_frame(adult(), "tid", specs, targets, mode="detect")
+    assert got == want
+    assert len(got) > 0
+
+
+def test_adult_repair_parity_and_golden_cells():
+    got, want, info = PU.run_both_frame(adult(), "tid", [{"type": "null"}], opts=FAST)
+    assert got == want
+    # bin/testdata/adult_repair.csv: the 7 repaired cells (values depend on LightGBM, not pinned)
+    golden = pd.read_csv(os.path.join(GOLDEN, "adult_repair.csv"))
+    assert sorted((str(t), a) for t, a in zip(golden.tid, golden.attribute)) == sorted((g[0], g[1]) for g in got)
+    assert all(g[3] is not None for g in got)
+    assert info["gpu_launches"] > 0
+
+
+def test_adult_repair_with_pair_stats():
+    opts = dict(FAST)
+    opts["error.pairwise_freq_ratio_threshold"] = 1.0
+    got, want, _ = PU.run_both_frame(adult(), "tid", [], opts=opts)
+    assert got == want
+
+
+def test_adult_given_error_cells():
+    dirty = pd.read_csv(os.path.join(GOLDEN, "adult_dirty.csv"))
+    rm, out = PU.run_product(adult(), "tid", [{"type": "null"}], opts=FAST, given=dirty)
+    got = sorted((g[0], g[1]) for g in PU.frame_tuples(out, "tid"))
+    assert got == sorted((str(t), a) for t, a in zip(dirty.tid, dirty.attribute))
+
+
+def test_adult_repair_data():
+    rm, out = PU.run_product(adult(), "tid", [{"type": "null"}], opts=FAST, mode="repair_data")
+    assert len(out) == 20 and out.isna().sum().sum() == 0
+    src = adult()
+    same = (out.fillna("<n>") == src.fillna("<n>"))
+    assert int((~same).sum().sum()) == 7  # exactly the 7 NULL cells changed
+
+
+def hospital():
+    return pd.read_csv(os.path.join(GOLDEN, "hospital.csv"), dtype=str).astype({"tid": int})
+
+
+def test_hospital_detect_parity_null_and_constraints():
+    # config C2: Null + Constraint detectors, pair stats enabled like tests/test_model_perf.py:204-209
+    specs = [{"type": "null"}, {"type": "constraint", "path": os.path.join(GOLDEN, "hospital_constraints.txt")}]
+    opts = {"error.pairwise_freq_ratio_threshold": 1.0}
+    got, want, _ = PU.run_both_frame(hospital(), "tid", specs, opts=opts, mode="detect")
+    assert got == want
+    assert len(got) > 2000
+
+
+def test_hospital_repair_parity():
+    specs = [{"type": "null"}, {"type": "constraint", "path": os.path.join(GOLDEN, "hospital_constraints.txt")}]
+    opts = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": 5}
+    got, want, _ = PU.run_both_frame(hospital(), "tid", specs, opts=opts,
+                                     targets=["City", "State", "ZipCode", "EmergencyService", "HospitalType"])
+    assert got == want
+    assert len(got) > 0
+
+
+def boston():
+    df = pd.read_csv(os.path.join(GOLDEN, "boston.csv"))
+    # tests/test_model_perf.py:74-76: CHAS and RAD are strings, ZN / TAX ints, the rest doubles
+    df["CHAS"] = df["CHAS"].map(lambda v: None if v != v else str(v))
+    df["RAD"] = df["RAD"].map(lambda v: None if v != v else str(int(v)) if float(v).is_integer() else str(v))
+    return df
+
+
+def test_boston_outlier_detect_parity():
+    got, want, _ = PU.run_both_frame(boston(), "tid", [{"type": "null"}, {"type": "outlier"}], mode="detect")
+    assert got == want
+    assert any(g[1] == "CRIM" and g[2] is not None for g in got)
+
+
+def test_boston_regression_repair_parity():
+    opts = {"model.lgb.n_estimators": 20}
+    got, want, _ = PU.run_both_frame(boston(), "tid", [{"type": "null"}], opts=opts)
+    assert got == want
+    assert {g[1] for g in got} >= {"CRIM", "TAX", "LSTAT"}
+
+
+@pytest.mark.parametrize("n_rows,n_cols,c4", [(3000, 8, True), (20000, 16, True), (20000, 16, False)])
+def test_synthetic_parity(n_rows, n_cols, c4):
+    got, want, info = PU.run_both_synth(n_rows, n_cols, seed=n_rows, n_estimators=10, c4=c4)
+    assert got == want
+    assert len(got) > 0.005 * n_rows
+
+
+def test_synthetic_detect_parity_larger():
+    got, want, _ = PU.run_both_synth(200000, 16, seed=1, c4=True, mode="detect")
+    assert got == want
+
+
+def test_escaped_column_names_and_mixed_types():
+    # tests/test_model.py:687-707 shape: spaces in names, string + double columns
+    rows = [(1, "1", None, 1.0), (2, None, "test-2", 2.0), (3, "1", "test-1", 1.0), (4, "2", "test-2", 2.0),
+            (5, "2", "test-2", 1.0), (6, "1", "test-1", 1.0)]
+    df = pd.DataFrame(rows, columns=["t i d", "x x", "y y", "z z"])
+    got, want, _ = PU.run_both_frame(df, "t i d", [{"type": "null"}], thres=10, opts=FAST)
+    assert got == want
+    assert [(g[0], g[1]) for g in got] == [("1", "y y"), ("2", "x x")]
+
+
+def test_error_paths():
+    from repair import RepairModel
+    from repair.utils import AnalysisException
+    df = pd.DataFrame([(1, 1, None), (1, 1, "test-1"), (1, 2, "test-1")], columns=["tid", "x", "y"])
+    with pytest.raises(AnalysisException, match="Uniqueness does not hold in column 'tid'"):
+        RepairModel().setInput(df).setRowId("tid").run()
+    df = pd.DataFrame([(1, None), (2, "test-1")], columns=["tid", "x"])
+    with pytest.raises(AnalysisException, match="A least three columns"):
+        RepairModel().setInput(df).setRowId("tid").run()
+    # tests/test_model.py:797-815: no discretizable feature
+    df = pd.DataFrame([(1, "1", None), (2, "1", None), (3, "1", "test-1"), (4, "1", "test-1"), (5, "1", "test-1"),
+                       (6, "1", None)], columns=["tid", "x", "y"])
+    from repair.errors import NullErrorDetector
+    with pytest.raises(ValueError, match="At least one valid discretizable feature is needed"):
+        RepairModel().setInput(df).setRowId("tid").setErrorDetectors([NullErrorDetector()]).run()
+
+
+def test_standalone_detector_protocol():
+    # ErrorDetector.setUp(...).detect() as tests/test_errors.py drives it
+    from repair.errors import ConstraintErrorDetector, NullErrorDetector, RegExErrorDetector
+    df = adult()
+    out = NullErrorDetector().setUp("tid", df, [], ["Sex", "Age", "Income"]).detect()
+    assert sorted(zip(out.tid.tolist(), out.attribute.tolist())) == \
+        [(3, "Sex"), (5, "Age"), (5, "Income"), (7, "Sex"), (12, "Age"), (12, "Sex"), (16, "Income")]
+    out = RegExErrorDetector("Country", "United-States").setUp("tid", df, [], ["Unknown", "Country"]).detect()
+    assert sorted(out.tid.tolist()) == [7, 19]
+    path = os.path.join(GOLDEN, "adult_constraints.txt")
+    out = ConstraintErrorDetector(path, targets=["Relationship"]).setUp("tid", df, [], ["Relationship", "Sex"]).detect()
+    assert sorted(zip(out.tid.tolist(), out.attribute.tolist())) == [(4, "Relationship"), (11, "Relationship")]
+    out = NullErrorDetector().setUp("tid", df, [], ["Non-existent"]).detect()
+    assert len(out) == 0

@@ -1,0 +1,394 @@
+"""CPU-only tests: the host logic above the C ABI, the API contract of the reference, the shared
+library's exports, and the oracle's forest evaluator against scikit-learn."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import parity_utils  # noqa: F401  (sys.path)
+from conftest import GOLDEN, ROOT
+
+
+# ------------------------------------------------------------------ C ABI
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "b200repair.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dr_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from repair import _native
+    lib = _native.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for sym in declared:
+        assert hasattr(lib, sym), "missing export: " + sym
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared
+    assert lib.dr_abi_version() == 1
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        getattr(raw, sym)
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from repair import RepairModel
+    from repair._native import NativeError
+    df = pd.read_csv(os.path.join(GOLDEN, "adult.csv"))
+    with pytest.raises(NativeError, match="no CPU fallback"):
+        RepairModel().setInput(df).setRowId("tid").run()
+
+
+# ------------------------------------------------------------------ API contract (tests/test_model.py:98-317)
+def test_invalid_params():
+    from repair import RepairModel
+    from repair.costs import Levenshtein
+    df = pd.read_csv(os.path.join(GOLDEN, "adult.csv"))
+    msg = "`setInput` and `setRowId` should be called before repairing"
+    for f in (lambda: RepairModel().run(), lambda: RepairModel().setTableName("dummyTab").run(),
+              lambda: RepairModel().setInput("dummyTab").run()):
+        with pytest.raises(ValueError, match=msg):
+            f()
+    with pytest.raises(ValueError, match="Can not specify a database name when input is `DataFrame`"):
+        RepairModel().setInput(df).setDbName("default")
+    with pytest.raises(ValueError, match="`setRepairDelta` should be called when enabling maximal likelihood"):
+        RepairModel().setTableName("dummyTab").setRowId("dummyId").run(maximal_likelihood_repair=True)
+    with pytest.raises(ValueError, match="`setUpdateCostFunction` should be called when enabling maximal"):
+        RepairModel().setInput("dummyTab").setRowId("dummyId").setRepairDelta(3).run(maximal_likelihood_repair=True)
+    with pytest.raises(ValueError, match="`UpdateCostFunction.targets` cannot be used when enabling maximal"):
+        RepairModel().setInput("dummyTab").setRowId("dummyId").setRepairDelta(3) \
+            .setUpdateCostFunction(Levenshtein(targets=["non-existent"])).run(maximal_likelihood_repair=True)
+    with pytest.raises(ValueError, match="`attrs` should have at least one attribute"):
+        RepairModel().setTargets([])
+    with pytest.raises(ValueError, match="`thres` should be bigger than 1, got 0"):
+        RepairModel().setDiscreteThreshold(0)
+    with pytest.raises(ValueError, match="`table_name` should have at least character"):
+        RepairModel().setTableName("")
+    with pytest.raises(ValueError, match="`table_name` should have at least character"):
+        RepairModel().setInput("")
+    with pytest.raises(ValueError, match="`row_id` should have at least character"):
+        RepairModel().setRowId("")
+    with pytest.raises(ValueError, match="Repair delta should be positive, got -1"):
+        RepairModel().setRepairDelta(-1)
+    with pytest.raises(ValueError, match="`error_cells` should have at least character"):
+        RepairModel().setErrorCells("")
+    with pytest.raises(ValueError, match="`setRowId` should be called before specifying error cells"):
+        RepairModel().setErrorCells(df)
+    with pytest.raises(ValueError, match="Error cells should have `tid` and `attribute` in columns"):
+        RepairModel().setInput(df).setRowId("tid").setErrorCells(df)
+
+
+def test_exclusive_params():
+    from repair import RepairModel
+    api = RepairModel().setTableName("dummyTab").setRowId("dummyId")
+    for kw in ({"detect_errors_only": True, "compute_repair_candidate_prob": True},
+               {"detect_errors_only": True, "repair_data": True},
+               {"compute_repair_candidate_prob": True, "repair_data": True},
+               {"compute_repair_candidate_prob": True, "compute_repair_prob": True},
+               {"compute_repair_candidate_prob": True, "compute_repair_score": True}):
+        with pytest.raises(ValueError, match="cannot be set to true simultaneously"):
+            api.run(**kw)
+
+
+def test_argtype_check():
+    from repair import RepairModel
+    cases = [
+        (lambda: RepairModel().setDbName(1), "`db_name` should be provided as str, got int"),
+        (lambda: RepairModel().setTableName(1), "`table_name` should be provided as str, got int"),
+        (lambda: RepairModel().setDiscreteThreshold("a"), "`thres` should be provided as int, got str"),
+        (lambda: RepairModel().setInput(1), "`input` should be provided as str/DataFrame, got int"),
+        (lambda: RepairModel().setTargets(1), "`attrs` should be provided as list[str], got int"),
+        (lambda: RepairModel().setTargets(["a", 1]), "`attrs` should be provided as list[str], got int in elements"),
+        (lambda: RepairModel().setErrorDetectors(1), "`detectors` should be provided as list[ErrorDetector], got int"),
+        (lambda: RepairModel().setErrorDetectors([1]),
+         "`detectors` should be provided as list[ErrorDetector], got int in elements"),
+        (lambda: RepairModel().setUpdateCostFunction(1), "`cf` should be provided as UpdateCostFunction, got int"),
+        (lambda: RepairModel().setUpdateCostFunction([1]), "`cf` should be provided as UpdateCostFunction, got list"),
+    ]
+    for f, msg in cases:
+        with pytest.raises(TypeError, match=re.escape(msg)):
+            f()
+
+
+def test_options():
+    from repair import RepairModel
+    with pytest.raises(ValueError, match="Non-existent key specified: key=non-existent"):
+        RepairModel().option("non-existent", "1")
+    keys = [("error.domain_threshold_alpha", "0.0"), ("error.domain_threshold_beta", "0.7"),
+            ("error.max_attrs_to_compute_pairwise_stats", "3"), ("error.max_attrs_to_compute_domains", "2"),
+            ("error.attr_freq_ratio_threshold", "0.0"), ("error.pairwise_freq_ratio_threshold", "0.05"),
+            ("model.max_training_row_num", "100000"), ("model.max_training_column_num", "65536"),
+            ("model.small_domain_threshold", "12"), ("model.rule.repair_by_nearest_values.disabled", "1"),
+            ("model.rule.merge_threshold", "2.0"), ("model.rule.repair_by_regex.disabled", ""),
+            ("model.rule.repair_by_functional_deps.disabled", ""), ("model.rule.max_domain_size", "1000"),
+            ("repair.pmf.cost_weight", "0.1"), ("repair.pmf.prob_threshold", "0.0"), ("repair.pmf.prob_top_k", "80"),
+            ("model.lgb.boosting_type", "gbdt"), ("model.lgb.class_weight", "balanced"),
+            ("model.lgb.learning_rate", "0.01"), ("model.lgb.max_depth", "7"), ("model.lgb.max_bin", "255"),
+            ("model.lgb.reg_alpha", "0.0"), ("model.lgb.min_split_gain", "0.0"), ("model.lgb.n_estimators", "300"),
+            ("model.lgb.importance_type", "gain"), ("model.cv.n_splits", "3"), ("model.hp.timeout", "0"),
+            ("model.hp.max_evals", "10000000"), ("model.hp.no_progress_loss", "50")]
+    for k, v in keys:
+        RepairModel().option(k, v)
+
+
+def test_option_value_parsing(monkeypatch):
+    from repair.utils import get_option_value
+    assert get_option_value({}, "k", 3, int) == 3
+    assert get_option_value({"k": "5"}, "k", 3, int, lambda v: v >= 2, "`{}` should be greater than 1") == 5
+    monkeypatch.delenv("SPARK_TESTING", raising=False)
+    assert get_option_value({"k": "x"}, "k", 3, int) == 3                       # warn + default
+    assert get_option_value({"k": "1"}, "k", 3, int, lambda v: v >= 2, "`{}` bad") == 3
+    monkeypatch.setenv("SPARK_TESTING", "1")
+    with pytest.raises(ValueError, match='Failed to cast "invalid" into float data: key=error.attr_freq'):
+        get_option_value({"error.attr_freq": "invalid"}, "error.attr_freq", 0.0, float)
+    with pytest.raises(ValueError, match="`k` should be greater than 1, got 1"):
+        get_option_value({"k": "1"}, "k", 3, int, lambda v: v >= 2, "`{}` should be greater than 1")
+    assert get_option_value({"b": ""}, "b", True, bool) is False  # bool("") is False (test_model.py:248)
+
+
+def test_detector_constructors_and_strings():
+    from repair.errors import (ConstraintErrorDetector, DomainValues, GaussianOutlierErrorDetector,
+                               NullErrorDetector, RegExErrorDetector)
+    assert str(NullErrorDetector()) == "NullErrorDetector()"
+    assert str(DomainValues("a", ["x"], False, 3)) == 'DomainValues(attr="a",size=1,autofill=False,min_count_thres=3)'
+    assert DomainValues("a", ["x"], autofill=True).values == []
+    assert str(RegExErrorDetector("a", "b.*")) == 'RegExErrorDetector(pattern="b.*")'
+    assert str(GaussianOutlierErrorDetector(True)) == "GaussianOutlierErrorDetector(approx_enabled=True)"
+    with pytest.raises(ValueError, match="At least one of `constraint_path` or `constraints` should be specified"):
+        ConstraintErrorDetector()
+    d = ConstraintErrorDetector(constraints="X->Y", targets=["Y"]).setUp("tid", "t", [], ["X", "Y", "Z"])
+    assert d._targets == ["Y"]
+    d = NullErrorDetector().setUp("tid", "t", [], ["X", "Y"])
+    assert d._targets == ["X", "Y"]
+
+
+# ------------------------------------------------------------------ host logic vs oracle
+def test_constraint_parser_matches_oracle():
+    from oracle import detect as OD
+    from repair import constraints as PC
+    stmts = ['t1&EQ(t1.v1,"abc")&EQ(t1.v2,"def")', "t1&t2&EQ(t1.v1,t2.v1)&IQ(t1.v2,t2.v2)",
+             "t1&t2&LT(t1.v1,t2.v1)&GT(t1.v2,t2.v2)&EQ(t1.v1,t2.v1)", ' t1 & EQ ( t1.v1 , "abc") & EQ ( t1.v2 , "def" ) ',
+             "X->Y", "v1 -> v2", 'EQ(t1.v1,"abc")', "t1&", "t1", "a&b&", "k1&k2", "X=>Y", "", 't1&EQ(t1.v1,"abc")',
+             't1&t2&GT(t3.v0,"abc")&EQ(t1.v1,t2.v1)&IQ(t1.v2,t2.v2)']
+    for s in stmts:
+        try:
+            try:
+                want = OD.parse(s)
+            except Exception:
+                want = OD.parse_alt(s)
+            want = [(p.sign, p.left, p.right, p.right_kind == "attr") for p in want]
+        except Exception:
+            want = "error"
+        try:
+            try:
+                got = PC.parse_denial_constraint(s)
+            except Exception:
+                got = PC.parse_fd_sugar(s)
+            got = [tuple(p) for p in got]
+        except Exception:
+            got = "error"
+        assert got == want, s
+    lines = PC.load_statements(os.path.join(GOLDEN, "hospital_constraints.txt"), "A->B;;C->D")
+    assert len(lines) == 17
+    preds = PC.parse_and_verify(lines, ["tid", "HospitalName", "ZipCode", "A", "B"])
+    assert len(preds) == 2
+    assert PC.classify(preds[0])[0] == "FD" and PC.classify(preds[1]) == ("FD", (["A"], "B"))
+    assert PC.classify(PC.parse_denial_constraint('t1&EQ(t1.Sex,"Female")&EQ(t1.Relationship,"Husband")'))[0] == "CONST"
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&EQ(t1.b,t2.b)"))[0] == "EQ_ONLY"
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.b)"))[0] == "OTHER"
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.b)&IQ(t1.c,t2.c)"))[0] == "OTHER"
+
+
+def _counts(codes_x, dx, codes_y=None, dy=None):
+    if codes_y is None:
+        return np.bincount(codes_x.astype(np.int64) + 1, minlength=dx + 1)
+    idx = (codes_x.astype(np.int64) + 1) * (dy + 1) + codes_y + 1
+    return np.bincount(idx, minlength=(dx + 1) * (dy + 1)).reshape(dx + 1, dy + 1)
+
+
+@pytest.mark.parametrize("having_thr", [0.0, 0.02])
+def test_entropies_and_pair_selection_match_oracle(having_thr):
+    from oracle import stats as OS
+    from oracle.table import OTable
+    from repair import stats_host as SH
+    rng = np.random.default_rng(3)
+    n, doms = 4000, [3, 5, 8, 4, 6]
+    cols = [rng.integers(0, d, size=n) for d in doms]
+    cols[1] = (cols[2] * 3 % 5)
+    for c in cols:
+        c[rng.random(n) < 0.04] = -1
+    names = ["a", "b", "c", "d", "e"]
+    otbl = OTable(["tid"] + names, ["int"] + ["str"] * 5, [np.arange(n, dtype=np.float64)] + cols)
+    ndv = {nm: len(np.unique(c[c >= 0])) for nm, c in zip(names, cols)}
+    targets = ["b", "d"]
+    fs, want_stats, want_pairs = OS.compute_attr_stats(otbl, "tid", targets, ndv, having_thr, 1.0, 2)
+    # product host logic on dense counts
+    hist = {nm: _counts(c, d) for nm, c, d in zip(names, cols, doms)}
+    cands = SH.candidate_pairs(targets, names)
+    col_of = dict(zip(names, zip(cols, doms)))
+    nnz = {frozenset(p): int(np.count_nonzero(_counts(col_of[p[0]][0], col_of[p[0]][1], col_of[p[1]][0], col_of[p[1]][1])))
+           for t in targets for p in cands[t]}
+    pairs = [p for t in targets for p in SH.select_scored(cands[t], nnz, ndv, 1.0, 2)]
+    assert pairs == want_pairs
+    tables = {p: _counts(col_of[p[0]][0], col_of[p[0]][1], col_of[p[1]][0], col_of[p[1]][1]) for p in pairs}
+    got = SH.pairwise_entropies(n, hist, tables, pairs, ndv, SH.having_threshold(n, having_thr))
+    assert set(got) == {k for k, v in want_stats.items() if v}
+    for t in got:
+        assert [a for a, _ in got[t]] == [a for a, _ in want_stats[t]]
+        for (_, h1), (_, h2) in zip(got[t], want_stats[t]):
+            assert abs(h1 - h2) < 1e-12
+    # lower bounds only ever exclude what the exact counts exclude
+    lower = {k: max(1, v // 2) for k, v in nnz.items()}
+    for t in targets:
+        und = SH.undecided(cands[t], lower, ndv, 0.9)
+        assert set(SH.select_scored(cands[t], nnz, ndv, 0.9, 2)) <= set(und)
+
+
+def test_tau_and_discretize_params_match_oracle():
+    from oracle import stats as OS
+    from repair import stats_host as SH
+    assert SH.tau_for(0.5, 1000, 7, 9) == int(0.5 * (1000 // 63))
+    for kind, lo, hi in (("float", 0.00632, 88.9762), ("float", 1e-5, 3.5), ("int", 0, 711), ("float", 0.5, 3.2),
+                         ("float", 187.0, 2.5e7)):
+        assert SH.discretize_params(kind, lo, hi) == OS.discretize_params(kind, lo, hi)
+
+
+def test_double_to_string_matches_oracle():
+    from oracle.table import spark_double_to_string
+    from repair.utils import double_to_string
+    rng = np.random.default_rng(0)
+    vals = [1.0, 3.2, 0.5, 1000.0, 1e7, 1.5e7, 0.001, 0.0001, 123456.789, -2.5e-5, 9999999.0, 0.0, -0.0, 1e-3, 1e22,
+            5e-324, 1.7976931348623157e308] + list(rng.normal(size=200) * 10.0 ** rng.integers(-8, 12, size=200))
+    for v in vals:
+        assert double_to_string(v) == spark_double_to_string(v), v
+    assert double_to_string(1e7) == "1.0E7" and double_to_string(0.0001) == "1.0E-4" and double_to_string(100.0) == "100.0"
+
+
+def test_encoders_match_oracle():
+    from oracle.forest import encode_rows
+    from repair.forest import encode_matrix, first_seen
+    rng = np.random.default_rng(1)
+    n = 300
+    dict_size = {"s": 4, "o": 15}
+    train = {"s": rng.integers(-1, 4, size=n), "o": rng.integers(-1, 12, size=n)}     # codes, -1 = NULL
+    train["s"][train["s"] == 2] = 1                                                 # value 2 unseen in training
+    test = {"s": rng.integers(-1, 4, size=n), "o": rng.integers(-1, 15, size=n)}
+    vals = {"x": np.where(rng.random(n) < 0.1, np.nan, rng.normal(size=n))}
+    for null_in_training in (True, False):
+        tr = {k: (v if null_in_training else np.where(v < 0, 0, v)) for k, v in train.items()}
+        p_enc = [{"attr": "s", "type": "sum", "categories": first_seen(tr["s"])},
+                 {"attr": "x", "type": "cont"},
+                 {"attr": "o", "type": "ordinal", "categories": first_seen(tr["o"])}]
+        o_enc = [dict(e, categories=[None if c < 0 else int(c) for c in e["categories"]]) if "categories" in e else e
+                 for e in p_enc]
+        got = encode_matrix(p_enc, test, vals, dict_size)
+        cols = {"s": [None if c < 0 else int(c) for c in test["s"]], "o": [None if c < 0 else int(c) for c in test["o"]],
+                "x": [None if v != v else float(v) for v in vals["x"]]}
+        want = encode_rows(o_enc, cols)
+        assert got.shape == want.shape
+        assert np.all((got == want) | (np.isnan(got) & np.isnan(want)))
+
+
+def test_select_features_matches_oracle():
+    from oracle.repair import select_features as o_sel
+    from repair.model import select_features as p_sel
+    stats = {"y": [("a", -0.1), ("b", 0.3), ("c", 0.0), ("d", 0.7)]}
+    feats = ["a", "b", "c", "d", "e"]
+    for m in (2, 3, 4, 10):
+        assert p_sel(stats, "y", feats, m) == o_sel(stats, "y", feats, m)
+    assert p_sel({}, "y", feats, 2) == feats
+
+
+# ------------------------------------------------------------------ forest: oracle vs scikit-learn
+@pytest.mark.parametrize("kind", ["binary", "multiclass", "regression"])
+def test_oracle_forest_matches_sklearn(kind):
+    """Pins the oracle's flat-forest evaluator to an independent implementation: margins are
+    bit-identical to HistGradientBoosting's own raw predictions, labels to its predict()."""
+    from oracle.forest import forest_margins, forest_predict, forest_proba
+    from repair.train import build_model
+    rng = np.random.default_rng(0)
+    n = 1500
+    X = rng.integers(0, 6, size=(n, 7)).astype(float)
+    X[rng.random(X.shape) < 0.08] = np.nan
+    base = np.nan_to_num(X[:, 0]) + np.nan_to_num(X[:, 3]) * 2
+    opts = {"model.lgb.n_estimators": "40", "model.lgb.learning_rate": "0.1"}
+    from sklearn.ensemble import HistGradientBoostingClassifier, HistGradientBoostingRegressor
+    common = dict(learning_rate=0.1, max_iter=40, max_depth=7, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255,
+                  l2_regularization=0.0, early_stopping=False, random_state=42)
+    Xt = rng.integers(-1, 7, size=(500, 7)).astype(float)
+    Xt[Xt < 0] = np.nan
+    if kind == "regression":
+        y = base + rng.normal(size=n)
+        forest, classes = build_model(X, y, False, 0, opts)
+        est = HistGradientBoostingRegressor(**common).fit(X, y)
+        assert classes is None
+        assert np.array_equal(forest_predict(forest, Xt), est.predict(Xt))
+        return
+    y = (base.astype(int) % (2 if kind == "binary" else 5))
+    forest, classes = build_model(X, y, True, len(set(y)), opts)
+    est = HistGradientBoostingClassifier(class_weight="balanced", **common).fit(X, y)
+    assert classes == sorted(set(y.tolist()))
+    raw = est._raw_predict(Xt)
+    assert np.array_equal(forest_margins(forest, Xt), raw)
+    pred = np.asarray(classes)[forest_predict(forest, Xt)]
+    assert np.array_equal(pred, est.predict(Xt))
+    assert np.allclose(forest_proba(forest, Xt), est.predict_proba(Xt), atol=1e-12)
+
+
+def test_pack_nodes_roundtrip():
+    from repair.forest import LEAF, pack_nodes
+    from repair.train import random_forest
+    rng = np.random.default_rng(0)
+    f = random_forest(10, 3, 5, [[0.5, 1.5]] * 10, rng)
+    thr, meta = pack_nodes(f)
+    leaf = f["feature"] < 0
+    assert np.array_equal((meta & 0xFFF) == LEAF, leaf)
+    assert np.array_equal((meta & 0xFFF)[~leaf], f["feature"][~leaf])
+    assert np.array_equal(((meta >> 13) & 0x1FF)[~leaf], f["left"][~leaf])
+    assert np.array_equal(((meta >> 22) & 0x1FF)[~leaf], f["right"][~leaf])
+    assert np.array_equal(((meta >> 12) & 1), f["missing_left"])
+    assert np.array_equal(thr[leaf], f["value"][leaf]) and np.array_equal(thr[~leaf], f["threshold"][~leaf])
+    sizes = np.diff(f["tree_offset"])
+    assert sizes.max() <= 61 and len(sizes) == 15
+
+
+# ------------------------------------------------------------------ ingest + synthetic data
+def test_ingest_encoding():
+    from repair.table import EncodedTable
+    from repair.utils import AnalysisException
+    df = pd.DataFrame({"tid": [10, 11, 12, 13], "s": ["b", None, "a", "b"], "i": [3, 1, None, 3],
+                       "f": [0.5, None, 2.5, 0.5]})
+    t = EncodedTable.from_pandas(df, "tid")
+    assert t.names == ["s", "i", "f"] and t.continuous_attrs == ["i", "f"]
+    s, i, f = t.columns
+    assert list(s.dictionary) == ["a", "b"] and s.codes.tolist() == [1, -1, 0, 1]
+    assert i.kind == "float" and i.codes.tolist() == [1, 0, -1, 1]  # pandas float column (NULL present)
+    assert f.strings() == ["0.5", "2.5"] and f.decode([1, -1]) == ["2.5", None]
+    assert s.code_of("b") == 1 and s.code_of("zz") == -2 and s.rank_bounds("aa") == (1, 1)
+    df["b"] = [True, False, True, False]
+    with pytest.raises(AnalysisException, match="unsupported ones found: boolean"):
+        EncodedTable.from_pandas(df, "tid")
+    sh = t.shard(1, 2)
+    assert sh.n_rows == 2 and sh.row_offset == 2 and sh.n_rows_global == 4 and sh.columns[0].codes.tolist() == [0, 1]
+
+
+def test_synthetic_generator_is_shardable_and_deterministic():
+    import torch
+    from repair import synth
+    spec = synth.SynthSpec.c4(50000, 16, seed=3)
+    full = synth.generate_numpy(spec)
+    part = synth.generate_numpy(spec, 12345, 23456)
+    assert all(np.array_equal(part[i], full[i][12345:23456]) for i in range(16))
+    t = synth.generate_torch(spec, "cpu", 1000, 9000, chunk=3000)
+    assert all(np.array_equal(t[i, :8000].numpy(), full[i][1000:9000]) for i in range(16))
+    assert all(full[i].max() < spec.dom[i] and full[i].min() >= -1 for i in range(16))
+    assert all((full[i] < 0).sum() == 0 for i in (4, 5, 12, 13)) and (full[0] < 0).mean() > 0.005
+    dep, det = full[4], full[5]
+    clean = det < spec.dom[5] - 3
+    assert all(len(set(dep[(det == v)].tolist())) == 1 for v in np.unique(det[clean]))
+    assert any(len(set(dep[(det == v)].tolist())) > 1 for v in range(spec.dom[5] - 3, spec.dom[5]))
