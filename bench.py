@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- one "step" = one pass of the hot path (error detection -> attribute statistics ->
+weak-label domain analysis -> repair-model inference -> encoded (tid, attribute, current, repaired)
+frame) over one synthetic N x K categorical table (config C4 of SURVEY.md section 8d).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--cols C] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); rows are sharded (weak scaling: every rank
+holds R rows of one global G*R-row table) and the only exchange is the all-reduce of the count
+tensors.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "spark-data-repair-plugin_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "rows scanned/sec through the full detect+stats+repair pass (cells repaired/sec alongside) " \
+         "on synthetic N x K categorical table"
+N_ESTIMATORS = 300  # train.py:54-56
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--cols", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-rows", type=int, default=20000, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-calls", action="store_true", help="print the per-call timing table to stderr")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# model producer used by both arms: random-init forests of the reference's architecture
+# (300 boosting rounds x one tree per class, depth <= 7, <= 31 leaves) on the REAL encoders of a
+# real training sample -- no data of this size can be fitted inside the benchmark's time budget,
+# and the timed region is inference only.
+# ---------------------------------------------------------------------------------------------
+def _thresholds_for(ctx):
+    out = []
+    for e in ctx["encoders"]:
+        if e["type"] == "cont":
+            out.append([0.0])
+        elif e["type"] == "ordinal":
+            k = len(e["categories"])
+            out.append([-0.5] + [j + 0.5 for j in range(1, max(k, 2))])
+        else:
+            k = len(e["categories"])
+            out += [[-0.5, 0.5]] * (k - 1 if k >= 2 else 0)
+    return out
+
+
+def random_forest_provider(n_iter):
+    def provider(ctx):
+        from repair.train import random_forest
+        n_feat = ctx["X"].shape[1]
+        if ctx["is_discrete"]:
+            classes = sorted(set(int(v) for v in np.asarray(ctx["y_values"]).tolist()))
+            n_classes = len(classes)
+        else:
+            classes, n_classes = None, 1
+        seed = abs(hash(ctx["y"])) % (1 << 31)
+        seed = sum(ord(ch) * (i + 1) for i, ch in enumerate(ctx["y"]))
+        forest = random_forest(n_feat, n_classes, n_iter, _thresholds_for(ctx), np.random.default_rng(seed),
+                               leaf_scale=0.05)
+        return {"forest": forest, "class_codes": classes}
+    return provider
+
+
+def detector_specs(n_cols):
+    from repair import synth
+    specs = [{"type": "null"}]
+    fds = synth.fd_constraints(n_cols)
+    if fds:
+        specs.append({"type": "constraint", "constraints": fds})
+    return specs
+
+
+OPTS = {"error.pairwise_freq_ratio_threshold": "1.0"}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------
+def run_oracle_sample(n_rows, n_cols, n_iter):
+    """One pass of the oracle pipeline over the first `n_rows` rows of the C4 table.
+    -> (seconds, rows, error cells, seconds of the detect phase, threads used)"""
+    from oracle import ckernels
+    from oracle import forest as OF
+    from oracle import repair as OR
+    from oracle.table import OTable
+    from repair import synth
+    threads = 1
+    if ckernels.available():
+        OF.forest_margins = ckernels.forest_margins  # compiled, OpenMP; checked in tests/test_oracle_c.py
+        threads = ckernels.num_threads()
+    spec = synth.SynthSpec.c4(n_rows, n_cols)
+    codes = synth.generate_numpy(spec)
+    names = synth.column_names(n_cols)
+    tbl = OTable(["tid"] + names, ["int"] + ["str"] * n_cols,
+                 [np.arange(n_rows, dtype=np.float64)] + [c.astype(np.int64) for c in codes])
+    rf = random_forest_provider(n_iter)
+
+    def provider(ctx):
+        octx = dict(ctx)
+        octx["encoders"] = [dict(e) for e in ctx["encoders"]]
+        spec_ = rf(octx)
+        return {"forest": spec_["forest"], "classes": spec_["class_codes"]}
+
+    o_opts = {"error.pairwise_freq_ratio_threshold": 1.0}
+    t0 = time.time()
+    cells = OR.run(tbl, "tid", detector_specs(n_cols), None, 80, None, o_opts, provider, detect_errors_only=True)
+    t_detect = time.time() - t0
+    t0 = time.time()
+    out = OR.run(tbl, "tid", detector_specs(n_cols), None, 80, None, o_opts, provider)
+    t_full = time.time() - t0
+    return t_full, n_rows, len(cells), t_detect, threads, len(out)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = run_oracle_sample(args.ref_rows, args.cols, N_ESTIMATORS)
+        if i >= args.warmup:
+            times.append(info[0])
+    t = float(np.mean(times))
+    value = info[1] / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 codes / f64 margins", "data": "synthetic",
+        "config": {"workload": "C4 synthetic {} rows x {} cols (bounded sample of the {}-row table), NULL + FD "
+                               "detectors, 300-round random-init forests".format(info[1], args.cols, args.rows)},
+        "cells_repaired_per_sec": info[2] / max(t - info[3], 1e-9),
+        "rows_scanned_per_sec": info[1] / info[3],
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": info[4], "kind": "port",
+                         "sample": "first {} rows of the C4 table; oracle (NumPy + OpenMP C forest) full pass".format(
+                             info[1])},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def b200_arm(args):
+    import torch
+    from repair import RepairModel, synth
+    from repair._native import profile_summary
+    from repair.engine import Dist, Engine
+    from repair.errors import ErrorModelOptions
+    from repair.model import build_models, repair_cells
+    from repair.table import DeviceTable, EncodedTable
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=device)
+        dist = Dist()
+    n, k = args.rows, args.cols
+    spec = synth.SynthSpec.c4(n * world, k)
+    lo, hi = rank * n, (rank + 1) * n
+
+    # ---- setup (untimed): table in HBM + a pinned host copy for the end-to-end leg ----------
+    codes_dev = synth.generate_torch(spec, device, lo, hi)
+    n_pad = codes_dev.shape[1]
+    host = None
+    if not args.no_e2e:
+        host = torch.empty((k, n_pad), dtype=torch.int32).pin_memory()
+        host.copy_(codes_dev)
+    names = synth.column_names(k)
+    host_np = [host[i, :n].numpy() if host is not None else np.zeros(0, dtype=np.int32) for i in range(k)]
+    table = EncodedTable.from_codes("tid", names, host_np, spec.dom, row_ids=np.arange(lo, hi, dtype=np.int64))
+    table.n_rows = n
+    table.row_offset, table.n_rows_global = lo, n * world
+    dt = DeviceTable(table, device, codes=codes_dev)
+    engine = Engine(table, local, dist=dist, device_table=dt)
+    rm = RepairModel()
+    rm.opts = dict(OPTS)
+    rm.model_provider = random_forest_provider(N_ESTIMATORS)
+    err_opts = ErrorModelOptions.resolve(rm.opts)
+    specs = detector_specs(k)
+    continuous = []
+
+    # frozen models: bookkeeping + encoders from a real training sample, random-init trees
+    res = engine.detect(specs, [], 80, err_opts)
+    if dist is None:
+        models = build_models(rm, engine, table, res, continuous)
+    else:
+        # rank 0's model specs are broadcast so that every shard applies the same forests
+        import torch.distributed as td
+        payload = [None]
+        if rank == 0:
+            built = build_models(rm, engine, table, res, continuous)
+            payload = [[(y, m[0], (m[1] if m[0] == "const" else m[2]["spec"])) for y, m in built]]
+        td.broadcast_object_list(payload, src=0)
+        from repair.forest import DeviceModel
+        tile_col = {c.name: i for i, c in enumerate(table.columns)}
+        dict_sizes = {c.name: c.dict_size for c in table.columns}
+        models = []
+        for y, kind, body in payload[0]:
+            models.append((y, ("const", body) if kind == "const" else
+                           ("forest", DeviceModel(body, tile_col, dict_sizes, {}, device), {"spec": body})))
+    n_trees = sum(m[1].n_trees for _, m in models if m[0] == "forest")
+
+    stats = {}
+
+    def step(e2e):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        if e2e:
+            dt.codes.copy_(host, non_blocking=True)
+        engine.reset()
+        r = engine.detect(specs, [], 80, err_opts)
+        ev[1].record()
+        out = repair_cells(rm, engine, table, r, continuous, models=models, encoded_output=True)
+        ev[2].record()
+        stats["cells"] = rm.last_run["n_error_cells"]
+        stats["dirty"] = rm.last_run["n_dirty_rows"]
+        stats["out_rows"] = sum(len(x[1]) for x in out)
+        stats["d2h"] = sum(x[1].nbytes + x[2].nbytes + x[3].nbytes for x in out)
+        return ev
+
+    def barrier():
+        if dist is not None:
+            dist.td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps, warmup):
+        for _ in range(warmup):
+            step(e2e)
+        barrier()
+        l0 = engine.ctx.launch_count
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        evs = [step(e2e) for _ in range(steps)]
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        tot = sum(e[0].elapsed_time(e[2]) for e in evs) / steps
+        det = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+        t = torch.tensor([tot, det], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.max_(t)
+        return float(t[0]), float(t[1]), (engine.ctx.launch_count - l0), clocks
+
+    ms, ms_det, launches, clocks = timed(False, args.steps, args.warmup)
+    cells = torch.tensor([stats["cells"], stats["out_rows"]], dtype=torch.int64, device=device)
+    if dist is not None:
+        dist.sum_(cells)
+    total_rows = n * world
+    line = {
+        "metric": METRIC, "value": total_rows / (ms / 1e3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 codes / f64 margins", "data": "synthetic",
+        "config": {"workload": "C4 synthetic {} rows x {} cols per GPU ({} rows total), 1% NULLs + 4 FD denial "
+                               "constraints, NULL + Constraint detectors, pairwise_freq_ratio_threshold=1.0, "
+                               "{} frozen repair models ({} trees: 300 rounds x classes, random-init), "
+                               "inputs > L2 (no flush needed)".format(n, k, total_rows, len(models), n_trees),
+                   "rows_per_gpu": n, "cols": k, "parallelism": "rows sharded x{}".format(world)},
+        "rows_scanned_per_sec": total_rows / (ms_det / 1e3),
+        "cells_repaired_per_sec": int(cells[0]) / max((ms - ms_det) / 1e3, 1e-9),
+        "error_cells": int(cells[0]), "repaired_cells_emitted": int(cells[1]),
+        "ms_detect_phase": ms_det, "ms_repair_phase": ms - ms_det,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+
+    # ---- per-kernel timing (CUDA events on the launching stream) and rooflines ------------------
+    engine.ctx.profile = []
+    step(False)
+    prof = profile_summary(engine.ctx)
+    engine.ctx.profile = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    n_disc = k
+    alg = {
+        "scan_hist": 4.0 * n_disc * n,                               # every code read once
+        "forest_predict": stats["cells"] * (4.0 * (k - 1) + 4.0),     # feature gather + fill per cell
+        "gather_rows_masked": stats["dirty"] * 4.0 * k * 2,          # dirty rows in, tile out
+        "cooc": None, "dc_fd_build": None, "dc_fd_flag": None, "domain_score": None,
+    }
+    kernels = {}
+    for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        entry = {"calls": cnt, "ms": round(tms, 3)}
+        if alg.get(name):
+            gbs = alg[name] / (tms / 1e3) / 1e9
+            entry.update({"algorithmic_gb": round(alg[name] / 1e9, 3), "achieved_gbs": round(gbs, 1),
+                          "frac_of_hbm_peak": round(gbs / peak, 4)})
+        kernels[name] = entry
+    dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+    line["kernels"] = kernels
+    if dominant:
+        d = kernels[dominant]
+        ach = d.get("achieved_gbs")
+        line["roofline"] = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src}
+    sh = kernels.get("scan_hist")
+    if sh:
+        line["roofline_scan"] = {"kernel": "k_scan_hist", "bound": "hbm", "achieved": sh.get("achieved_gbs"),
+                                 "peak": peak, "unit": "GB/s", "frac": sh.get("frac_of_hbm_peak"), "traffic": None,
+                                 "peak_source": peak_src}
+    if args.profile_calls and rank == 0:
+        for kname, v in kernels.items():
+            print(kname, v, file=sys.stderr)
+
+    # ---- end to end: host buffers in, host frame out, every step --------------------------------
+    if host is not None:
+        e_ms, _, _, _ = timed(True, max(1, min(args.steps, 3)), 1)
+        line["e2e"] = {"value": total_rows / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
+                       "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(stats["d2h"])}
+
+    # ---- CPU baseline (rank 0, single GPU run only) -----------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_full, rows, ncells, t_det, threads, _ = run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)
+        line["cpu_baseline"] = {"value": rows / t_full, "unit": "rows/s", "cores": threads, "kind": "port",
+                                "sample": "first {} rows of the C4 table, oracle full pass in {:.1f} s "
+                                          "(detect phase {:.1f} s)".format(rows, t_full, t_det),
+                                "cells_repaired_per_sec": ncells / max(t_full - t_det, 1e-9)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.td.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,7 @@ class Context:
 
     def __init__(self, device_index):
         import torch
+        self.profile = None  # set to [] to collect (name, start_event, end_event) per C-ABI call
         if not torch.cuda.is_available():
             raise NativeError("no CUDA device is available; the repair engine has no CPU fallback")
         self.lib = load_library()
@@ -266,3 +267,38 @@ class Context:
     def tile_fill(self, tile, n_cols, col, cells, n_cells, value):
         self._check(self.lib.dr_tile_fill_i32(self._h, _dp(tile), n_cols, col, _dp(cells), n_cells, value,
                                               self._stream()))
+
+
+def _profiled(name, fn):
+    def wrapper(self, *args, **kwargs):
+        if self.profile is None:
+            return fn(self, *args, **kwargs)
+        import torch
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        try:
+            return fn(self, *args, **kwargs)
+        finally:
+            end.record()
+            self.profile.append((name, start, end))
+    wrapper.__name__ = name
+    return wrapper
+
+
+for _name in ("scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
+              "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_gather", "bitmap_clear_rows", "discretize",
+              "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
+              "tile_gather", "lookup_sorted", "forest_predict", "tile_fill"):
+    setattr(Context, _name, _profiled(_name, getattr(Context, _name)))
+
+
+def profile_summary(ctx):
+    """{call name: (count, total milliseconds)} of the calls recorded while ctx.profile was a list
+    (CUDA events on the launching stream)."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, start, end in ctx.profile or []:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + start.elapsed_time(end))
+    return out

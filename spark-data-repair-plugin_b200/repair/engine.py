@@ -537,5 +537,10 @@ class Engine:
         del col
         return rows.cpu().numpy().astype(np.int64), n_valid
 
+    def reset(self):
+        """Forget per-run state so that the same resident table can be processed again."""
+        self._hist_cache = {}
+        self.disc_cols, self.disc_dom = {}, {}
+
     def close(self):
         self.ctx.close()

@@ -383,8 +383,19 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col):
     return ("forest", dm, {"spec": full, "ctx": ctx})
 
 
-def repair_cells(rm, engine, table, res, continuous, repair_data=False):
-    """Phases 2-3 of RepairModel._run (model.py:1311-1408) on the device."""
+def build_models(rm, engine, table, res, continuous):
+    """Training phase: one model per target column, in target order (model.py:1001-1052)."""
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    return [(y, _train_model(rm, engine, table, res, y, continuous, tile_col)) for y in res.target_columns]
+
+
+def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=None, encoded_output=False):
+    """Phases 2-3 of RepairModel._run (model.py:1311-1408) on the device.
+
+    models: frozen output of build_models (skips the training phase).
+    encoded_output: return [(attr, row positions, current codes, repaired codes)] -- the
+    (tid, attribute, current_value, repaired) frame in dictionary-encoded form, already filtered --
+    instead of materialising Python strings."""
     torch = engine.torch
     targets = res.target_columns
     K = len(table.columns)
@@ -395,9 +406,11 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False):
         return rm._input_frame(table) if repair_data else rm._empty_frame(table, repaired=True)
     # models (training phase)
     t0 = time.time()
-    models = [(y, _train_model(rm, engine, table, res, y, continuous, tile_col)) for y in targets]
-    rm.last_run["models"] = models
-    rm.last_run["elapsed_training"] = time.time() - t0
+    if models is None:
+        models = build_models(rm, engine, table, res, continuous)
+        rm.last_run["models"] = models
+        rm.last_run["elapsed_training"] = time.time() - t0
+    models = [(y, m) for y, m in models if y in targets]
     # repair phase: sequential chain over the targets on the dirty-row tile
     t0 = time.time()
     drows, tile, ctile = engine.build_dirty_tile(res, targets)
@@ -429,6 +442,13 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False):
         d_rows = torch.from_numpy(rows.astype(np.int32)).to(engine.device)
         dpos = torch.empty(len(rows), dtype=torch.int32, device=engine.device)
         engine.ctx.lookup_sorted(drows, D, d_rows, len(rows), dpos)
+        if encoded_output and not col.continuous:
+            out = torch.empty(len(rows), dtype=torch.int32, device=engine.device)
+            engine.ctx.tile_gather(tile, K, tile_col[a], dpos, len(rows), out)
+            codes = out.cpu().numpy()
+            keep = (codes < 0) | (codes != cur)
+            repaired_cells.append((a, rows[keep], cur[keep], codes[keep]))
+            continue
         cur_s = col.decode(cur)
         if col.continuous:
             out = torch.empty(len(rows), dtype=torch.float64, device=engine.device)
@@ -447,8 +467,10 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False):
         curs += cur_s
         reps += rep_s
     rm.last_run["elapsed_repair"] = time.time() - t0
-    rm.last_run["n_error_cells"] = len(attrs)
+    rm.last_run["n_error_cells"] = sum(len(r) for _, r, _ in cells)
     rm.last_run["n_dirty_rows"] = D
+    if encoded_output:
+        return repaired_cells
     if repair_data:
         return _apply_repairs(rm, table, repaired_cells)
     frame = DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs,
