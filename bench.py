@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-rows", type=int, default=20000, help="rows of the CPU baseline sample")
+    ap.add_argument("--ref-rows", type=int, default=10000, help="rows of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-calls", action="store_true", help="print the per-call timing table to stderr")
@@ -65,6 +65,8 @@ def _thresholds_for(ctx):
 
 
 def random_forest_provider(n_iter):
+    cache = {}
+
     def provider(ctx):
         from repair.train import random_forest
         n_feat = ctx["X"].shape[1]
@@ -73,11 +75,12 @@ def random_forest_provider(n_iter):
             n_classes = len(classes)
         else:
             classes, n_classes = None, 1
-        seed = abs(hash(ctx["y"])) % (1 << 31)
         seed = sum(ord(ch) * (i + 1) for i, ch in enumerate(ctx["y"]))
-        forest = random_forest(n_feat, n_classes, n_iter, _thresholds_for(ctx), np.random.default_rng(seed),
-                               leaf_scale=0.05)
-        return {"forest": forest, "class_codes": classes}
+        thr = _thresholds_for(ctx)
+        key = (ctx["y"], n_feat, tuple(classes or ()), tuple(len(t) for t in thr))
+        if key not in cache:  # building the forest is the model producer's cost, not inference
+            cache[key] = random_forest(n_feat, n_classes, n_iter, thr, np.random.default_rng(seed), leaf_scale=0.05)
+        return {"forest": cache[key], "class_codes": classes}
     return provider
 
 
@@ -96,6 +99,9 @@ OPTS = {"error.pairwise_freq_ratio_threshold": "1.0"}
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on a bounded sample of the same workload
 # ---------------------------------------------------------------------------------------------
+_ORACLE_RF = {}
+
+
 def run_oracle_sample(n_rows, n_cols, n_iter):
     """One pass of the oracle pipeline over the first `n_rows` rows of the C4 table.
     -> (seconds, rows, error cells, seconds of the detect phase, threads used)"""
@@ -113,7 +119,7 @@ def run_oracle_sample(n_rows, n_cols, n_iter):
     names = synth.column_names(n_cols)
     tbl = OTable(["tid"] + names, ["int"] + ["str"] * n_cols,
                  [np.arange(n_rows, dtype=np.float64)] + [c.astype(np.int64) for c in codes])
-    rf = random_forest_provider(n_iter)
+    rf = _ORACLE_RF.setdefault(n_iter, random_forest_provider(n_iter))  # forests are built once
 
     def provider(ctx):
         octx = dict(ctx)
@@ -137,6 +143,7 @@ def reference_arm(args):
         return
     times = []
     info = None
+    run_oracle_sample(args.ref_rows, args.cols, N_ESTIMATORS)  # untimed: builds the frozen forests
     for i in range(args.warmup + args.steps):
         info = run_oracle_sample(args.ref_rows, args.cols, N_ESTIMATORS)
         if i >= args.warmup:
@@ -224,7 +231,7 @@ def b200_arm(args):
     n_pad = codes_dev.shape[1]
     host = None
     if not args.no_e2e:
-        host = torch.empty((k, n_pad), dtype=torch.int32).pin_memory()
+        host = torch.empty((k, n_pad), dtype=torch.int32, pin_memory=True)
         host.copy_(codes_dev)
     names = synth.column_names(k)
     host_np = [host[i, :n].numpy() if host is not None else np.zeros(0, dtype=np.int32) for i in range(k)]
@@ -374,6 +381,7 @@ def b200_arm(args):
 
     # ---- CPU baseline (rank 0, single GPU run only) -----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)  # untimed: builds the frozen forests
         t_full, rows, ncells, t_det, threads, _ = run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)
         line["cpu_baseline"] = {"value": rows / t_full, "unit": "rows/s", "cores": threads, "kind": "port",
                                 "sample": "first {} rows of the C4 table, oracle full pass in {:.1f} s "
