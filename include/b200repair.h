@@ -232,6 +232,35 @@ typedef struct dr_forest {
 } dr_forest;
 int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n_cols, double* ctile, int n_ccols,
                       const int32_t* cells, int64_t n_cells, int target_col, double* out_margin, void* stream);
+/* Rank-coded variant for all-discrete models (the common case: every feature is a label-encoded
+ * attribute).  An encoded feature then takes only a handful of distinct values, so the host replaces
+ * every value by its RANK among the feature's sorted distinct values (255 = NaN) and every threshold
+ * by the number of values <= threshold: `x <= thr` becomes `rank < thr_rank` -- same decisions, but a
+ * node is ONE 32-bit word and a cell's feature vector is one byte per feature, which is what lets
+ * 16+ warps per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins
+ * remain bit-identical to dr_forest_predict / the oracle.
+ *   node word: bits 21..31 feature (0x7FF = leaf), 13..20 thr_rank, bit 12 NaN-goes-left,
+ *              bits 6..11 left child, bits 0..5 right child (relative to the tree root; trees have
+ *              at most 64 nodes); leaf: bits 0..20 = leaf index within the tree.
+ *   rank_lut:  uint8, feature f of a row = rank_lut[rank_lut_off[f] + tile[row][feat_col[f]] + 1]
+ *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels). */
+typedef struct dr_forest_ranked {
+    int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth;
+    const int32_t* seq_tree_off;
+    const int32_t* tree_node_off;
+    const int32_t* tree_leaf_off;
+    const uint32_t* node_word;
+    const double* leaf_value;
+    const double* baseline;
+    const int32_t* feat_col;
+    const int32_t* rank_lut_off;
+    const uint8_t* rank_lut;
+    const int32_t* class_code;
+    int32_t n_classes;
+} dr_forest_ranked;
+int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* forest, int32_t* tile, int n_cols,
+                             const int32_t* cells, int64_t n_cells, int target_col, double* out_margin,
+                             void* stream);
 /* PoorModel (model.py:44-61): constant fill of the listed tile rows. */
 int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int32_t* cells, int64_t n_cells,
                      int32_t value, void* stream);

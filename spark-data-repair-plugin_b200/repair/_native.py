@@ -28,6 +28,16 @@ class dr_forest(ctypes.Structure):
     ]
 
 
+class dr_forest_ranked(ctypes.Structure):
+    _fields_ = [
+        ("n_seq", c_int32), ("n_trees", c_int32), ("n_nodes", c_int32), ("n_leaves", c_int32),
+        ("n_feat", c_int32), ("max_depth", c_int32),
+        ("seq_tree_off", c_void_p), ("tree_node_off", c_void_p), ("tree_leaf_off", c_void_p),
+        ("node_word", c_void_p), ("leaf_value", c_void_p), ("baseline", c_void_p), ("feat_col", c_void_p),
+        ("rank_lut_off", c_void_p), ("rank_lut", c_void_p), ("class_code", c_void_p), ("n_classes", c_int32),
+    ]
+
+
 _PP = POINTER(c_void_p)
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -70,6 +80,8 @@ _SIGNATURES = {
     "dr_lookup_sorted": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_forest_predict": (c_int, [c_void_p, POINTER(dr_forest), c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
                                   c_int, c_void_p, c_void_p]),
+    "dr_forest_predict_ranked": (c_int, [c_void_p, POINTER(dr_forest_ranked), c_void_p, c_int, c_void_p, c_int64,
+                                         c_int, c_void_p, c_void_p]),
     "dr_tile_fill_i32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int32, c_void_p]),
 }
 
@@ -264,6 +276,10 @@ class Context:
         self._check(self.lib.dr_forest_predict(self._h, byref(forest_struct), _dp(tile), n_cols, _dp(ctile), n_ccols,
                                                _dp(cells), n_cells, target_col, _dp(out_margin), self._stream()))
 
+    def forest_predict_ranked(self, forest_struct, tile, n_cols, cells, n_cells, target_col, out_margin=None):
+        self._check(self.lib.dr_forest_predict_ranked(self._h, byref(forest_struct), _dp(tile), n_cols, _dp(cells),
+                                                      n_cells, target_col, _dp(out_margin), self._stream()))
+
     def tile_fill(self, tile, n_cols, col, cells, n_cells, value):
         self._check(self.lib.dr_tile_fill_i32(self._h, _dp(tile), n_cols, col, _dp(cells), n_cells, value,
                                               self._stream()))
@@ -288,7 +304,7 @@ def _profiled(name, fn):
 for _name in ("scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
-              "tile_gather", "lookup_sorted", "forest_predict", "tile_fill"):
+              "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))
 
 

@@ -122,6 +122,75 @@ def group_by_sequence(forest):
     return off, order
 
 
+def rank_code(spec, dict_sizes):
+    """Rank-coded image of an all-discrete model for dr_forest_predict_ranked, or None when the
+    model does not qualify (continuous feature, > 254 distinct values per feature, a tree with more
+    than 64 nodes, > 2046 features).  Decisions are unchanged: `x <= thr` <=> `rank(x) < #values <= thr`."""
+    f = spec["forest"]
+    encoders = spec["encoders"]
+    if any(e["type"] == "cont" for e in encoders) or spec.get("class_codes") is None:
+        return None
+    luts, feat_attr = [], []
+    for e in encoders:
+        lut = encoder_lut(e, dict_sizes[e["attr"]])
+        for j in range(lut.shape[1]):
+            luts.append(lut[:, j])
+            feat_attr.append(e["attr"])
+    n_feat = len(luts)
+    if n_feat != int(f["n_features"]) or n_feat >= 2047:
+        return None
+    toff = np.asarray(f["tree_offset"], dtype=np.int64)
+    sizes = toff[1:] - toff[:-1]
+    if len(sizes) and sizes.max() > 64:
+        return None
+    rank_lut, rank_off, values = [], [0], []
+    for col in luts:
+        vals = np.unique(col[~np.isnan(col)])
+        if len(vals) > 254:
+            return None
+        r = np.full(len(col), 255, dtype=np.uint8)
+        ok = ~np.isnan(col)
+        r[ok] = np.searchsorted(vals, col[ok]).astype(np.uint8)
+        rank_lut.append(r)
+        rank_off.append(rank_off[-1] + len(r))
+        values.append(vals)
+    feat = np.asarray(f["feature"], dtype=np.int64)
+    is_leaf = feat < 0
+    thr = np.asarray(f["threshold"], dtype=np.float64)
+    thr_rank = np.zeros(len(feat), dtype=np.uint32)
+    for j in range(n_feat):  # number of distinct values <= threshold, per feature
+        m = feat == j
+        if m.any():
+            thr_rank[m] = np.searchsorted(values[j], thr[m], side="right")
+    tree_of = np.repeat(np.arange(len(sizes)), sizes)
+    leaf_cum = np.cumsum(is_leaf) - is_leaf                      # leaves before each node
+    tree_leaf_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    tree_leaf_off[:-1] = leaf_cum[toff[:-1]] if len(sizes) else 0
+    tree_leaf_off[-1] = int(is_leaf.sum())
+    leaf_idx = leaf_cum - tree_leaf_off[tree_of] if len(feat) else leaf_cum
+    word = np.where(
+        is_leaf, (np.uint32(0x7FF) << np.uint32(21)) | leaf_idx.astype(np.uint32),
+        (np.where(is_leaf, 0, feat).astype(np.uint32) << np.uint32(21)) | (thr_rank << np.uint32(13)) |
+        ((np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)) << np.uint32(12)) |
+        ((np.asarray(f["left"], dtype=np.uint32) & np.uint32(0x3F)) << np.uint32(6)) |
+        (np.asarray(f["right"], dtype=np.uint32) & np.uint32(0x3F))).astype(np.uint32)
+    # deepest leaf: breadth-first sweep over all trees at once
+    depth, frontier = 0, toff[:-1].copy()
+    base = toff[:-1].copy()
+    left, right = np.asarray(f["left"], dtype=np.int64), np.asarray(f["right"], dtype=np.int64)
+    while True:
+        inner = ~is_leaf[frontier] if len(frontier) else np.zeros(0, dtype=bool)
+        if not inner.any():
+            break
+        fr, bs = frontier[inner], base[inner]
+        frontier = np.concatenate([bs + left[fr], bs + right[fr]])
+        base = np.concatenate([bs, bs])
+        depth += 1
+    return {"word": word, "leaf_value": np.asarray(f["value"], dtype=np.float64)[is_leaf],
+            "tree_leaf_off": tree_leaf_off, "rank_lut": np.concatenate(rank_lut) if rank_lut else np.zeros(1, np.uint8),
+            "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth}
+
+
 class DeviceModel:
     """Device image of one repair model (forest + encoder LUTs) ready for dr_forest_predict."""
 
@@ -186,3 +255,45 @@ class DeviceModel:
         self.n_seq = s.n_seq
         self.n_trees = s.n_trees
         self.n_nodes = s.n_nodes
+        self.ranked = None
+        rk = rank_code(spec, dict_sizes) if self.kind == 0 else None
+        if rk is not None:
+            from ._native import dr_forest_ranked
+            lo = rk["tree_leaf_off"]
+            leaf_sizes = (lo[1:] - lo[:-1])[order]
+            new_lo = np.zeros(len(order) + 1, dtype=np.int64)
+            new_lo[1:] = np.cumsum(leaf_sizes)
+            lidx = np.concatenate([np.arange(lo[t], lo[t + 1]) for t in order]) if len(order) else \
+                np.zeros(0, dtype=np.int64)
+            self._keep.update({
+                "r_node_word": dev(rk["word"][idx].view(np.int32) if len(idx) else np.zeros(1, np.int32), np.int32),
+                "r_leaf_value": dev(rk["leaf_value"][lidx] if len(lidx) else np.zeros(1), np.float64),
+                "r_tree_leaf_off": dev(new_lo, np.int32),
+                "r_rank_lut": dev(rk["rank_lut"], np.uint8),
+                "r_rank_lut_off": dev(rk["rank_lut_off"], np.int32),
+                "r_feat_col": dev([feature_tile_cols[a] for a in rk["feat_attr"]] or [0], np.int32),
+            })
+            r = dr_forest_ranked()
+            r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, s.n_nodes, len(lidx)
+            r.n_feat, r.max_depth = n_feat, int(rk["max_depth"])
+            r.seq_tree_off = self._keep["seq_tree_off"].data_ptr()
+            r.tree_node_off = self._keep["tree_node_off"].data_ptr()
+            r.tree_leaf_off = self._keep["r_tree_leaf_off"].data_ptr()
+            r.node_word = self._keep["r_node_word"].data_ptr()
+            r.leaf_value = self._keep["r_leaf_value"].data_ptr()
+            r.baseline = self._keep["baseline"].data_ptr()
+            r.feat_col = self._keep["r_feat_col"].data_ptr()
+            r.rank_lut_off = self._keep["r_rank_lut_off"].data_ptr()
+            r.rank_lut = self._keep["r_rank_lut"].data_ptr()
+            r.class_code = self._keep["class_code"].data_ptr()
+            r.n_classes = s.n_classes
+            self.ranked = r
+
+    def predict(self, ctx, tile, n_cols, ctile, n_ccols, cells, n_cells, target_col, out_margin=None,
+                force_generic=False):
+        """Fills the target column of the listed tile rows in place (rank-coded kernel when the model
+        qualifies, the generic float64 kernel otherwise)."""
+        if self.ranked is not None and not force_generic:
+            ctx.forest_predict_ranked(self.ranked, tile, n_cols, cells, n_cells, target_col, out_margin)
+        else:
+            ctx.forest_predict(self.struct, tile, n_cols, ctile, n_ccols, cells, n_cells, target_col, out_margin)

@@ -432,8 +432,7 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
                 engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, int(m[1]))
             continue
         dm = m[1]
-        engine.ctx.forest_predict(dm.struct, tile, K, ctile, n_cc, todo, n,
-                                  cont_idx[y] if ycol.continuous else tile_col[y])
+        dm.predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
     # output: (row id, attribute, current_value, repaired) for the error cells
     ids, attrs, curs, reps = [], [], [], []
     repaired_cells = []

@@ -397,3 +397,43 @@ def test_domain_score_matches_oracle(ctx):
             else:
                 assert t1[i] == -1
             assert bool(wk[i]) == ((r, "t") in weak_want)
+
+
+@pytest.mark.parametrize("n_classes,n_iter,n", [(2, 9, 300), (5, 33, 2000), (64, 300, 1500)])
+def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter, n):
+    """All-discrete model: rank-coded kernel == generic kernel == oracle, margins bit-exact."""
+    from oracle.forest import forest_margins, forest_predict
+    from repair.forest import DeviceModel, encode_matrix, encoder_width
+    from repair.train import random_forest
+    rng = np.random.default_rng(n_classes + n)
+    doms = [7, 4, 30, 3, 9, 64, 2, 12]
+    k = len(doms)
+    tile_np = np.stack(rand_cols(rng, n, doms, null_p=0.08), axis=1).astype(np.int32)
+    names = ["a%d" % i for i in range(k)]
+    encoders = []
+    for i in range(1, k):
+        cats = list(rng.permutation(doms[i]))[: doms[i] - (i % 3 == 0)]       # sometimes an unseen value
+        if i % 2:
+            cats.insert(1, -1)                                                 # NULL seen in training
+        encoders.append({"attr": names[i], "type": "sum" if doms[i] < 12 else "ordinal",
+                         "categories": [int(c) for c in cats]})
+    n_feat = sum(encoder_width(e) for e in encoders)
+    thr = []
+    for e in encoders:
+        kk = len(e["categories"])
+        thr += [[-0.5, 0.5]] * (kk - 1) if e["type"] == "sum" else [[-1.0] + [j + 0.5 for j in range(1, kk)]]
+    forest = random_forest(n_feat, n_classes, n_iter, thr, rng, leaf_scale=0.1)
+    spec = {"forest": forest, "encoders": encoders, "class_codes": list(range(max(n_classes, 2))), "integral": False}
+    tile_cols = {nm: i for i, nm in enumerate(names)}
+    dict_sizes = dict(zip(names, doms))
+    dm = DeviceModel(spec, tile_cols, dict_sizes, {}, torch.device("cuda", 0))
+    assert dm.ranked is not None
+    cells = np.sort(rng.choice(n, size=n * 2 // 3, replace=False)).astype(np.int32)
+    X = encode_matrix(encoders, {nm: tile_np[cells, tile_cols[nm]] for nm in names[1:]}, {}, dict_sizes)
+    want_m, want = forest_margins(forest, X), forest_predict(forest, X)
+    for generic in (False, True):
+        tile = dev(tile_np)
+        margins = torch.empty((len(cells), dm.n_seq), dtype=torch.float64, device="cuda")
+        dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=generic)
+        assert np.array_equal(margins.cpu().numpy(), want_m), generic
+        assert np.array_equal(tile.cpu().numpy()[cells, 0], want.astype(np.int32))

@@ -392,3 +392,49 @@ def test_synthetic_generator_is_shardable_and_deterministic():
     clean = det < spec.dom[5] - 3
     assert all(len(set(dep[(det == v)].tolist())) == 1 for v in np.unique(det[clean]))
     assert any(len(set(dep[(det == v)].tolist())) > 1 for v in range(spec.dom[5] - 3, spec.dom[5]))
+
+
+def _eval_ranked(rk, forest, codes_by_feat):
+    """Reference evaluation of the rank-coded layout (what k_forest_predict_ranked does)."""
+    n = len(codes_by_feat[0])
+    toff = np.asarray(forest["tree_offset"])
+    S = len(forest["baseline"])
+    raw = np.tile(np.asarray(forest["baseline"], dtype=np.float64), (n, 1))
+    ranks = [rk["rank_lut"][rk["rank_lut_off"][j] + codes_by_feat[j] + 1] for j in range(len(codes_by_feat))]
+    for t in range(len(toff) - 1):
+        for i in range(n):
+            w = int(rk["word"][toff[t]])
+            for _ in range(rk["max_depth"]):
+                feat = w >> 21
+                if feat == 0x7FF:
+                    break
+                r = int(ranks[feat][i])
+                go_left = ((w >> 12) & 1) if r == 255 else (r < ((w >> 13) & 0xFF))
+                w = int(rk["word"][toff[t] + (((w >> 6) & 0x3F) if go_left else (w & 0x3F))])
+            assert (w >> 21) == 0x7FF
+            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + (w & 0x1FFFFF)]
+    return raw
+
+
+def test_rank_coded_forest_makes_the_same_decisions():
+    from oracle.forest import forest_margins
+    from repair.forest import encode_matrix, encoder_width, rank_code
+    from repair.train import random_forest
+    rng = np.random.default_rng(4)
+    dict_sizes = {"a": 5, "b": 14, "c": 3}
+    encoders = [{"attr": "a", "type": "sum", "categories": [2, -1, 0, 4]},
+                {"attr": "b", "type": "ordinal", "categories": list(range(13))},
+                {"attr": "c", "type": "sum", "categories": [1, 0, 2]}]
+    n_feat = sum(encoder_width(e) for e in encoders)
+    thr = [[-1.5, -0.5, 0.5, 1.5]] * 3 + [[-3.0, -1.0, 0.5, 3.5, 7.5, 12.5, 20.0]] + [[-0.5, 0.5]] * 2
+    forest = random_forest(n_feat, 3, 6, thr, rng, leaf_scale=0.2)
+    spec = {"forest": forest, "encoders": encoders, "class_codes": [0, 1, 2]}
+    rk = rank_code(spec, dict_sizes)
+    assert rk is not None and rk["max_depth"] <= 7
+    n = 200
+    codes = {a: rng.integers(-1, d, size=n) for a, d in dict_sizes.items()}
+    X = encode_matrix(encoders, codes, {}, dict_sizes)
+    by_feat = [codes[a] for a in rk["feat_attr"]]
+    assert np.array_equal(_eval_ranked(rk, forest, by_feat), forest_margins(forest, X))
+    spec["encoders"] = encoders + [{"attr": "x", "type": "cont"}]
+    assert rank_code(spec, dict_sizes) is None  # continuous feature -> generic kernel
