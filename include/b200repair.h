@@ -117,6 +117,10 @@ int dr_bitmap_andnot(dr_ctx* ctx, uint32_t* dst, const uint32_t* src, int64_t n_
 int dr_bitmap_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int64_t* out_count, void* stream);
 int dr_bitmap_to_rows(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t capacity,
                       int64_t* out_count, void* stream);
+/* Second half of the ordered compaction when the count was already taken: must directly follow
+ * dr_bitmap_count on the SAME bitmap (it reuses the per-block offsets left in the context scratch). */
+int dr_bitmap_rows_after_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows,
+                               int64_t capacity, void* stream);
 int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int64_t n, uint32_t* out,
                      void* stream);
 int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,
@@ -181,6 +185,10 @@ int dr_tile_null_bitmap(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols,
                         void* stream);
 int dr_tile_null_bitmap_f64(dr_ctx* ctx, const double* tile, int64_t n, int n_cols, int col, uint32_t* out,
                             void* stream);
+/* All columns at once: out[c * words_per_col + w] (one coalesced pass over the tile; a model only
+ * ever fills its own column, so the bitmaps taken before the chain stay valid for every target). */
+int dr_tile_null_bitmaps(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols, int64_t words_per_col,
+                         uint32_t* out, void* stream);
 /* out[i] = col[rows[i]]  (current values of error cells, RepairApi.withCurrentValues :69-104). */
 int dr_gather_i32(dr_ctx* ctx, const int32_t* col, const int32_t* rows, int64_t n, int32_t* out, void* stream);
 int dr_gather_f64(dr_ctx* ctx, const double* col, const int32_t* rows, int64_t n, double* out, void* stream);
@@ -239,10 +247,13 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  * node is ONE 32-bit word and a cell's feature vector is one byte per feature, which is what lets
  * 16+ warps per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins
  * remain bit-identical to dr_forest_predict / the oracle.
- *   node word: bits 21..31 feature (0x7FF = leaf), 13..20 thr_rank, bit 12 NaN-goes-left,
- *              bits 6..11 left child, bits 0..5 right child (relative to the tree root; trees have
- *              at most 64 nodes); leaf: bits 0..20 = leaf index within the tree.
- *   rank_lut:  uint8, feature f of a row = rank_lut[rank_lut_off[f] + tile[row][feat_col[f]] + 1]
+ *   node word: bits 21..31 feature, bit 20 NaN-goes-left, bits 12..19 thr_rank + 1, bits 6..11 left
+ *              child, bits 0..5 right child (relative to the tree root; trees have at most 64 nodes).
+ *              A LEAF points at itself (left = right = own index) with feature 0 and its leaf index
+ *              (within the tree, < 256) in bits 12..19, so the walk is branch-free.
+ *   rank_lut:  uint8, rank (0..253) of feature f of a row = rank_lut[rank_lut_off[f] +
+ *              tile[row][feat_col[f]] + 1], 255 = NaN; the kernel compares (rank + 1) < (thr_rank + 1)
+ *              with NaN mapped to 0 / 255 according to the node's NaN direction.
  *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels). */
 typedef struct dr_forest_ranked {
     int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth;

@@ -205,6 +205,24 @@ __global__ void __launch_bounds__(kThreads) k_tile_null_bitmap(const T* __restri
     }
 }
 
+// NULL bitmaps of ALL columns of the row-major tile in one pass: a warp takes 32 rows (lane = row,
+// each lane walks its own 4*K-byte row, which stays L1-resident), one ballot per column.
+__global__ void __launch_bounds__(kThreads) k_tile_null_bitmaps(const int32_t* __restrict__ tile, int64_t n, int K,
+                                                                int64_t words_per_col, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_groups = (n + 31) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+        const int64_t i = (grp << 5) + lane;
+        const int32_t* row = tile + (i < n ? i : 0) * K;
+        for (int c = 0; c < K; ++c) {
+            const bool bit = i < n && row[c] < 0;
+            const unsigned w = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) out[(int64_t)c * words_per_col + grp] = w;
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_gather(const T* __restrict__ col, const int32_t* __restrict__ rows,
                                                      int64_t n, int64_t row_stride, int64_t col_off,
@@ -316,6 +334,32 @@ int dr_bitmap_to_rows(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32
     DR_CUDA(ctx, cudaStreamSynchronize(st));
     *out_count = (int64_t) * (unsigned long long*)ctx->pinned;
     if (*out_count > capacity) return dr_fail(ctx, DR_ERR_INVALID, "dr_bitmap_to_rows: capacity too small");
+    return DR_OK;
+}
+
+int dr_bitmap_rows_after_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows,
+                               int64_t capacity, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, bitmap && (out_rows || capacity == 0), "null pointer");
+    if (n_rows <= 0 || capacity <= 0) return DR_OK;
+    const int64_t n_words = (n_rows + 31) >> 5;
+    const int64_t n_blocks = (n_words + kWordsPerBlock - 1) / kWordsPerBlock;
+    DR_REQUIRE(ctx, ctx->scratch_bytes >= sizeof(unsigned long long) * (size_t)(n_blocks + 1),
+               "dr_bitmap_rows_after_count must follow dr_bitmap_count on the same bitmap");
+    k_write_rows<<<(int)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        bitmap, n_rows, n_words, (const unsigned long long*)ctx->scratch, out_rows, capacity);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_null_bitmaps(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols, int64_t words_per_col,
+                         uint32_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0 || n_cols <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && out && words_per_col >= (n + 31) / 32, "bad arguments");
+    k_tile_null_bitmaps<<<dr_grid_for(ctx, (n + 31) / 32, kThreads / 32, kCtasPerSm), kThreads, 0,
+                          (cudaStream_t)stream>>>(tile, n, n_cols, words_per_col, out);
+    DR_LAUNCHED(ctx);
     return DR_OK;
 }
 

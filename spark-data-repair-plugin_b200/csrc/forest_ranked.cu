@@ -14,7 +14,6 @@ namespace {
 constexpr int T = 256;
 constexpr int kChunkNodes = 8192;   // 32 KB of node words
 constexpr int kChunkLeaves = 4352;  // 34 KB of float64 leaf values
-constexpr uint32_t kLeafFeat = 0x7FFu;
 
 struct RankedParams {
     dr_forest_ranked f;
@@ -27,16 +26,14 @@ struct RankedParams {
     int feat_stride;  // bytes per thread row of the feature tile (multiple of 4, odd number of words)
 };
 
+// One level: two shared-memory loads (feature rank, next node word) and six ALU ops.  Leaves point
+// at themselves (left = right = own index), so a finished tree just re-reads its leaf word.
 __device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, int root, uint32_t w,
                                               const uint8_t* __restrict__ my_feat) {
-    const uint32_t feat = w >> 21;
-    const bool is_leaf = feat == kLeafFeat;
-    const uint32_t r = my_feat[is_leaf ? 0 : feat];
-    const uint32_t thr = (w >> 13) & 0xFFu;
-    const bool go_left = (r == 255u) ? ((w >> 12) & 1u) : (r < thr);
-    const uint32_t child = go_left ? ((w >> 6) & 0x3Fu) : (w & 0x3Fu);
-    const uint32_t nw = nodes[is_leaf ? root : root + (int)child];
-    return is_leaf ? w : nw;
+    const uint32_t r = my_feat[w >> 20];            // rank of feature (w >> 21) in its NaN-left / NaN-right variant
+    const uint32_t thr = (w >> 12) & 0xFFu;
+    const uint32_t child = (r < thr) ? ((w >> 6) & 0x3Fu) : (w & 0x3Fu);
+    return nodes[root + (int)child];
 }
 
 __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
@@ -57,13 +54,16 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
         {
             const int32_t* trow = p.tile + row * p.n_cols;
             for (int f = 0; f < F.n_feat; ++f) {
-                uint8_t r = 255;
+                uint8_t r = 255;  // NaN
                 if (live) {
                     const int lo = F.rank_lut_off[f], hi = F.rank_lut_off[f + 1];
                     const int k = lo + trow[F.feat_col[f]] + 1;
                     if (k >= lo && k < hi) r = __ldg(F.rank_lut + k);
                 }
-                my_feat[f] = r;
+                // ranks are stored +1 (1..254); NaN becomes 0 in the "NaN goes left" variant and 255
+                // in the "NaN goes right" one, so `rank < thr` needs no special case
+                my_feat[2 * f + 0] = r == 255 ? 255 : r;   // variant read by nodes whose NaN goes right
+                my_feat[2 * f + 1] = r == 255 ? 0 : r;     // variant read by nodes whose NaN goes left
             }
         }
         double best = 0.0, margin0 = 0.0;
@@ -94,16 +94,16 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
                         w2 = step_node(s_node, r2, w2, my_feat);
                         w3 = step_node(s_node, r3, w3, my_feat);
                     }
-                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)(w0 & 0x1FFFFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 1] - l0 + (int)(w1 & 0x1FFFFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 2] - l0 + (int)(w2 & 0x1FFFFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 3] - l0 + (int)(w3 & 0x1FFFFFu)];
+                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
+                    acc += s_leaf[F.tree_leaf_off[q + 1] - l0 + (int)((w1 >> 12) & 0xFFu)];
+                    acc += s_leaf[F.tree_leaf_off[q + 2] - l0 + (int)((w2 >> 12) & 0xFFu)];
+                    acc += s_leaf[F.tree_leaf_off[q + 3] - l0 + (int)((w3 >> 12) & 0xFFu)];
                 }
                 for (; q < tr_hi; ++q) {
                     const int r0 = F.tree_node_off[q] - n0;
                     uint32_t w0 = s_node[r0];
                     for (int d = 0; d < depth; ++d) w0 = step_node(s_node, r0, w0, my_feat);
-                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)(w0 & 0x1FFFFFu)];
+                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
                 }
                 tr = tr_hi;
             }
@@ -127,7 +127,7 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (n_cells <= 0) return DR_OK;
     DR_REQUIRE(ctx, forest && cells && tile, "null pointer");
     const dr_forest_ranked& f = *forest;
-    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat < 2047, "bad forest sizes");
+    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 2047, "bad forest sizes");
     DR_REQUIRE(ctx, f.seq_tree_off && f.tree_node_off && f.tree_leaf_off && f.baseline && f.feat_col &&
                         f.rank_lut_off && f.class_code, "null forest array");
     DR_REQUIRE(ctx, f.max_depth >= 0 && f.max_depth <= 63, "bad max_depth");
@@ -141,7 +141,7 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     p.n_cells = n_cells;
     p.target_col = target_col;
     p.out_margin = out_margin;
-    int words = (f.n_feat + 3) / 4;
+    int words = (2 * f.n_feat + 3) / 4;
     if (words < 1) words = 1;
     if ((words & 1) == 0) ++words;  // odd word stride: consecutive threads land on different banks
     p.feat_stride = words * 4;

@@ -20,7 +20,7 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTileRows = 128;             // rows per warp-wide 128-bit load
-constexpr int kTilesPerChunk = 8;          // independent loads in flight per lane and column
+constexpr int kTilesPerChunk = 4;          // tiles per chunk; two chunks (current + prefetched) in registers
 constexpr int kChunkRows = kTileRows * kTilesPerChunk;
 
 struct ScanParams {
@@ -35,10 +35,26 @@ struct ScanParams {
     int64_t* hist;
 };
 
-__device__ __forceinline__ void count_one(int32_t* bins, int loc, int dom, int code, int lane) {
-    unsigned s = (unsigned)(code + 1);
-    s = s > (unsigned)dom ? (unsigned)dom : s;  // memory safety for out-of-range codes
-    bins[(loc + (int)s) * 32 + lane] += 1;
+// lane-private bin update: `b` already points at this lane's copy of the column's slot 0
+__device__ __forceinline__ void count_one(int32_t* b, unsigned dom, int code) {
+    const unsigned s = min((unsigned)(code + 1), dom);  // clamp: memory safety for out-of-range codes
+    b[s * 32] += 1;
+}
+
+__device__ __forceinline__ void store_null_bits(uint32_t* __restrict__ bm, int64_t tile_base, unsigned nib,
+                                                int lane) {
+    unsigned w = nib << (4 * (lane & 7));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if ((lane & 7) == 0 && w != 0) bm[(tile_base >> 5) + (lane >> 3)] |= w;  // word owned by this warp
+}
+
+__device__ __forceinline__ void load_chunk(int4 (&v)[kTilesPerChunk], const int32_t* __restrict__ col,
+                                           int64_t base, int lane) {
+#pragma unroll
+    for (int t = 0; t < kTilesPerChunk; ++t)
+        v[t] = __ldcs(reinterpret_cast<const int4*>(col + base + t * kTileRows) + lane);
 }
 
 __global__ void __launch_bounds__(kThreads) k_scan_hist(const __grid_constant__ ScanParams p) {
@@ -51,57 +67,65 @@ __global__ void __launch_bounds__(kThreads) k_scan_hist(const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_rows = p.n_rows;
+    const int64_t n_full = n_rows / kChunkRows;  // chunks that need no bounds checks
     const int64_t n_chunks = (n_rows + kChunkRows - 1) / kChunkRows;
 
     for (int c = c_begin + warp; c < c_end; c += kWarps) {
         const int32_t* __restrict__ col = p.cols[c];
         uint32_t* __restrict__ bm = p.bitmaps[c];
-        const int loc = p.local_off[c], dom = p.dom[c];
+        const int loc = p.local_off[c];
+        const unsigned dom = (unsigned)p.dom[c];
+        int32_t* const b = bins + loc * 32 + lane;
         const bool vec_ok = ((uintptr_t)col & 15) == 0;
-        for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-            const int64_t base = chunk * kChunkRows;
-            int4 v[kTilesPerChunk];
-            if (vec_ok && base + kChunkRows <= n_rows) {
-#pragma unroll
-                for (int t = 0; t < kTilesPerChunk; ++t)
-                    v[t] = __ldcs(reinterpret_cast<const int4*>(col + base + t * kTileRows) + lane);
-            } else {
+        int64_t chunk = blockIdx.x;
+        if (vec_ok) {
+            // software pipeline: the next chunk's four 128-bit loads are in flight while this one is counted
+            int4 cur[kTilesPerChunk], nxt[kTilesPerChunk];
+            if (chunk < n_full) load_chunk(cur, col, chunk * kChunkRows, lane);
+            while (chunk < n_full) {
+                const int64_t next = chunk + gridDim.x;
+                if (next < n_full) load_chunk(nxt, col, next * kChunkRows, lane);
 #pragma unroll
                 for (int t = 0; t < kTilesPerChunk; ++t) {
-                    const int64_t r = base + t * kTileRows + lane * 4;
-                    // INT32_MIN marks "row does not exist": not counted, no bit
-                    v[t].x = r + 0 < n_rows ? col[r + 0] : INT32_MIN;
-                    v[t].y = r + 1 < n_rows ? col[r + 1] : INT32_MIN;
-                    v[t].z = r + 2 < n_rows ? col[r + 2] : INT32_MIN;
-                    v[t].w = r + 3 < n_rows ? col[r + 3] : INT32_MIN;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < kTilesPerChunk; ++t) {
-                const int4 q = v[t];
-                unsigned nib = 0;
-                if (q.x != INT32_MIN) { count_one(bins, loc, dom, q.x, lane); nib |= (q.x < 0) << 0; }
-                if (q.y != INT32_MIN) { count_one(bins, loc, dom, q.y, lane); nib |= (q.y < 0) << 1; }
-                if (q.z != INT32_MIN) { count_one(bins, loc, dom, q.z, lane); nib |= (q.z < 0) << 2; }
-                if (q.w != INT32_MIN) { count_one(bins, loc, dom, q.w, lane); nib |= (q.w < 0) << 3; }
-                if (bm != nullptr) {
-                    unsigned w = nib << (4 * (lane & 7));
-                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-                    if ((lane & 7) == 0 && w != 0) {
-                        const int64_t word = ((base + t * kTileRows) >> 5) + (lane >> 3);
-                        bm[word] |= w;  // this word belongs to this warp only
+                    const int4 q = cur[t];
+                    count_one(b, dom, q.x);
+                    count_one(b, dom, q.y);
+                    count_one(b, dom, q.z);
+                    count_one(b, dom, q.w);
+                    if (bm != nullptr) {
+                        const unsigned nib = ((unsigned)q.x >> 31) | (((unsigned)q.y >> 31) << 1) |
+                                             (((unsigned)q.z >> 31) << 2) | (((unsigned)q.w >> 31) << 3);
+                        store_null_bits(bm, chunk * kChunkRows + t * kTileRows, nib, lane);
                     }
                 }
+#pragma unroll
+                for (int t = 0; t < kTilesPerChunk; ++t) cur[t] = nxt[t];
+                chunk = next;
+            }
+        }
+        // ragged tail (and unaligned columns): bounds-checked scalar loads
+        for (; chunk < n_chunks; chunk += gridDim.x) {
+            const int64_t base = chunk * kChunkRows;
+            for (int t = 0; t < kTilesPerChunk; ++t) {
+                unsigned nib = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = base + t * kTileRows + lane * 4 + j;
+                    if (r < n_rows) {
+                        const int code = col[r];
+                        count_one(b, dom, code);
+                        nib |= (unsigned)(code < 0) << j;
+                    }
+                }
+                if (bm != nullptr) store_null_bits(bm, base + t * kTileRows, nib, lane);
             }
         }
         // reduce the lane-private copies of this column's bins; lane L sums bin (s0 + L), reading
         // the 32 copies in a rotated order so that the 32 lanes hit 32 different banks
         __syncwarp();
-        for (int s0 = 0; s0 <= dom; s0 += 32) {
+        for (int s0 = 0; s0 <= (int)dom; s0 += 32) {
             const int s = s0 + lane;
-            if (s <= dom) {
+            if (s <= (int)dom) {
                 long long total = 0;
 #pragma unroll 8
                 for (int j = 0; j < 32; ++j) total += bins[(loc + s) * 32 + ((j + lane) & 31)];

@@ -88,8 +88,7 @@ class Engine:
         cnt = self.ctx.bitmap_count(bitmap, n)
         rows = self.torch.empty(max(cnt, 1), dtype=self.torch.int32, device=self.device)
         if cnt:
-            got = self.ctx.bitmap_to_rows(bitmap, n, rows, cnt)
-            assert got == cnt
+            self.ctx.bitmap_rows_after_count(bitmap, n, rows, cnt)  # reuses the block offsets of the count
         return rows[:cnt]
 
     # ---- a7: discretisation ------------------------------------------------------------------

@@ -146,11 +146,11 @@ def rank_code(spec, dict_sizes):
     rank_lut, rank_off, values = [], [0], []
     for col in luts:
         vals = np.unique(col[~np.isnan(col)])
-        if len(vals) > 254:
+        if len(vals) > 253:
             return None
         r = np.full(len(col), 255, dtype=np.uint8)
         ok = ~np.isnan(col)
-        r[ok] = np.searchsorted(vals, col[ok]).astype(np.uint8)
+        r[ok] = (np.searchsorted(vals, col[ok]) + 1).astype(np.uint8)  # ranks are stored +1 (1..254)
         rank_lut.append(r)
         rank_off.append(rank_off[-1] + len(r))
         values.append(vals)
@@ -168,12 +168,16 @@ def rank_code(spec, dict_sizes):
     tree_leaf_off[:-1] = leaf_cum[toff[:-1]] if len(sizes) else 0
     tree_leaf_off[-1] = int(is_leaf.sum())
     leaf_idx = leaf_cum - tree_leaf_off[tree_of] if len(feat) else leaf_cum
-    word = np.where(
-        is_leaf, (np.uint32(0x7FF) << np.uint32(21)) | leaf_idx.astype(np.uint32),
-        (np.where(is_leaf, 0, feat).astype(np.uint32) << np.uint32(21)) | (thr_rank << np.uint32(13)) |
-        ((np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)) << np.uint32(12)) |
-        ((np.asarray(f["left"], dtype=np.uint32) & np.uint32(0x3F)) << np.uint32(6)) |
-        (np.asarray(f["right"], dtype=np.uint32) & np.uint32(0x3F))).astype(np.uint32)
+    node_in_tree = (np.arange(len(feat)) - toff[tree_of]).astype(np.uint32) if len(feat) else np.zeros(0, np.uint32)
+    if len(leaf_idx) and leaf_idx.max() > 255:
+        return None
+    internal = ((np.where(is_leaf, 0, feat).astype(np.uint32) << np.uint32(21)) |
+                ((np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)) << np.uint32(20)) |
+                ((thr_rank + np.uint32(1)) << np.uint32(12)) |
+                ((np.asarray(f["left"], dtype=np.uint32) & np.uint32(0x3F)) << np.uint32(6)) |
+                (np.asarray(f["right"], dtype=np.uint32) & np.uint32(0x3F)))
+    leaf = (leaf_idx.astype(np.uint32) << np.uint32(12)) | (node_in_tree << np.uint32(6)) | node_in_tree
+    word = np.where(is_leaf, leaf, internal).astype(np.uint32)
     # deepest leaf: breadth-first sweep over all trees at once
     depth, frontier = 0, toff[:-1].copy()
     base = toff[:-1].copy()

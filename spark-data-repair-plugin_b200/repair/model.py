@@ -416,14 +416,18 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
     drows, tile, ctile = engine.build_dirty_tile(res, targets)
     D = int(drows.numel())
     n_cc = len(cont_idx)
-    nullbits = torch.zeros((D + 31) // 32 + 1, dtype=torch.int32, device=engine.device)
+    words = (D + 31) // 32 + 1
+    nullbits = torch.zeros(words, dtype=torch.int32, device=engine.device)
+    # NULL cells of every discrete column in one pass (a model only fills its own column)
+    all_null = torch.zeros((K, words), dtype=torch.int32, device=engine.device)
+    engine.ctx.tile_null_bitmaps(tile, D, K, words, all_null)
     for y, m in models:
         ycol = table.by_name[y]
         if ycol.continuous:
             engine.ctx.tile_null_bitmap(ctile, D, n_cc, cont_idx[y], nullbits, f64=True)
+            todo = engine.bitmap_rows(nullbits, D)
         else:
-            engine.ctx.tile_null_bitmap(tile, D, K, tile_col[y], nullbits)
-        todo = engine.bitmap_rows(nullbits, D)
+            todo = engine.bitmap_rows(all_null[tile_col[y]], D)
         n = int(todo.numel())
         if n == 0:
             continue

@@ -437,3 +437,38 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
         dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=generic)
         assert np.array_equal(margins.cpu().numpy(), want_m), generic
         assert np.array_equal(tile.cpu().numpy()[cells, 0], want.astype(np.int32))
+
+
+def test_tile_null_bitmaps_and_rows_after_count(ctx):
+    rng = np.random.default_rng(9)
+    n, k = 70001, 19
+    tile_np = np.stack(rand_cols(rng, n, [5] * k, null_p=0.2), axis=1).astype(np.int32)
+    words = (n + 31) // 32 + 1
+    out = torch.zeros((k, words), dtype=torch.int32, device="cuda")
+    ctx.tile_null_bitmaps(dev(tile_np), n, k, words, out)
+    for c in range(k):
+        assert np.array_equal(bits_of(out[c], n), tile_np[:, c] < 0)
+        cnt = ctx.bitmap_count(out[c], n)
+        rows = torch.empty(cnt, dtype=torch.int32, device="cuda")
+        ctx.bitmap_rows_after_count(out[c], n, rows, cnt)
+        assert np.array_equal(rows.cpu().numpy(), np.nonzero(tile_np[:, c] < 0)[0].astype(np.int32))
+
+
+def test_dc_fd_large_key_space_uses_global_tables(ctx):
+    rng = np.random.default_rng(12)
+    n = 60000
+    a, b, c = rand_cols(rng, n, [200, 150, 9], null_p=0.05)
+    space = 201 * 151  # > 8192: global-atomic path
+    lo = torch.full((space,), 2 ** 31 - 1, dtype=torch.int32, device="cuda")
+    hi = torch.full((space,), -2 ** 31, dtype=torch.int32, device="cuda")
+    ctx.dc_fd_build([dev(a), dev(b)], [1, 201], dev(c), n, space, lo, hi)
+    bm = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    ctx.dc_fd_flag([dev(a), dev(b)], [1, 201], n, space, lo, hi, bm)
+    key = (a.astype(np.int64) + 1) + (b.astype(np.int64) + 1) * 201
+    order = np.argsort(key, kind="stable")
+    ks, cs = key[order], c[order]
+    starts = np.r_[0, np.nonzero(np.diff(ks))[0] + 1]
+    mn, mx = np.minimum.reduceat(cs, starts), np.maximum.reduceat(cs, starts)
+    viol_key = dict(zip(ks[starts].tolist(), (mn != mx).tolist()))
+    want = np.array([viol_key[kk] for kk in key.tolist()])
+    assert np.array_equal(bits_of(bm, n), want)

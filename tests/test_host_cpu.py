@@ -405,14 +405,13 @@ def _eval_ranked(rk, forest, codes_by_feat):
         for i in range(n):
             w = int(rk["word"][toff[t]])
             for _ in range(rk["max_depth"]):
-                feat = w >> 21
-                if feat == 0x7FF:
-                    break
+                feat, nan_left = w >> 21, (w >> 20) & 1
                 r = int(ranks[feat][i])
-                go_left = ((w >> 12) & 1) if r == 255 else (r < ((w >> 13) & 0xFF))
+                r = (0 if nan_left else 255) if r == 255 else r
+                go_left = r < ((w >> 12) & 0xFF)
                 w = int(rk["word"][toff[t] + (((w >> 6) & 0x3F) if go_left else (w & 0x3F))])
-            assert (w >> 21) == 0x7FF
-            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + (w & 0x1FFFFF)]
+            assert ((w >> 6) & 0x3F) == (w & 0x3F)  # a leaf points at itself
+            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + ((w >> 12) & 0xFF)]
     return raw
 
 
