@@ -254,9 +254,19 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  *   rank_lut:  uint8, rank (0..253) of feature f of a row = rank_lut[rank_lut_off[f] +
  *              tile[row][feat_col[f]] + 1], 255 = NaN; the kernel compares (rank + 1) < (thr_rank + 1)
  *              with NaN mapped to 0 / 255 according to the node's NaN direction.
- *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels). */
+ *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels).
+ *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered),
+ *   so every tree's node words are padded to a multiple of 4 and its leaf values to a multiple of 2
+ *   (16-byte granules), and the host supplies the chunk table: chunk c = trees
+ *   [chunk_tree_off[c], chunk_tree_off[c+1]) of sequence chunk_seq[c], at most DR_RANKED_CHUNK_NODES
+ *   node words and DR_RANKED_CHUNK_LEAVES leaf values, never straddling a sequence; every sequence
+ *   has at least one tree. */
+#define DR_RANKED_CHUNK_NODES 4096
+#define DR_RANKED_CHUNK_LEAVES 2176
 typedef struct dr_forest_ranked {
-    int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth;
+    int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth, n_chunks;
+    const int32_t* chunk_tree_off;
+    const int32_t* chunk_seq;
     const int32_t* seq_tree_off;
     const int32_t* tree_node_off;
     const int32_t* tree_leaf_off;

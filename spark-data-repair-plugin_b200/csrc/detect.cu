@@ -11,7 +11,7 @@ constexpr int kThreads = 256;
 constexpr int kCtasPerSm = 8;
 
 // Evaluate `pred(row)` for every row and OR the resulting bits into `bm`.  Each 32-row word is
-// produced by exactly one warp (ballot), so the read-modify-write needs no atomics.
+// produced by exactly one warp (ballot); it is merged with a fire-and-forget RED.OR.
 template <class Pred>
 __device__ __forceinline__ void rows_to_bitmap(int64_t n_rows, uint32_t* __restrict__ bm, Pred pred) {
     const int lane = threadIdx.x & 31;
@@ -20,7 +20,7 @@ __device__ __forceinline__ void rows_to_bitmap(int64_t n_rows, uint32_t* __restr
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
         const bool bit = r < n_rows ? pred(r) : false;
         const unsigned w = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0 && w != 0) bm[r >> 5] |= w;
+        if (lane == 0 && w != 0) atomicOr(bm + (r >> 5), w);  // RED.OR: no load stall in the stream
     }
 }
 

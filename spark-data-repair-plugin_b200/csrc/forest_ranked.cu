@@ -1,19 +1,21 @@
 // dr_forest_predict_ranked: rank-coded forest inference for all-discrete models (see the header).
 //
-// Compared with the generic float64 kernel: a node is one 32-bit word instead of 12 bytes, a cell's
-// features are one byte each instead of eight, so a CTA of 256 cells needs ~25 KB of features and the
-// rest of shared memory holds bigger forest chunks at 2 CTAs (16 warps) per SM.  Each thread walks FOUR
-// trees at a time for a fixed number of levels (leaves self-loop), which gives the scheduler four
-// independent dependent-load chains per thread and removes all data-dependent branches; the four
-// leaf values are then added to the sequence's float64 accumulator in tree order, so the margins are
-// bit-identical to the generic kernel and to the oracle.
+// Compared with the generic float64 kernel: a node is one 32-bit word instead of 12 bytes and a
+// cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~40 KB of features
+// and 16 warps stay resident per SM.  The forest is streamed through shared memory in chunks of whole
+// trees by the TMA engine (cp.async.bulk + mbarrier, double buffered: chunk k+1 lands while chunk k is
+// walked).  Each thread walks FOUR trees at a time for a fixed number of levels -- leaves point at
+// themselves, NaN is folded into two rank variants -- so a level is two shared-memory loads and six ALU
+// ops with no data-dependent branch, and the four dependent chains overlap.  Leaf values are float64
+// and are added to the sequence's accumulator in tree order: margins are bit-identical to the generic
+// kernel and to the oracle.
 #include "common.cuh"
 
 namespace {
 
 constexpr int T = 256;
-constexpr int kChunkNodes = 8192;   // 32 KB of node words
-constexpr int kChunkLeaves = 4352;  // 34 KB of float64 leaf values
+constexpr int kChunkNodes = DR_RANKED_CHUNK_NODES;
+constexpr int kChunkLeaves = DR_RANKED_CHUNK_LEAVES;
 
 struct RankedParams {
     dr_forest_ranked f;
@@ -26,31 +28,81 @@ struct RankedParams {
     int feat_stride;  // bytes per thread row of the feature tile (multiple of 4, odd number of words)
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (16-byte granules)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // One level: two shared-memory loads (feature rank, next node word) and six ALU ops.  Leaves point
 // at themselves (left = right = own index), so a finished tree just re-reads its leaf word.
 __device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, int root, uint32_t w,
                                               const uint8_t* __restrict__ my_feat) {
-    const uint32_t r = my_feat[w >> 20];            // rank of feature (w >> 21) in its NaN-left / NaN-right variant
+    const uint32_t r = my_feat[w >> 20];  // rank of feature (w >> 21), NaN-left / NaN-right variant
     const uint32_t thr = (w >> 12) & 0xFFu;
     const uint32_t child = (r < thr) ? ((w >> 6) & 0x3Fu) : (w & 0x3Fu);
     return nodes[root + (int)child];
 }
 
+struct __align__(16) ChunkBuf {
+    double leaf[kChunkLeaves];
+    uint32_t node[kChunkNodes];
+};
+
 __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const dr_forest_ranked& F = p.f;
-    double* s_leaf = reinterpret_cast<double*>(smem_raw);                            // kChunkLeaves
-    uint32_t* s_node = reinterpret_cast<uint32_t*>(s_leaf + kChunkLeaves);           // kChunkNodes
-    uint8_t* s_feat = reinterpret_cast<uint8_t*>(s_node + kChunkNodes);              // T * feat_stride
+    ChunkBuf* buf = reinterpret_cast<ChunkBuf*>(smem_raw);                       // two chunk buffers
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(ChunkBuf));  // two mbarriers
+    uint8_t* s_feat = smem_raw + 2 * sizeof(ChunkBuf) + 16;
     const int t = threadIdx.x;
     uint8_t* my_feat = s_feat + (size_t)t * p.feat_stride;
     const int depth = F.max_depth;
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+
+    auto issue = [&](int c, int b) {  // thread 0: start the TMA copies of chunk c into buffer b
+        const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
+        const int n0 = F.tree_node_off[ta], n1 = F.tree_node_off[tb];
+        const int l0 = F.tree_leaf_off[ta], l1 = F.tree_leaf_off[tb];
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u;
+        mbar_expect_tx(&bar[b], nb + lb);
+        bulk_g2s(buf[b].node, F.node_word + n0, nb, &bar[b]);
+        bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &bar[b]);
+    };
 
     for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
         const int64_t i = base + t;
         const bool live = i < p.n_cells;
         const int64_t row = live ? p.cells[i] : 0;
-        __syncthreads();
+        if (t == 0) issue(0, 0);  // both buffers are idle here (trailing barrier of the previous tile)
         {
             const int32_t* trow = p.tile + row * p.n_cols;
             for (int f = 0; f < F.n_feat; ++f) {
@@ -60,57 +112,58 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
                     const int k = lo + trow[F.feat_col[f]] + 1;
                     if (k >= lo && k < hi) r = __ldg(F.rank_lut + k);
                 }
-                // ranks are stored +1 (1..254); NaN becomes 0 in the "NaN goes left" variant and 255
-                // in the "NaN goes right" one, so `rank < thr` needs no special case
-                my_feat[2 * f + 0] = r == 255 ? 255 : r;   // variant read by nodes whose NaN goes right
-                my_feat[2 * f + 1] = r == 255 ? 0 : r;     // variant read by nodes whose NaN goes left
+                // ranks are stored +1 (1..254); NaN becomes 255 where NaN goes right and 0 where it
+                // goes left, so `rank < thr` needs no special case
+                my_feat[2 * f + 0] = r;
+                my_feat[2 * f + 1] = r == 255 ? 0 : r;
             }
         }
-        double best = 0.0, margin0 = 0.0;
-        int best_s = 0;
-        for (int s = 0; s < F.n_seq; ++s) {
-            double acc = F.baseline[s];
-            const int t_end = F.seq_tree_off[s + 1];
-            int tr = F.seq_tree_off[s];
-            while (tr < t_end) {
-                const int n0 = F.tree_node_off[tr], l0 = F.tree_leaf_off[tr];
-                int tr_hi = tr + 1;
-                while (tr_hi < t_end && F.tree_node_off[tr_hi + 1] - n0 <= kChunkNodes &&
-                       F.tree_leaf_off[tr_hi + 1] - l0 <= kChunkLeaves)
-                    ++tr_hi;
-                const int n1 = F.tree_node_off[tr_hi], l1 = F.tree_leaf_off[tr_hi];
-                __syncthreads();
-                for (int k = t; k < n1 - n0; k += T) s_node[k] = F.node_word[n0 + k];
-                for (int k = t; k < l1 - l0; k += T) s_leaf[k] = F.leaf_value[l0 + k];
-                __syncthreads();
-                int q = tr;
-                for (; q + 4 <= tr_hi; q += 4) {
-                    const int r0 = F.tree_node_off[q] - n0, r1 = F.tree_node_off[q + 1] - n0;
-                    const int r2 = F.tree_node_off[q + 2] - n0, r3 = F.tree_node_off[q + 3] - n0;
-                    uint32_t w0 = s_node[r0], w1 = s_node[r1], w2 = s_node[r2], w3 = s_node[r3];
-                    for (int d = 0; d < depth; ++d) {
-                        w0 = step_node(s_node, r0, w0, my_feat);
-                        w1 = step_node(s_node, r1, w1, my_feat);
-                        w2 = step_node(s_node, r2, w2, my_feat);
-                        w3 = step_node(s_node, r3, w3, my_feat);
-                    }
-                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 1] - l0 + (int)((w1 >> 12) & 0xFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 2] - l0 + (int)((w2 >> 12) & 0xFFu)];
-                    acc += s_leaf[F.tree_leaf_off[q + 3] - l0 + (int)((w3 >> 12) & 0xFFu)];
-                }
-                for (; q < tr_hi; ++q) {
-                    const int r0 = F.tree_node_off[q] - n0;
-                    uint32_t w0 = s_node[r0];
-                    for (int d = 0; d < depth; ++d) w0 = step_node(s_node, r0, w0, my_feat);
-                    acc += s_leaf[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
-                }
-                tr = tr_hi;
+        double best = 0.0, margin0 = 0.0, acc = F.baseline[0];
+        int best_s = 0, cur_s = 0;
+        for (int c = 0; c < F.n_chunks; ++c) {
+            const int b = c & 1;
+            if (t == 0 && c + 1 < F.n_chunks) issue(c + 1, b ^ 1);
+            const int s = F.chunk_seq[c];
+            if (s != cur_s) {  // previous sequence is complete
+                if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
+                if (cur_s == 0) { best = acc; margin0 = acc; }
+                else if (acc > best) { best = acc; best_s = cur_s; }
+                cur_s = s;
+                acc = F.baseline[s];
             }
-            if (live && p.out_margin) p.out_margin[i * F.n_seq + s] = acc;
-            if (s == 0) { best = acc; best_s = 0; margin0 = acc; }
-            else if (acc > best) { best = acc; best_s = s; }
+            if (b == 0) { while (!mbar_try_wait(&bar[0], phase0)) {} phase0 ^= 1; }
+            else        { while (!mbar_try_wait(&bar[1], phase1)) {} phase1 ^= 1; }
+            const uint32_t* __restrict__ nodes = buf[b].node;
+            const double* __restrict__ leaves = buf[b].leaf;
+            const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
+            const int n0 = F.tree_node_off[ta], l0 = F.tree_leaf_off[ta];
+            int q = ta;
+            for (; q + 4 <= tb; q += 4) {
+                const int r0 = F.tree_node_off[q] - n0, r1 = F.tree_node_off[q + 1] - n0;
+                const int r2 = F.tree_node_off[q + 2] - n0, r3 = F.tree_node_off[q + 3] - n0;
+                uint32_t w0 = nodes[r0], w1 = nodes[r1], w2 = nodes[r2], w3 = nodes[r3];
+                for (int d = 0; d < depth; ++d) {
+                    w0 = step_node(nodes, r0, w0, my_feat);
+                    w1 = step_node(nodes, r1, w1, my_feat);
+                    w2 = step_node(nodes, r2, w2, my_feat);
+                    w3 = step_node(nodes, r3, w3, my_feat);
+                }
+                acc += leaves[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
+                acc += leaves[F.tree_leaf_off[q + 1] - l0 + (int)((w1 >> 12) & 0xFFu)];
+                acc += leaves[F.tree_leaf_off[q + 2] - l0 + (int)((w2 >> 12) & 0xFFu)];
+                acc += leaves[F.tree_leaf_off[q + 3] - l0 + (int)((w3 >> 12) & 0xFFu)];
+            }
+            for (; q < tb; ++q) {
+                const int r0 = F.tree_node_off[q] - n0;
+                uint32_t w0 = nodes[r0];
+                for (int d = 0; d < depth; ++d) w0 = step_node(nodes, r0, w0, my_feat);
+                acc += leaves[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
+            }
+            __syncthreads();  // buffer b may be refilled (chunk c + 2) only after everybody left it
         }
+        if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
+        if (cur_s == 0) { best = acc; margin0 = acc; }
+        else if (acc > best) { best = acc; best_s = cur_s; }
         if (live) {
             const int cls = F.n_seq == 1 ? (margin0 > 0.0 ? 1 : 0) : best_s;
             p.tile[row * p.n_cols + p.target_col] = cls < F.n_classes ? F.class_code[cls] : -1;
@@ -129,7 +182,11 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     const dr_forest_ranked& f = *forest;
     DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 2047, "bad forest sizes");
     DR_REQUIRE(ctx, f.seq_tree_off && f.tree_node_off && f.tree_leaf_off && f.baseline && f.feat_col &&
-                        f.rank_lut_off && f.class_code, "null forest array");
+                        f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq && f.node_word &&
+                        f.leaf_value, "null forest array");
+    DR_REQUIRE(ctx, f.n_chunks >= 1, "the ranked forest needs at least one chunk (one tree per sequence)");
+    DR_REQUIRE(ctx, ((uintptr_t)f.node_word & 15) == 0 && ((uintptr_t)f.leaf_value & 15) == 0,
+               "node / leaf arrays must be 16-byte aligned");
     DR_REQUIRE(ctx, f.max_depth >= 0 && f.max_depth <= 63, "bad max_depth");
     DR_REQUIRE(ctx, target_col >= 0 && target_col < n_cols, "bad target column");
     DR_REQUIRE(ctx, f.n_seq == 1 ? f.n_classes >= 2 : f.n_classes == f.n_seq, "class count mismatch");
@@ -145,7 +202,7 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (words < 1) words = 1;
     if ((words & 1) == 0) ++words;  // odd word stride: consecutive threads land on different banks
     p.feat_stride = words * 4;
-    const size_t smem = (size_t)kChunkLeaves * 8 + (size_t)kChunkNodes * 4 + (size_t)T * p.feat_stride;
+    const size_t smem = 2 * sizeof(ChunkBuf) + 16 + (size_t)T * p.feat_stride;
     if (smem > 200 * 1024)
         return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d features exceeds shared memory", f.n_feat);
     DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -47,7 +47,8 @@ __device__ __forceinline__ void store_null_bits(uint32_t* __restrict__ bm, int64
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if ((lane & 7) == 0 && w != 0) bm[(tile_base >> 5) + (lane >> 3)] |= w;  // word owned by this warp
+    // RED.OR: fire-and-forget, so the streaming loop never waits on a read-modify-write of the bitmap
+    if ((lane & 7) == 0 && w != 0) atomicOr(bm + (tile_base >> 5) + (lane >> 3), w);
 }
 
 __device__ __forceinline__ void load_chunk(int4 (&v)[kTilesPerChunk], const int32_t* __restrict__ col,
@@ -154,7 +155,7 @@ __global__ void k_scan_hist_global(const int32_t* __restrict__ col, uint32_t* __
             is_null = code < 0;
         }
         const unsigned w = __ballot_sync(0xffffffffu, is_null);
-        if (bm != nullptr && lane == 0 && w != 0) bm[r >> 5] |= w;
+        if (bm != nullptr && lane == 0 && w != 0) atomicOr(bm + (r >> 5), w);
     }
 }
 

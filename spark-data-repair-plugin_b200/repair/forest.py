@@ -195,6 +195,48 @@ def rank_code(spec, dict_sizes):
             "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth}
 
 
+RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES = 4096, 2176  # DR_RANKED_CHUNK_* in include/b200repair.h
+
+
+def ranked_image(rk, toff, order, seq_tree_off):
+    """Device layout of a rank-coded forest: trees grouped by sequence (`order`), every tree's node
+    words padded to a multiple of 4 and its leaves to a multiple of 2 (16-byte TMA granules), plus the
+    chunk table the kernel streams by (whole trees, never straddling a sequence)."""
+    toff = np.asarray(toff, dtype=np.int64)
+    lo = np.asarray(rk["tree_leaf_off"], dtype=np.int64)
+    n_sizes = (toff[1:] - toff[:-1])[order]
+    l_sizes = (lo[1:] - lo[:-1])[order]
+    n_pad, l_pad = (n_sizes + 3) // 4 * 4, (l_sizes + 1) // 2 * 2
+    node_off = np.zeros(len(order) + 1, dtype=np.int64)
+    leaf_off = np.zeros(len(order) + 1, dtype=np.int64)
+    node_off[1:], leaf_off[1:] = np.cumsum(n_pad), np.cumsum(l_pad)
+    word = np.zeros(int(node_off[-1]), dtype=np.uint32)
+    leaf = np.zeros(int(leaf_off[-1]), dtype=np.float64)
+    # scatter every tree's nodes / leaves to its padded slot (vectorised over all trees)
+    tree_new = np.repeat(np.arange(len(order)), n_sizes)
+    within = np.arange(int(n_sizes.sum())) - np.repeat(np.cumsum(n_sizes) - n_sizes, n_sizes)
+    src = np.repeat(toff[:-1][order], n_sizes) + within
+    word[node_off[tree_new] + within] = rk["word"][src]
+    ltree_new = np.repeat(np.arange(len(order)), l_sizes)
+    lwithin = np.arange(int(l_sizes.sum())) - np.repeat(np.cumsum(l_sizes) - l_sizes, l_sizes)
+    lsrc = np.repeat(lo[:-1][order], l_sizes) + lwithin
+    leaf[leaf_off[ltree_new] + lwithin] = rk["leaf_value"][lsrc]
+    chunk_tree_off, chunk_seq = [0], []
+    for s in range(len(seq_tree_off) - 1):
+        t, t_end = int(seq_tree_off[s]), int(seq_tree_off[s + 1])
+        while t < t_end:
+            # largest hi with node/leaf footprint of trees [t, hi) inside the chunk buffers
+            hi_n = int(np.searchsorted(node_off, node_off[t] + RANKED_CHUNK_NODES, side="right")) - 1
+            hi_l = int(np.searchsorted(leaf_off, leaf_off[t] + RANKED_CHUNK_LEAVES, side="right")) - 1
+            hi = max(t + 1, min(hi_n, hi_l, t_end))
+            chunk_tree_off.append(hi)
+            chunk_seq.append(s)
+            t = hi
+    return {"word": word, "leaf": leaf, "node_off": node_off, "leaf_off": leaf_off,
+            "chunk_tree_off": np.asarray(chunk_tree_off, dtype=np.int32),
+            "chunk_seq": np.asarray(chunk_seq, dtype=np.int32)}
+
+
 class DeviceModel:
     """Device image of one repair model (forest + encoder LUTs) ready for dr_forest_predict."""
 
@@ -261,35 +303,30 @@ class DeviceModel:
         self.n_nodes = s.n_nodes
         self.ranked = None
         rk = rank_code(spec, dict_sizes) if self.kind == 0 else None
-        if rk is not None:
+        if rk is not None and len(order) and np.all(np.diff(off) > 0):
             from ._native import dr_forest_ranked
-            lo = rk["tree_leaf_off"]
-            leaf_sizes = (lo[1:] - lo[:-1])[order]
-            new_lo = np.zeros(len(order) + 1, dtype=np.int64)
-            new_lo[1:] = np.cumsum(leaf_sizes)
-            lidx = np.concatenate([np.arange(lo[t], lo[t + 1]) for t in order]) if len(order) else \
-                np.zeros(0, dtype=np.int64)
+            img = ranked_image(rk, toff, order, off)
             self._keep.update({
-                "r_node_word": dev(rk["word"][idx].view(np.int32) if len(idx) else np.zeros(1, np.int32), np.int32),
-                "r_leaf_value": dev(rk["leaf_value"][lidx] if len(lidx) else np.zeros(1), np.float64),
-                "r_tree_leaf_off": dev(new_lo, np.int32),
+                "r_node_word": dev(img["word"].view(np.int32), np.int32),
+                "r_leaf_value": dev(img["leaf"], np.float64),
+                "r_tree_node_off": dev(img["node_off"], np.int32),
+                "r_tree_leaf_off": dev(img["leaf_off"], np.int32),
+                "r_chunk_tree_off": dev(img["chunk_tree_off"], np.int32),
+                "r_chunk_seq": dev(img["chunk_seq"], np.int32),
                 "r_rank_lut": dev(rk["rank_lut"], np.uint8),
                 "r_rank_lut_off": dev(rk["rank_lut_off"], np.int32),
                 "r_feat_col": dev([feature_tile_cols[a] for a in rk["feat_attr"]] or [0], np.int32),
             })
             r = dr_forest_ranked()
-            r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, s.n_nodes, len(lidx)
-            r.n_feat, r.max_depth = n_feat, int(rk["max_depth"])
-            r.seq_tree_off = self._keep["seq_tree_off"].data_ptr()
-            r.tree_node_off = self._keep["tree_node_off"].data_ptr()
-            r.tree_leaf_off = self._keep["r_tree_leaf_off"].data_ptr()
-            r.node_word = self._keep["r_node_word"].data_ptr()
-            r.leaf_value = self._keep["r_leaf_value"].data_ptr()
-            r.baseline = self._keep["baseline"].data_ptr()
-            r.feat_col = self._keep["r_feat_col"].data_ptr()
-            r.rank_lut_off = self._keep["r_rank_lut_off"].data_ptr()
-            r.rank_lut = self._keep["r_rank_lut"].data_ptr()
-            r.class_code = self._keep["class_code"].data_ptr()
+            r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, len(img["word"]), len(img["leaf"])
+            r.n_feat, r.max_depth, r.n_chunks = n_feat, int(rk["max_depth"]), len(img["chunk_seq"])
+            for field, key in (("chunk_tree_off", "r_chunk_tree_off"), ("chunk_seq", "r_chunk_seq"),
+                               ("seq_tree_off", "seq_tree_off"), ("tree_node_off", "r_tree_node_off"),
+                               ("tree_leaf_off", "r_tree_leaf_off"), ("node_word", "r_node_word"),
+                               ("leaf_value", "r_leaf_value"), ("baseline", "baseline"), ("feat_col", "r_feat_col"),
+                               ("rank_lut_off", "r_rank_lut_off"), ("rank_lut", "r_rank_lut"),
+                               ("class_code", "class_code")):
+                setattr(r, field, self._keep[key].data_ptr())
             r.n_classes = s.n_classes
             self.ranked = r
 

@@ -437,3 +437,32 @@ def test_rank_coded_forest_makes_the_same_decisions():
     assert np.array_equal(_eval_ranked(rk, forest, by_feat), forest_margins(forest, X))
     spec["encoders"] = encoders + [{"attr": "x", "type": "cont"}]
     assert rank_code(spec, dict_sizes) is None  # continuous feature -> generic kernel
+
+
+def test_ranked_image_padding_and_chunks():
+    from repair.forest import (RANKED_CHUNK_LEAVES, RANKED_CHUNK_NODES, encoder_width, group_by_sequence,
+                               rank_code, ranked_image)
+    from repair.train import random_forest
+    rng = np.random.default_rng(8)
+    dict_sizes = {"a": 6, "b": 20}
+    encoders = [{"attr": "a", "type": "sum", "categories": [0, 1, 2, 3, 4, 5]},
+                {"attr": "b", "type": "ordinal", "categories": list(range(20))}]
+    n_feat = sum(encoder_width(e) for e in encoders)
+    forest = random_forest(n_feat, 7, 120, [[-0.5, 0.5]] * 5 + [[j + 0.5 for j in range(1, 20)]], rng)
+    rk = rank_code({"forest": forest, "encoders": encoders, "class_codes": list(range(7))}, dict_sizes)
+    off, order = group_by_sequence(forest)
+    img = ranked_image(rk, forest["tree_offset"], order, off)
+    assert np.all(img["node_off"] % 4 == 0) and np.all(img["leaf_off"] % 2 == 0)
+    cto, cs = img["chunk_tree_off"], img["chunk_seq"]
+    assert cto[0] == 0 and cto[-1] == len(order) and np.all(np.diff(cto) > 0) and len(cs) == len(cto) - 1
+    for c in range(len(cs)):
+        assert off[cs[c]] <= cto[c] and cto[c + 1] <= off[cs[c] + 1]                    # inside one sequence
+        assert img["node_off"][cto[c + 1]] - img["node_off"][cto[c]] <= RANKED_CHUNK_NODES
+        assert img["leaf_off"][cto[c + 1]] - img["leaf_off"][cto[c]] <= RANKED_CHUNK_LEAVES
+    assert list(cs) == sorted(cs) and set(cs) == set(range(7))
+    # every tree's words survive the move
+    t_new = 37
+    t_old = order[t_new]
+    n = forest["tree_offset"][t_old + 1] - forest["tree_offset"][t_old]
+    assert np.array_equal(img["word"][img["node_off"][t_new]:img["node_off"][t_new] + n],
+                          rk["word"][forest["tree_offset"][t_old]:forest["tree_offset"][t_old + 1]])
