@@ -269,6 +269,7 @@ def b200_arm(args):
     n_trees = sum(m[1].n_trees for _, m in models if m[0] == "forest")
 
     stats = {}
+    res_cells = {}
 
     def step(e2e):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -280,6 +281,8 @@ def b200_arm(args):
         ev[1].record()
         out = repair_cells(rm, engine, table, r, continuous, models=models, encoded_output=True)
         ev[2].record()
+        for a_, n_ in r.n_cells.items():
+            res_cells[a_] = n_
         stats["cells"] = rm.last_run["n_error_cells"]
         stats["dirty"] = rm.last_run["n_dirty_rows"]
         stats["out_rows"] = sum(len(x[1]) for x in out)
@@ -346,6 +349,7 @@ def b200_arm(args):
     alg = {
         "scan_hist": 4.0 * n_disc * n,                               # every code read once
         "forest_predict": stats["cells"] * (4.0 * (k - 1) + 4.0),     # feature gather + fill per cell
+        "forest_predict_ranked": stats["cells"] * (4.0 * (k - 1) + 4.0),
         "gather_rows_masked": stats["dirty"] * 4.0 * k * 2,          # dirty rows in, tile out
         "cooc": None, "dc_fd_build": None, "dc_fd_flag": None, "domain_score": None,
     }
@@ -359,6 +363,12 @@ def b200_arm(args):
         kernels[name] = entry
     dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
     line["kernels"] = kernels
+    fp = [v for kname, v in prof.items() if kname.startswith("forest_predict")]
+    if fp:
+        # forest inference is bounded by dependent shared-memory look-ups, not HBM: report tree levels walked
+        levels = sum((m[1].n_trees * (m[1].ranked.max_depth if m[1].ranked is not None else 5)) *
+                     res_cells.get(y, 0) for y, m in models if m[0] == "forest")
+        line["forest_tree_levels_per_sec"] = levels / (sum(v[1] for v in fp) / 1e3)
     if dominant:
         d = kernels[dominant]
         ach = d.get("achieved_gbs")

@@ -197,6 +197,10 @@ int dr_tile_gather_i32(dr_ctx* ctx, const int32_t* tile, int n_cols, int col, co
                        int32_t* out, void* stream);
 int dr_tile_gather_f64(dr_ctx* ctx, const double* tile, int n_cols, int col, const int32_t* drows, int64_t n,
                        double* out, void* stream);
+/* a14 filter on codes: out bit i = repaired[i] < 0 (NULL) || repaired[i] != current[i], i.e. the
+ * reference's `repaired IS NULL OR NOT(current_value <=> repaired)` (model.py:1401). */
+int dr_changed_bitmap(dr_ctx* ctx, const int32_t* current, const int32_t* repaired, int64_t n, uint32_t* out,
+                      void* stream);
 /* out[i] = position of keys[i] in the ascending array sorted[n_sorted] (binary search), -1 if
  * absent: maps an error cell's row to its dirty-tile row. */
 int dr_lookup_sorted(dr_ctx* ctx, const int32_t* sorted, int64_t n_sorted, const int32_t* keys, int64_t n,

@@ -223,6 +223,24 @@ __global__ void __launch_bounds__(kThreads) k_tile_null_bitmaps(const int32_t* _
     }
 }
 
+// bit i = repaired[i] IS NULL OR NOT(current[i] <=> repaired[i])  (model.py:1401), on codes
+__global__ void __launch_bounds__(kThreads) k_changed_bitmap(const int32_t* __restrict__ cur,
+                                                             const int32_t* __restrict__ rep, int64_t n,
+                                                             uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool bit = false;
+        if (i < n) {
+            const int r = rep[i];
+            bit = r < 0 || r != cur[i];
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) out[i >> 5] = w;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_gather(const T* __restrict__ col, const int32_t* __restrict__ rows,
                                                      int64_t n, int64_t row_stride, int64_t col_off,
@@ -359,6 +377,16 @@ int dr_tile_null_bitmaps(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols
     DR_REQUIRE(ctx, tile && out && words_per_col >= (n + 31) / 32, "bad arguments");
     k_tile_null_bitmaps<<<dr_grid_for(ctx, (n + 31) / 32, kThreads / 32, kCtasPerSm), kThreads, 0,
                           (cudaStream_t)stream>>>(tile, n, n_cols, words_per_col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_changed_bitmap(dr_ctx* ctx, const int32_t* current, const int32_t* repaired, int64_t n, uint32_t* out,
+                      void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, current && repaired && out, "null pointer");
+    k_changed_bitmap<<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(current, repaired, n, out);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "dr_bitmap_to_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dr_bitmap_rows_after_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "dr_tile_null_bitmaps": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "dr_changed_bitmap": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_bitmap_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_bitmap_clear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dr_discretize": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p, c_void_p]),
@@ -231,6 +232,9 @@ class Context:
         self._check(self.lib.dr_tile_null_bitmaps(self._h, _dp(tile), n, n_cols, words_per_col, _dp(out),
                                                   self._stream()))
 
+    def changed_bitmap(self, current, repaired, n, out):
+        self._check(self.lib.dr_changed_bitmap(self._h, _dp(current), _dp(repaired), n, _dp(out), self._stream()))
+
     def bitmap_gather(self, src, rows, n, out):
         self._check(self.lib.dr_bitmap_gather(self._h, _dp(src), _dp(rows), n, _dp(out), self._stream()))
 
@@ -313,7 +317,7 @@ def _profiled(name, fn):
 
 
 for _name in ("scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
-              "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "bitmap_gather", "bitmap_clear_rows", "discretize",
+              "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))

@@ -82,11 +82,13 @@ class Engine:
     def _sync(self):
         self.torch.cuda.current_stream().synchronize()
 
-    def bitmap_rows(self, bitmap, n=None):
-        """Ascending row indices (device int32 tensor) of the set bits."""
+    def bitmap_rows(self, bitmap, n=None, out=None):
+        """Ascending row indices (device int32 tensor) of the set bits (written into `out` if given)."""
         n = self.n_rows if n is None else n
         cnt = self.ctx.bitmap_count(bitmap, n)
-        rows = self.torch.empty(max(cnt, 1), dtype=self.torch.int32, device=self.device)
+        rows = out if out is not None else \
+            self.torch.empty(max(cnt, 1), dtype=self.torch.int32, device=self.device)
+        assert rows.numel() >= cnt
         if cnt:
             self.ctx.bitmap_rows_after_count(bitmap, n, rows, cnt)  # reuses the block offsets of the count
         return rows[:cnt]

@@ -389,32 +389,13 @@ def build_models(rm, engine, table, res, continuous):
     return [(y, _train_model(rm, engine, table, res, y, continuous, tile_col)) for y in res.target_columns]
 
 
-def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=None, encoded_output=False):
-    """Phases 2-3 of RepairModel._run (model.py:1311-1408) on the device.
-
-    models: frozen output of build_models (skips the training phase).
-    encoded_output: return [(attr, row positions, current codes, repaired codes)] -- the
-    (tid, attribute, current_value, repaired) frame in dictionary-encoded form, already filtered --
-    instead of materialising Python strings."""
+def run_chain(engine, table, models, tile, ctile, D):
+    """Repair phase proper: the sequential chain over the targets on the dirty-row tile, in place
+    (the reference's `repair` pandas UDF, model.py:1096-1135)."""
     torch = engine.torch
-    targets = res.target_columns
     K = len(table.columns)
     tile_col = {c.name: i for i, c in enumerate(table.columns)}
     cont_idx = engine.dt.cont_index
-    cells = engine.cells_of(res, targets)           # (attr, rows, current codes), table order
-    if not cells:
-        return rm._input_frame(table) if repair_data else rm._empty_frame(table, repaired=True)
-    # models (training phase)
-    t0 = time.time()
-    if models is None:
-        models = build_models(rm, engine, table, res, continuous)
-        rm.last_run["models"] = models
-        rm.last_run["elapsed_training"] = time.time() - t0
-    models = [(y, m) for y, m in models if y in targets]
-    # repair phase: sequential chain over the targets on the dirty-row tile
-    t0 = time.time()
-    drows, tile, ctile = engine.build_dirty_tile(res, targets)
-    D = int(drows.numel())
     n_cc = len(cont_idx)
     words = (D + 31) // 32 + 1
     nullbits = torch.zeros(words, dtype=torch.int32, device=engine.device)
@@ -435,8 +416,92 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
             if m[1] is not None and not ycol.continuous:
                 engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, int(m[1]))
             continue
-        dm = m[1]
-        dm.predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
+        m[1].predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
+
+
+def repair_cells_encoded(rm, engine, table, res, models):
+    """Default-mode repair of an all-discrete table with frozen models, everything device-side:
+    -> [(attr, row positions int32, current codes, repaired codes)] already filtered like
+    model.py:1401.  One D2H of the result at the end (pinned), no per-attribute host round trips."""
+    torch = engine.torch
+    targets = res.target_columns
+    K = len(table.columns)
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    attrs = [a for a in table.names if a in targets and res.n_cells.get(a, 0) > 0]
+    E = sum(res.n_cells[a] for a in attrs)
+    rm.last_run["n_error_cells"] = E
+    if E == 0:
+        rm.last_run["n_dirty_rows"] = 0
+        return []
+    rows_all = torch.empty(E, dtype=torch.int32, device=engine.device)
+    cur_all = torch.empty(E, dtype=torch.int32, device=engine.device)
+    rep_all = torch.empty(E, dtype=torch.int32, device=engine.device)
+    seg, off = [], 0
+    for a in attrs:
+        n = res.n_cells[a]
+        rows = engine.bitmap_rows(res.bitmaps[a], out=rows_all[off:off + n])
+        engine.ctx.gather(engine.dt.col(a), rows, n, cur_all[off:off + n])
+        seg.append((a, off, n))
+        off += n
+    drows, tile, ctile = engine.build_dirty_tile(res, targets)
+    D = int(drows.numel())
+    rm.last_run["n_dirty_rows"] = D
+    run_chain(engine, table, [(y, m) for y, m in models if y in targets], tile, ctile, D)
+    dpos = torch.empty(E, dtype=torch.int32, device=engine.device)
+    engine.ctx.lookup_sorted(drows, D, rows_all, E, dpos)
+    for a, o, n in seg:
+        engine.ctx.tile_gather(tile, K, tile_col[a], dpos[o:o + n], n, rep_all[o:o + n])
+    keep = torch.zeros((E + 31) // 32 + 1, dtype=torch.int32, device=engine.device)
+    engine.ctx.changed_bitmap(cur_all, rep_all, E, keep)
+    idx = engine.bitmap_rows(keep, E)
+    n_keep = int(idx.numel())
+    host = torch.empty((4, max(n_keep, 1)), dtype=torch.int32, pin_memory=True)
+    packed = torch.empty((4, max(n_keep, 1)), dtype=torch.int32, device=engine.device)
+    if n_keep:
+        packed[0, :n_keep].copy_(idx)
+        engine.ctx.gather(rows_all, idx, n_keep, packed[1])
+        engine.ctx.gather(cur_all, idx, n_keep, packed[2])
+        engine.ctx.gather(rep_all, idx, n_keep, packed[3])
+    host.copy_(packed, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    h = host.numpy()
+    out = []
+    bounds = np.searchsorted(h[0, :n_keep], [o for _, o, _ in seg] + [E])
+    for (a, _, _), lo, hi in zip(seg, bounds[:-1], bounds[1:]):
+        out.append((a, h[1, lo:hi], h[2, lo:hi], h[3, lo:hi]))
+    return out
+
+
+def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=None, encoded_output=False):
+    """Phases 2-3 of RepairModel._run (model.py:1311-1408) on the device.
+
+    models: frozen output of build_models (skips the training phase).
+    encoded_output: return [(attr, row positions, current codes, repaired codes)] -- the
+    (tid, attribute, current_value, repaired) frame in dictionary-encoded form, already filtered --
+    instead of materialising Python strings."""
+    torch = engine.torch
+    targets = res.target_columns
+    K = len(table.columns)
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    cont_idx = engine.dt.cont_index
+    if encoded_output and models is not None and not engine.dt.cont_index:
+        return repair_cells_encoded(rm, engine, table, res, models)
+    cells = engine.cells_of(res, targets)           # (attr, rows, current codes), table order
+    if not cells:
+        return rm._input_frame(table) if repair_data else rm._empty_frame(table, repaired=True)
+    # models (training phase)
+    t0 = time.time()
+    if models is None:
+        models = build_models(rm, engine, table, res, continuous)
+        rm.last_run["models"] = models
+        rm.last_run["elapsed_training"] = time.time() - t0
+    models = [(y, m) for y, m in models if y in targets]
+    # repair phase: sequential chain over the targets on the dirty-row tile
+    t0 = time.time()
+    drows, tile, ctile = engine.build_dirty_tile(res, targets)
+    D = int(drows.numel())
+    n_cc = len(cont_idx)
+    run_chain(engine, table, models, tile, ctile, D)
     # output: (row id, attribute, current_value, repaired) for the error cells
     ids, attrs, curs, reps = [], [], [], []
     repaired_cells = []

@@ -182,3 +182,26 @@ def test_standalone_detector_protocol():
     assert sorted(zip(out.tid.tolist(), out.attribute.tolist())) == [(4, "Relationship"), (11, "Relationship")]
     out = NullErrorDetector().setUp("tid", df, [], ["Non-existent"]).detect()
     assert len(out) == 0
+
+
+def test_encoded_output_with_frozen_models_matches_string_frame():
+    """bench.py's path (frozen models, dictionary-encoded frame assembled on the device) == public API."""
+    from repair.engine import Engine
+    from repair.errors import ErrorModelOptions
+    from repair.model import repair_cells
+    spec, names, codes, enc, specs = PU.synth_inputs(30000, 16, seed=5, c4=True)
+    opts = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": 8, "model.max_training_row_num": 1500}
+    rm, out = PU.run_product(enc, "tid", specs, None, 80, opts, encoded=True)
+    want = PU.frame_tuples(out, "tid")
+    engine = Engine(enc, 0)
+    try:
+        res = engine.detect(specs, [], 80, ErrorModelOptions.resolve({k: str(v) for k, v in opts.items()}))
+        cells = repair_cells(rm, engine, enc, res, [], models=rm.last_run["models"], encoded_output=True)
+    finally:
+        engine.close()
+    got = []
+    for a, rows, cur, rep in cells:
+        col = enc.by_name[a]
+        for r, c, p in zip(rows.tolist(), col.decode(cur), col.decode(rep)):
+            got.append((str(r), a, c, p))
+    assert sorted(got, key=lambda t: (t[0], t[1])) == want
