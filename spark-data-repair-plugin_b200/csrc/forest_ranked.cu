@@ -4,9 +4,9 @@
 // cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~40 KB of features
 // and 16 warps stay resident per SM.  The forest is streamed through shared memory in chunks of whole
 // trees by the TMA engine (cp.async.bulk + mbarrier, double buffered: chunk k+1 lands while chunk k is
-// walked).  Each thread walks FOUR trees at a time for a fixed number of levels -- leaves point at
+// walked).  Each thread walks kIlp trees at a time for a fixed number of levels -- leaves point at
 // themselves, NaN is folded into two rank variants -- so a level is two shared-memory loads and six ALU
-// ops with no data-dependent branch, and the four dependent chains overlap.  Leaf values are float64
+// ops with no data-dependent branch, and the kIlp dependent chains overlap.  Leaf values are float64
 // and are added to the sequence's accumulator in tree order: margins are bit-identical to the generic
 // kernel and to the oracle.
 #include "common.cuh"
@@ -16,6 +16,10 @@ namespace {
 constexpr int T = 256;
 constexpr int kChunkNodes = DR_RANKED_CHUNK_NODES;
 constexpr int kChunkLeaves = DR_RANKED_CHUNK_LEAVES;
+#ifndef DR_FOREST_ILP
+#define DR_FOREST_ILP 8
+#endif
+constexpr int kIlp = DR_FOREST_ILP;  // trees walked concurrently per thread
 
 struct RankedParams {
     dr_forest_ranked f;
@@ -138,20 +142,21 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
             const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
             const int n0 = F.tree_node_off[ta], l0 = F.tree_leaf_off[ta];
             int q = ta;
-            for (; q + 4 <= tb; q += 4) {
-                const int r0 = F.tree_node_off[q] - n0, r1 = F.tree_node_off[q + 1] - n0;
-                const int r2 = F.tree_node_off[q + 2] - n0, r3 = F.tree_node_off[q + 3] - n0;
-                uint32_t w0 = nodes[r0], w1 = nodes[r1], w2 = nodes[r2], w3 = nodes[r3];
-                for (int d = 0; d < depth; ++d) {
-                    w0 = step_node(nodes, r0, w0, my_feat);
-                    w1 = step_node(nodes, r1, w1, my_feat);
-                    w2 = step_node(nodes, r2, w2, my_feat);
-                    w3 = step_node(nodes, r3, w3, my_feat);
+            for (; q + kIlp <= tb; q += kIlp) {
+                int root[kIlp];
+                uint32_t w[kIlp];
+#pragma unroll
+                for (int j = 0; j < kIlp; ++j) {
+                    root[j] = F.tree_node_off[q + j] - n0;
+                    w[j] = nodes[root[j]];
                 }
-                acc += leaves[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
-                acc += leaves[F.tree_leaf_off[q + 1] - l0 + (int)((w1 >> 12) & 0xFFu)];
-                acc += leaves[F.tree_leaf_off[q + 2] - l0 + (int)((w2 >> 12) & 0xFFu)];
-                acc += leaves[F.tree_leaf_off[q + 3] - l0 + (int)((w3 >> 12) & 0xFFu)];
+                for (int d = 0; d < depth; ++d) {
+#pragma unroll
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node(nodes, root[j], w[j], my_feat);
+                }
+#pragma unroll
+                for (int j = 0; j < kIlp; ++j)  // tree order: bit-identical float64 sums
+                    acc += leaves[F.tree_leaf_off[q + j] - l0 + (int)((w[j] >> 12) & 0xFFu)];
             }
             for (; q < tb; ++q) {
                 const int r0 = F.tree_node_off[q] - n0;
