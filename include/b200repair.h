@@ -251,26 +251,30 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  * node is ONE 32-bit word and a cell's feature vector is one byte per feature, which is what lets
  * 16+ warps per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins
  * remain bit-identical to dr_forest_predict / the oracle.
- *   node word: bits 21..31 feature, bit 20 NaN-goes-left, bits 12..19 thr_rank + 1, bits 6..11 left
- *              child, bits 0..5 right child (relative to the tree root; trees have at most 64 nodes).
- *              A LEAF points at itself (left = right = own index) with feature 0 and its leaf index
- *              (within the tree, < 256) in bits 12..19, so the walk is branch-free.
- *   rank_lut:  uint8, rank (0..253) of feature f of a row = rank_lut[rank_lut_off[f] +
- *              tile[row][feat_col[f]] + 1], 255 = NaN; the kernel compares (rank + 1) < (thr_rank + 1)
- *              with NaN mapped to 0 / 255 according to the node's NaN direction.
+ *   node word (all fields byte aligned): byte 3 = 2 * feature + (NaN goes left), byte 2 = thr_rank + 1,
+ *              byte 1 = left child, byte 0 = right child, both as BYTE offsets from the tree root
+ *              (4 * node index; trees have at most 64 nodes; at most 127 features).
+ *              A LEAF points at itself (left = right = own offset) with byte 3 = 0 and its leaf index
+ *              (within the tree) in byte 2, so the walk is branch-free.
+ *   rank_lut:  uint8, rank + 1 (1..254) of feature f of a row = rank_lut[rank_lut_off[f] +
+ *              tile[row][feat_col[f]] + 1], 255 = NaN; the kernel compares it with thr_rank + 1, NaN
+ *              mapped to 0 / 255 according to the node's NaN direction.
  *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels).
  *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered),
  *   so every tree's node words are padded to a multiple of 4 and its leaf values to a multiple of 2
  *   (16-byte granules), and the host supplies the chunk table: chunk c = trees
  *   [chunk_tree_off[c], chunk_tree_off[c+1]) of sequence chunk_seq[c], at most DR_RANKED_CHUNK_NODES
  *   node words and DR_RANKED_CHUNK_LEAVES leaf values, never straddling a sequence; every sequence
- *   has at least one tree. */
+ *   has at least one tree and a chunk at most 256 trees.  tree_hdr[chunk_hdr_off[c] + j] = (first node word of the chunk's j-th
+ *   tree << 16) | its first leaf, both relative to the chunk (chunk_hdr_off is a multiple of 4). */
 #define DR_RANKED_CHUNK_NODES 4096
 #define DR_RANKED_CHUNK_LEAVES 2176
 typedef struct dr_forest_ranked {
     int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth, n_chunks;
     const int32_t* chunk_tree_off;
     const int32_t* chunk_seq;
+    const int32_t* chunk_hdr_off;
+    const uint32_t* tree_hdr;
     const int32_t* seq_tree_off;
     const int32_t* tree_node_off;
     const int32_t* tree_leaf_off;

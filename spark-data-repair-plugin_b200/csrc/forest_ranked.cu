@@ -60,19 +60,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// One level: two shared-memory loads (feature rank, next node word) and six ALU ops.  Leaves point
-// at themselves (left = right = own index), so a finished tree just re-reads its leaf word.
-__device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, int root, uint32_t w,
+// One level: two shared-memory loads (feature rank, next node word) and five ALU ops.  All fields
+// of the node word are byte aligned (PRMT extracts), children are stored as byte offsets from the
+// tree root, leaves point at themselves (left = right = own offset).
+__device__ __forceinline__ uint32_t step_node(const unsigned char* __restrict__ tree, uint32_t w,
                                               const uint8_t* __restrict__ my_feat) {
-    const uint32_t r = my_feat[w >> 20];  // rank of feature (w >> 21), NaN-left / NaN-right variant
-    const uint32_t thr = (w >> 12) & 0xFFu;
-    const uint32_t child = (r < thr) ? ((w >> 6) & 0x3Fu) : (w & 0x3Fu);
-    return nodes[root + (int)child];
+    const uint32_t r = my_feat[w >> 24];                       // rank, NaN-left / NaN-right variant
+    const uint32_t thr = __byte_perm(w, 0, 0x4442);            // byte 2
+    const uint32_t off = __byte_perm(w, 0, r < thr ? 0x4441 : 0x4440);  // byte 1 (left) or byte 0 (right)
+    return *reinterpret_cast<const uint32_t*>(tree + off);
 }
+
+constexpr int kChunkTrees = 256;  // trees per chunk (host caps the chunk table accordingly)
 
 struct __align__(16) ChunkBuf {
     double leaf[kChunkLeaves];
     uint32_t node[kChunkNodes];
+    uint32_t hdr[kChunkTrees];  // per tree of the chunk: (first node word << 16) | first leaf, chunk relative
 };
 
 __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
@@ -96,10 +100,12 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
         const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
         const int n0 = F.tree_node_off[ta], n1 = F.tree_node_off[tb];
         const int l0 = F.tree_leaf_off[ta], l1 = F.tree_leaf_off[tb];
-        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u;
-        mbar_expect_tx(&bar[b], nb + lb);
+        const int h0 = F.chunk_hdr_off[c], h1 = F.chunk_hdr_off[c + 1];
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u, hb = (uint32_t)(h1 - h0) * 4u;
+        mbar_expect_tx(&bar[b], nb + lb + hb);
         bulk_g2s(buf[b].node, F.node_word + n0, nb, &bar[b]);
         bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &bar[b]);
+        bulk_g2s(buf[b].hdr, F.tree_hdr + h0, hb, &bar[b]);
     };
 
     for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
@@ -137,32 +143,32 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
             }
             if (b == 0) { while (!mbar_try_wait(&bar[0], phase0)) {} phase0 ^= 1; }
             else        { while (!mbar_try_wait(&bar[1], phase1)) {} phase1 ^= 1; }
-            const uint32_t* __restrict__ nodes = buf[b].node;
+            const unsigned char* __restrict__ nodes = reinterpret_cast<const unsigned char*>(buf[b].node);
             const double* __restrict__ leaves = buf[b].leaf;
-            const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
-            const int n0 = F.tree_node_off[ta], l0 = F.tree_leaf_off[ta];
-            int q = ta;
-            for (; q + kIlp <= tb; q += kIlp) {
-                int root[kIlp];
+            const uint32_t* __restrict__ hdr = buf[b].hdr;
+            const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
+            int q = 0;
+            for (; q + kIlp <= n_trees; q += kIlp) {
+                const unsigned char* tree[kIlp];
                 uint32_t w[kIlp];
 #pragma unroll
                 for (int j = 0; j < kIlp; ++j) {
-                    root[j] = F.tree_node_off[q + j] - n0;
-                    w[j] = nodes[root[j]];
+                    tree[j] = nodes + (hdr[q + j] >> 16) * 4u;
+                    w[j] = *reinterpret_cast<const uint32_t*>(tree[j]);
                 }
                 for (int d = 0; d < depth; ++d) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) w[j] = step_node(nodes, root[j], w[j], my_feat);
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node(tree[j], w[j], my_feat);
                 }
 #pragma unroll
                 for (int j = 0; j < kIlp; ++j)  // tree order: bit-identical float64 sums
-                    acc += leaves[F.tree_leaf_off[q + j] - l0 + (int)((w[j] >> 12) & 0xFFu)];
+                    acc += leaves[(hdr[q + j] & 0xFFFFu) + __byte_perm(w[j], 0, 0x4442)];
             }
-            for (; q < tb; ++q) {
-                const int r0 = F.tree_node_off[q] - n0;
-                uint32_t w0 = nodes[r0];
-                for (int d = 0; d < depth; ++d) w0 = step_node(nodes, r0, w0, my_feat);
-                acc += leaves[F.tree_leaf_off[q] - l0 + (int)((w0 >> 12) & 0xFFu)];
+            for (; q < n_trees; ++q) {
+                const unsigned char* tree = nodes + (hdr[q] >> 16) * 4u;
+                uint32_t w0 = *reinterpret_cast<const uint32_t*>(tree);
+                for (int d = 0; d < depth; ++d) w0 = step_node(tree, w0, my_feat);
+                acc += leaves[(hdr[q] & 0xFFFFu) + __byte_perm(w0, 0, 0x4442)];
             }
             __syncthreads();  // buffer b may be refilled (chunk c + 2) only after everybody left it
         }
@@ -185,9 +191,10 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (n_cells <= 0) return DR_OK;
     DR_REQUIRE(ctx, forest && cells && tile, "null pointer");
     const dr_forest_ranked& f = *forest;
-    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 2047, "bad forest sizes");
+    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 127, "the ranked kernel takes at most 127 features");
     DR_REQUIRE(ctx, f.seq_tree_off && f.tree_node_off && f.tree_leaf_off && f.baseline && f.feat_col &&
-                        f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq && f.node_word &&
+                        f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq && f.chunk_hdr_off && f.tree_hdr &&
+                        f.node_word &&
                         f.leaf_value, "null forest array");
     DR_REQUIRE(ctx, f.n_chunks >= 1, "the ranked forest needs at least one chunk (one tree per sequence)");
     DR_REQUIRE(ctx, ((uintptr_t)f.node_word & 15) == 0 && ((uintptr_t)f.leaf_value & 15) == 0,

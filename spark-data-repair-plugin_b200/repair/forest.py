@@ -137,7 +137,7 @@ def rank_code(spec, dict_sizes):
             luts.append(lut[:, j])
             feat_attr.append(e["attr"])
     n_feat = len(luts)
-    if n_feat != int(f["n_features"]) or n_feat >= 2047:
+    if n_feat != int(f["n_features"]) or n_feat > 127:
         return None
     toff = np.asarray(f["tree_offset"], dtype=np.int64)
     sizes = toff[1:] - toff[:-1]
@@ -171,12 +171,13 @@ def rank_code(spec, dict_sizes):
     node_in_tree = (np.arange(len(feat)) - toff[tree_of]).astype(np.uint32) if len(feat) else np.zeros(0, np.uint32)
     if len(leaf_idx) and leaf_idx.max() > 255:
         return None
-    internal = ((np.where(is_leaf, 0, feat).astype(np.uint32) << np.uint32(21)) |
-                ((np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)) << np.uint32(20)) |
-                ((thr_rank + np.uint32(1)) << np.uint32(12)) |
-                ((np.asarray(f["left"], dtype=np.uint32) & np.uint32(0x3F)) << np.uint32(6)) |
-                (np.asarray(f["right"], dtype=np.uint32) & np.uint32(0x3F)))
-    leaf = (leaf_idx.astype(np.uint32) << np.uint32(12)) | (node_in_tree << np.uint32(6)) | node_in_tree
+    ml = np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)
+    internal = (((np.where(is_leaf, 0, feat).astype(np.uint32) * np.uint32(2) + ml) << np.uint32(24)) |
+                ((thr_rank + np.uint32(1)) << np.uint32(16)) |
+                ((np.asarray(f["left"], dtype=np.uint32) * np.uint32(4)) << np.uint32(8)) |
+                (np.asarray(f["right"], dtype=np.uint32) * np.uint32(4)))
+    leaf = (leaf_idx.astype(np.uint32) << np.uint32(16)) | ((node_in_tree * np.uint32(4)) << np.uint32(8)) | \
+        (node_in_tree * np.uint32(4))
     word = np.where(is_leaf, leaf, internal).astype(np.uint32)
     # deepest leaf: breadth-first sweep over all trees at once
     depth, frontier = 0, toff[:-1].copy()
@@ -221,20 +222,26 @@ def ranked_image(rk, toff, order, seq_tree_off):
     lwithin = np.arange(int(l_sizes.sum())) - np.repeat(np.cumsum(l_sizes) - l_sizes, l_sizes)
     lsrc = np.repeat(lo[:-1][order], l_sizes) + lwithin
     leaf[leaf_off[ltree_new] + lwithin] = rk["leaf_value"][lsrc]
-    chunk_tree_off, chunk_seq = [0], []
+    chunk_tree_off, chunk_seq, chunk_hdr_off, hdr = [0], [], [0], []
     for s in range(len(seq_tree_off) - 1):
         t, t_end = int(seq_tree_off[s]), int(seq_tree_off[s + 1])
         while t < t_end:
             # largest hi with node/leaf footprint of trees [t, hi) inside the chunk buffers
             hi_n = int(np.searchsorted(node_off, node_off[t] + RANKED_CHUNK_NODES, side="right")) - 1
             hi_l = int(np.searchsorted(leaf_off, leaf_off[t] + RANKED_CHUNK_LEAVES, side="right")) - 1
-            hi = max(t + 1, min(hi_n, hi_l, t_end))
+            hi = max(t + 1, min(hi_n, hi_l, t_end, t + 256))
             chunk_tree_off.append(hi)
             chunk_seq.append(s)
+            h = ((node_off[t:hi] - node_off[t]) << 16) | (leaf_off[t:hi] - leaf_off[t])
+            pad = (-len(h)) % 4
+            hdr.append(np.concatenate([h, np.zeros(pad, dtype=np.int64)]))
+            chunk_hdr_off.append(chunk_hdr_off[-1] + len(h) + pad)
             t = hi
     return {"word": word, "leaf": leaf, "node_off": node_off, "leaf_off": leaf_off,
             "chunk_tree_off": np.asarray(chunk_tree_off, dtype=np.int32),
-            "chunk_seq": np.asarray(chunk_seq, dtype=np.int32)}
+            "chunk_seq": np.asarray(chunk_seq, dtype=np.int32),
+            "chunk_hdr_off": np.asarray(chunk_hdr_off, dtype=np.int32),
+            "tree_hdr": np.concatenate(hdr).astype(np.uint32) if hdr else np.zeros(4, dtype=np.uint32)}
 
 
 class DeviceModel:
@@ -313,6 +320,8 @@ class DeviceModel:
                 "r_tree_leaf_off": dev(img["leaf_off"], np.int32),
                 "r_chunk_tree_off": dev(img["chunk_tree_off"], np.int32),
                 "r_chunk_seq": dev(img["chunk_seq"], np.int32),
+                "r_chunk_hdr_off": dev(img["chunk_hdr_off"], np.int32),
+                "r_tree_hdr": dev(img["tree_hdr"].view(np.int32), np.int32),
                 "r_rank_lut": dev(rk["rank_lut"], np.uint8),
                 "r_rank_lut_off": dev(rk["rank_lut_off"], np.int32),
                 "r_feat_col": dev([feature_tile_cols[a] for a in rk["feat_attr"]] or [0], np.int32),
@@ -321,6 +330,7 @@ class DeviceModel:
             r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, len(img["word"]), len(img["leaf"])
             r.n_feat, r.max_depth, r.n_chunks = n_feat, int(rk["max_depth"]), len(img["chunk_seq"])
             for field, key in (("chunk_tree_off", "r_chunk_tree_off"), ("chunk_seq", "r_chunk_seq"),
+                               ("chunk_hdr_off", "r_chunk_hdr_off"), ("tree_hdr", "r_tree_hdr"),
                                ("seq_tree_off", "seq_tree_off"), ("tree_node_off", "r_tree_node_off"),
                                ("tree_leaf_off", "r_tree_leaf_off"), ("node_word", "r_node_word"),
                                ("leaf_value", "r_leaf_value"), ("baseline", "baseline"), ("feat_col", "r_feat_col"),

@@ -405,13 +405,13 @@ def _eval_ranked(rk, forest, codes_by_feat):
         for i in range(n):
             w = int(rk["word"][toff[t]])
             for _ in range(rk["max_depth"]):
-                feat, nan_left = w >> 21, (w >> 20) & 1
-                r = int(ranks[feat][i])
-                r = (0 if nan_left else 255) if r == 255 else r
-                go_left = r < ((w >> 12) & 0xFF)
-                w = int(rk["word"][toff[t] + (((w >> 6) & 0x3F) if go_left else (w & 0x3F))])
-            assert ((w >> 6) & 0x3F) == (w & 0x3F)  # a leaf points at itself
-            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + ((w >> 12) & 0xFF)]
+                fidx = w >> 24
+                r = int(ranks[fidx >> 1][i])
+                r = (0 if (fidx & 1) else 255) if r == 255 else r
+                go_left = r < ((w >> 16) & 0xFF)
+                w = int(rk["word"][toff[t] + (((w >> 8) & 0xFF) if go_left else (w & 0xFF)) // 4])
+            assert ((w >> 8) & 0xFF) == (w & 0xFF)  # a leaf points at itself
+            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + ((w >> 16) & 0xFF)]
     return raw
 
 
