@@ -45,6 +45,12 @@ int dr_abi_version(void);
 /* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
 int64_t dr_launch_count(const dr_ctx* ctx);
 
+/* ---- ingest ----------------------------------------------------------------------------------------
+ * Replaces handing Spark view names across Py4J (model.py:477-480): label-encoded columns whose
+ * dictionary has <= 254 entries travel host -> device as ONE byte per cell (255 = NULL) and are
+ * widened to the int32 table layout here (4x less PCIe traffic than int32 codes). */
+int dr_widen_u8(dr_ctx* ctx, const uint8_t* src, int64_t n, int32_t* dst, void* stream);
+
 /* ---- a2 + a7/a8: NULL scan fused with per-column histograms ------------------------------------
  * Replaces ErrorDetectorApi.detectNullCells (ErrorDetectorApi.scala:30-34,128-157: K_t UNION-ALL
  * scans) and the single-attribute GROUPING SETS of RepairApi.computeFreqStats

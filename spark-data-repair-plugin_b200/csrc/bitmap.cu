@@ -223,6 +223,33 @@ __global__ void __launch_bounds__(kThreads) k_tile_null_bitmaps(const int32_t* _
     }
 }
 
+// Ingest: codes of small dictionaries cross PCIe as one byte each (255 = NULL) and are widened to
+// the int32 layout on the device: 16 codes per thread, 128-bit load -> four 128-bit stores.
+__global__ void __launch_bounds__(kThreads) k_widen_u8(const uint8_t* __restrict__ src, int64_t n,
+                                                       int32_t* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n16 = n >> 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int4* out = reinterpret_cast<int4*>(dst) + i * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int4 o;
+            const uint32_t b0 = w[j] & 0xFF, b1 = (w[j] >> 8) & 0xFF, b2 = (w[j] >> 16) & 0xFF, b3 = w[j] >> 24;
+            o.x = b0 == 255 ? -1 : (int)b0;
+            o.y = b1 == 255 ? -1 : (int)b1;
+            o.z = b2 == 255 ? -1 : (int)b2;
+            o.w = b3 == 255 ? -1 : (int)b3;
+            __stcs(out + j, o);
+        }
+    }
+    for (int64_t i = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t b = src[i];
+        dst[i] = b == 255 ? -1 : (int)b;
+    }
+}
+
 // bit i = repaired[i] IS NULL OR NOT(current[i] <=> repaired[i])  (model.py:1401), on codes
 __global__ void __launch_bounds__(kThreads) k_changed_bitmap(const int32_t* __restrict__ cur,
                                                              const int32_t* __restrict__ rep, int64_t n,
@@ -377,6 +404,17 @@ int dr_tile_null_bitmaps(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols
     DR_REQUIRE(ctx, tile && out && words_per_col >= (n + 31) / 32, "bad arguments");
     k_tile_null_bitmaps<<<dr_grid_for(ctx, (n + 31) / 32, kThreads / 32, kCtasPerSm), kThreads, 0,
                           (cudaStream_t)stream>>>(tile, n, n_cols, words_per_col, out);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_widen_u8(dr_ctx* ctx, const uint8_t* src, int64_t n, int32_t* dst, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, src && dst, "null pointer");
+    DR_REQUIRE(ctx, ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "buffers must be 16-byte aligned");
+    k_widen_u8<<<dr_grid_for(ctx, (n + 15) / 16, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(src, n,
+                                                                                                            dst);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "dr_last_error": (c_char_p, [c_void_p]),
     "dr_abi_version": (c_int, []),
     "dr_launch_count": (c_int64, [c_void_p]),
+    "dr_widen_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_scan_hist": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, c_int64, _PP, c_void_p, c_void_p]),
     "dr_lut_scan": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "dr_quartiles": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_int64), c_void_p]),
@@ -171,6 +172,9 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.dr_launch_count(self._h))
+
+    def widen_u8(self, src, n, dst):
+        self._check(self.lib.dr_widen_u8(self._h, _dp(src), n, _dp(dst), self._stream()))
 
     # ---- detectors -------------------------------------------------------------------------------
     def scan_hist(self, cols, dom, n_rows, bitmaps, hist):
@@ -316,7 +320,7 @@ def _profiled(name, fn):
     return wrapper
 
 
-for _name in ("scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
+for _name in ("widen_u8", "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill"):

@@ -62,7 +62,7 @@ class Engine:
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
         self.table = table
-        self.dt = device_table if device_table is not None else DeviceTable(table, self.device)
+        self.dt = device_table if device_table is not None else DeviceTable(table, self.device, ctx=self.ctx)
         self.dist = dist
         self.n_rows = table.n_rows
         self.n_words = (self.dt.n_pad + 31) // 32

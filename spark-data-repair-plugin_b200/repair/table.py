@@ -32,9 +32,9 @@ class Column:
         if len(self.dictionary) == 0:
             return -2
         if self.kind == "str":
-            i = int(np.searchsorted(self.dictionary.astype(str) if self.dictionary.dtype != object else
-                                    np.array(self.dictionary, dtype=object).astype(str), str(value)))
-            return i if i < len(self.dictionary) and str(self.dictionary[i]) == str(value) else -2
+            if getattr(self, "_lut", None) is None:
+                self._lut = {str(v): i for i, v in enumerate(self.dictionary)}
+            return self._lut.get(str(value), -2)
         try:
             x = float(value)
         except (TypeError, ValueError):
@@ -197,7 +197,7 @@ class DeviceTable:
     """The encoded table resident in HBM: ``codes`` int32 [K][n_pad] (one contiguous column per
     attribute) and ``values`` float64 [Kc][n_pad] for the continuous attributes."""
 
-    def __init__(self, table, device, codes=None, values=None):
+    def __init__(self, table, device, codes=None, values=None, ctx=None):
         import torch
         self.table = table
         self.device = device
@@ -208,10 +208,21 @@ class DeviceTable:
         if codes is None:
             codes = torch.empty((K, self.n_pad), dtype=torch.int32, device=device)
             staging = torch.empty((self.n_pad,), dtype=torch.int32).pin_memory()
+            narrow = narrow_dev = None
             for i, c in enumerate(table.columns):
-                staging[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.codes)))
-                staging[self.n_rows:].fill_(-1)
-                codes[i].copy_(staging, non_blocking=True)
+                if c.dict_size <= 254 and ctx is not None:
+                    # small dictionaries cross PCIe as one byte per cell and are widened on the device
+                    if narrow is None:
+                        narrow = torch.empty((self.n_pad,), dtype=torch.uint8).pin_memory()
+                        narrow_dev = torch.empty((self.n_pad,), dtype=torch.uint8, device=device)
+                    narrow[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.codes).astype(np.uint8)))
+                    narrow[self.n_rows:].fill_(255)
+                    narrow_dev.copy_(narrow, non_blocking=True)
+                    ctx.widen_u8(narrow_dev, self.n_pad, codes[i])
+                else:
+                    staging[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.codes)))
+                    staging[self.n_rows:].fill_(-1)
+                    codes[i].copy_(staging, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         self.codes = codes
         if values is None and self.cont_index:

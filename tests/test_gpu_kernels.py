@@ -472,3 +472,17 @@ def test_dc_fd_large_key_space_uses_global_tables(ctx):
     viol_key = dict(zip(ks[starts].tolist(), (mn != mx).tolist()))
     want = np.array([viol_key[kk] for kk in key.tolist()])
     assert np.array_equal(bits_of(bm, n), want)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 1000, 128 * 4001])
+def test_widen_u8(ctx, n):
+    rng = np.random.default_rng(n)
+    codes = rng.integers(-1, 254, size=n).astype(np.int32)
+    n_pad = (n + 127) // 128 * 128
+    src = np.full(n_pad, 255, dtype=np.uint8)
+    src[:n] = codes.astype(np.uint8)
+    dst = torch.empty(n_pad, dtype=torch.int32, device="cuda")
+    ctx.widen_u8(dev(src), n_pad, dst)
+    want = np.full(n_pad, -1, dtype=np.int32)
+    want[:n] = codes
+    assert np.array_equal(dst.cpu().numpy(), want)
