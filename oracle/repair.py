@@ -165,8 +165,82 @@ def column_values(tbl, name, rows=None):
     return [tbl.value(name, int(r)) for r in idx]
 
 
+def levenshtein(a, b):
+    """python-Levenshtein distance as used by costs.Levenshtein (costs.py:38-49)."""
+    a, b = str(a), str(b)
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return float(prev[-1])
+
+
+class _Unknown:
+    """Stands for the JSON pmf string the reference writes into a repaired cell in pmf mode
+    (model.py:1118-1128): later models see a value that is neither NULL nor a known category."""
+
+    def __repr__(self):
+        return "<pmf>"
+
+
+UNKNOWN = _Unknown()
+
+
+def shape_pmf(cells_pmf, opts=None, cost_fn=None, cost_targets=None):
+    """_compute_repair_pmf (model.py:1174-1225).  cells_pmf: [(rid, attr, cur, classes, probs)]
+    (classes None for continuous: pmf = [(value, 1.0)]).
+    -> [(rid, attr, (cur, cur_prob), [(class, prob)] sorted by prob desc, filtered, top-k)]"""
+    thr = float((opts or {}).get("repair.pmf.prob_threshold", 0.0))
+    top_k = int((opts or {}).get("repair.pmf.prob_top_k", 32))
+    weight = float((opts or {}).get("repair.pmf.cost_weight", 0.1))
+    out = []
+    for rid, attr, cur, classes, probs in cells_pmf:
+        if classes is None:
+            out.append((rid, attr, (cur, 0.0), [(probs, 1.0)]))
+            continue
+        classes = [cast_to_string("str", c) if isinstance(c, str) else
+                   (str(c) if not isinstance(c, float) else cast_to_string("float", c)) for c in classes]
+        probs = [float(p) for p in probs][:len(classes)]
+        if cost_fn is not None and (not cost_targets or attr in cost_targets) and cur:
+            probs = [p * (1.0 / (1.0 + weight * cost_fn(cur, c))) for p, c in zip(probs, classes)]
+        if cost_fn is not None:
+            norm = 0.0
+            for p in probs:
+                norm += p
+            probs = [p / norm for p in probs]
+        cur_prob = probs[classes.index(cur)] if cur in classes else 0.0
+        pmf = sorted(zip(classes, probs), key=lambda t: -t[1])  # stable: ties keep class order
+        pmf = [t for t in pmf if t[1] > thr][:top_k]
+        out.append((rid, attr, (cur, cur_prob), pmf))
+    return out
+
+
+def compute_score(shaped, cost_fn):
+    """_compute_score (model.py:1227-1248) -> [(rid, attr, cur, repaired, score)]"""
+    import math
+    out = []
+    for rid, attr, (cur, cur_prob), pmf in shaped:
+        rep, rep_prob = pmf[0]
+        base = cur if cur is not None else rep
+        cost = cost_fn(base, rep)
+        cost = 256.0 if cost is None else cost
+        score = math.log(rep_prob / (cur_prob if cur_prob > 0.0 else 1e-6)) * (1.0 / (1.0 + cost))
+        out.append((rid, attr, cur, rep, score))
+    return out
+
+
+def maximal_likelihood_repair(scored, delta):
+    """_maximal_likelihood_repair (model.py:1259-1277): keep score >= percentile(score, 1 - delta/n)."""
+    n = len(scored)
+    percent = min(1.0, 1.0 - delta / n)
+    thres = D.spark_percentile(sorted(s[4] for s in scored), percent)
+    return [s[:4] for s in scored if s[4] >= thres]
+
+
 def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stats, continuous, opts,
-           model_provider, repair_data=False):
+           model_provider, repair_data=False, pmf_mode=False):
     """RepairModel._run phases 2-3 (model.py:1311-1408), default mode.
 
     ``model_provider(ctx) -> spec`` is called once per target that needs a statistical model with
@@ -216,9 +290,25 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
         models.append((y, spec, features, encoders))
     # ---- repair UDF (model.py:1096-1135): sequential chain over targets on the dirty rows ----
     dirty = base.take(np.array(dirty_pos, dtype=np.int64))
+    for c in dirty.names:  # pmf mode parks JSON strings in repaired cells: needs object columns
+        if pmf_mode and dirty.kinds[c] == "str" and dirty.cols[c].dtype != object:
+            dirty.cols[c] = np.array([None if v < 0 else int(v) for v in dirty.cols[c]], dtype=object)
+    pmf_of = {}
     for (y, spec, features, encoders) in models:
         ycol = dirty.cols[y]
         n = dirty.n_rows
+        if pmf_mode and y not in continuous:  # model.py:1118-1128
+            from .forest import forest_proba
+            if "const" in spec:
+                classes, probs = [spec["const"]], [[1.0]] * n
+            else:
+                X = encode_rows(encoders, {f: column_values(dirty, f) for f in features})
+                classes, probs = spec["classes"], forest_proba(spec["forest"], X)
+            for i in range(n):
+                if dirty.value(y, i) is None:
+                    pmf_of[(dirty_pos[i], y)] = (classes, list(probs[i]))
+                    ycol[i] = UNKNOWN
+            continue
         if "const" in spec:
             pred = [spec["const"]] * n
         else:
@@ -239,6 +329,17 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
                     ycol[i] = -1 if v is None else int(v)
                 else:
                     ycol[i] = np.nan if v is None else float(v)
+    if pmf_mode:
+        dpos = {r: i for i, r in enumerate(dirty_pos)}
+        out = []
+        for (r, a, cur) in error_cells:
+            rid = cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r))
+            if a in continuous:
+                out.append((rid, a, cur, None, cast_to_string(dirty.kinds[a], dirty.value(a, dpos[r]))))
+            else:
+                classes, probs = pmf_of[(r, a)]
+                out.append((rid, a, cur, classes, probs))
+        return out
     if repair_data:
         out = base.copy()
         for i, r in enumerate(dirty_pos):
@@ -257,7 +358,7 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
 
 
 def run(tbl, row_id, detectors=None, targets=None, discrete_thres=80, given_error_cells=None, opts=None,
-        model_provider=None, detect_errors_only=False, repair_data=False):
+        model_provider=None, detect_errors_only=False, repair_data=False, pmf_mode=False):
     """RepairModel.run, default / detect_errors_only / repair_data modes."""
     continuous = S.check_input_table(tbl, row_id)
     targets = targets or []
@@ -270,4 +371,4 @@ def run(tbl, row_id, detectors=None, targets=None, discrete_thres=80, given_erro
     if not cells:
         return tbl if repair_data else []
     return repair(tbl, row_id, cells, target_columns, pairwise, domain_stats, continuous, opts,
-                  model_provider, repair_data=repair_data)
+                  model_provider, repair_data=repair_data, pmf_mode=pmf_mode)

@@ -58,6 +58,35 @@ __device__ __forceinline__ void load_chunk(int4 (&v)[kTilesPerChunk], const int3
         v[t] = __ldcs(reinterpret_cast<const int4*>(col + base + t * kTileRows) + lane);
 }
 
+// Counts the four codes of one 128-bit load.  The four bin addresses may coincide (same lane, same
+// column), so instead of four dependent read-modify-writes the four bins are LOADED together, each
+// new value gets +1 for itself and +1 for every earlier equal code of the quad, and the four stores
+// go out in order -- the last store to an address carries the full count.  One shared-memory latency
+// per quad instead of four.
+__device__ __forceinline__ void count_quad(int32_t* b, unsigned dom, const int4 q) {
+    const unsigned s0 = min((unsigned)(q.x + 1), dom), s1 = min((unsigned)(q.y + 1), dom);
+    const unsigned s2 = min((unsigned)(q.z + 1), dom), s3 = min((unsigned)(q.w + 1), dom);
+    const int v0 = b[s0 * 32], v1 = b[s1 * 32], v2 = b[s2 * 32], v3 = b[s3 * 32];
+    b[s0 * 32] = v0 + 1;
+    b[s1 * 32] = v1 + 1 + (s1 == s0);
+    b[s2 * 32] = v2 + 1 + (s2 == s0) + (s2 == s1);
+    b[s3 * 32] = v3 + 1 + (s3 == s0) + (s3 == s1) + (s3 == s2);
+}
+
+__device__ __forceinline__ void count_chunk(const int4 (&v)[kTilesPerChunk], int32_t* b, unsigned dom,
+                                            uint32_t* __restrict__ bm, int64_t base, int lane) {
+#pragma unroll
+    for (int t = 0; t < kTilesPerChunk; ++t) {
+        const int4 q = v[t];
+        count_quad(b, dom, q);
+        if (bm != nullptr) {
+            const unsigned nib = ((unsigned)q.x >> 31) | (((unsigned)q.y >> 31) << 1) |
+                                 (((unsigned)q.z >> 31) << 2) | (((unsigned)q.w >> 31) << 3);
+            store_null_bits(bm, base + t * kTileRows, nib, lane);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_scan_hist(const __grid_constant__ ScanParams p) {
     extern __shared__ int32_t bins[];
     const int g = blockIdx.y;
@@ -80,27 +109,19 @@ __global__ void __launch_bounds__(kThreads) k_scan_hist(const __grid_constant__ 
         const bool vec_ok = ((uintptr_t)col & 15) == 0;
         int64_t chunk = blockIdx.x;
         if (vec_ok) {
-            // software pipeline: the next chunk's four 128-bit loads are in flight while this one is counted
-            int4 cur[kTilesPerChunk], nxt[kTilesPerChunk];
-            if (chunk < n_full) load_chunk(cur, col, chunk * kChunkRows, lane);
+            // software pipeline, ping-pong register buffers: the next chunk's four 128-bit loads are in
+            // flight while this one is counted
+            int4 bufA[kTilesPerChunk], bufB[kTilesPerChunk];
+            if (chunk < n_full) load_chunk(bufA, col, chunk * kChunkRows, lane);
             while (chunk < n_full) {
-                const int64_t next = chunk + gridDim.x;
-                if (next < n_full) load_chunk(nxt, col, next * kChunkRows, lane);
-#pragma unroll
-                for (int t = 0; t < kTilesPerChunk; ++t) {
-                    const int4 q = cur[t];
-                    count_one(b, dom, q.x);
-                    count_one(b, dom, q.y);
-                    count_one(b, dom, q.z);
-                    count_one(b, dom, q.w);
-                    if (bm != nullptr) {
-                        const unsigned nib = ((unsigned)q.x >> 31) | (((unsigned)q.y >> 31) << 1) |
-                                             (((unsigned)q.z >> 31) << 2) | (((unsigned)q.w >> 31) << 3);
-                        store_null_bits(bm, chunk * kChunkRows + t * kTileRows, nib, lane);
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < kTilesPerChunk; ++t) cur[t] = nxt[t];
+                int64_t next = chunk + gridDim.x;
+                if (next < n_full) load_chunk(bufB, col, next * kChunkRows, lane);
+                count_chunk(bufA, b, dom, bm, chunk * kChunkRows, lane);
+                chunk = next;
+                if (chunk >= n_full) break;
+                next = chunk + gridDim.x;
+                if (next < n_full) load_chunk(bufA, col, next * kChunkRows, lane);
+                count_chunk(bufB, b, dom, bm, chunk * kChunkRows, lane);
                 chunk = next;
             }
         }

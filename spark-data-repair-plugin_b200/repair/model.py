@@ -270,8 +270,6 @@ class RepairModel():
         validate_options(self.opts)
         for key in _MODEL_OPT:
             self._opt(key)
-        if compute_repair_candidate_prob or maximal_likelihood_repair:
-            raise NotImplementedError("pmf / score / maximal-likelihood modes are not built yet (SURVEY.md 8f)")
         if self.repair_by_rules:
             raise NotImplementedError("rule-based repairs are not built yet (SURVEY.md 8f)")
 
@@ -291,12 +289,54 @@ class RepairModel():
             if len(res.target_columns) == 0:
                 raise ValueError("At least one valid discretizable feature is needed to repair error cells, "
                                  "but no such feature found")
-            out = repair_cells(self, engine, table, res, continuous, repair_data)
+            if compute_repair_candidate_prob or maximal_likelihood_repair:
+                out = self._run_pmf_modes(engine, table, res, continuous, compute_repair_prob, compute_repair_score,
+                                          repair_data, maximal_likelihood_repair)
+            else:
+                out = repair_cells(self, engine, table, res, continuous, repair_data)
             _logger.info("!!!Total Processing time is {}(s)!!!".format(time.time() - t0))
             return out
         finally:
             self.last_run["gpu_launches"] = engine.ctx.launch_count
             engine.close()
+
+    # ---- pmf / score / maximal-likelihood modes (model.py:1350-1390) -------------------------------
+    def _run_pmf_modes(self, engine, table, res, continuous, compute_repair_prob, compute_repair_score,
+                       repair_data, maximal_likelihood_repair):
+        from . import pmf as P
+        cells = repair_cells_pmf(self, engine, table, res, continuous)
+        opts = {k: self._opt(k) for k in ("repair.pmf.cost_weight", "repair.pmf.prob_threshold",
+                                          "repair.pmf.prob_top_k")}
+        shaped = P.shape_pmf(cells, opts, self.cf)
+        rid = table.row_id
+        if not maximal_likelihood_repair:
+            if compute_repair_prob:
+                return DataFrame({rid: [c[0] for c in shaped], "attribute": [c[1] for c in shaped],
+                                  "current_value": pd.array([c[2][0] for c in shaped], dtype=object),
+                                  "repaired": pd.array([c[3][0][0] if c[3] else None for c in shaped], dtype=object),
+                                  "prob": [c[3][0][1] if c[3] else None for c in shaped]})
+            return DataFrame({rid: [c[0] for c in shaped], "attribute": [c[1] for c in shaped],
+                              "current_value": pd.array([c[2][0] for c in shaped], dtype=object),
+                              "pmf": [[{"class": k, "prob": p} for k, p in c[3]] for c in shaped]})
+        assert self.cf is not None
+        scored = P.compute_score(shaped, self.cf)
+        if compute_repair_score:
+            return DataFrame({rid: [c[0] for c in scored], "attribute": [c[1] for c in scored],
+                              "current_value": pd.array([c[2] for c in scored], dtype=object),
+                              "repaired": pd.array([c[3] for c in scored], dtype=object),
+                              "score": [c[4] for c in scored]})
+        top = P.maximal_likelihood_repair(scored, int(self.repair_delta))
+        if repair_data:
+            frame = self._input_frame(table)
+            pos_of = {v: i for i, v in enumerate(table.row_ids.tolist())}
+            for r, a, _, rep in top:
+                col = frame[a].to_numpy(dtype=object, copy=True)
+                col[pos_of[r]] = rep
+                frame[a] = col
+            return frame
+        return DataFrame({rid: [c[0] for c in top], "attribute": [c[1] for c in top],
+                          "current_value": pd.array([c[2] for c in top], dtype=object),
+                          "repaired": pd.array([c[3] for c in top], dtype=object)})
 
     # ---- frames ----------------------------------------------------------------------------------
     def _empty_frame(self, table, repaired=False):
@@ -417,6 +457,79 @@ def run_chain(engine, table, models, tile, ctile, D):
                 engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, int(m[1]))
             continue
         m[1].predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
+
+
+def repair_cells_pmf(rm, engine, table, res, continuous):
+    """pmf variant of the repair phase (model.py:1104-1128): discrete targets keep the class margins of
+    every predicted cell, and the cell itself becomes "neither NULL nor a known category" for the
+    later models (the reference parks a JSON string there).
+    -> [(row id, attribute, current_value, classes or None, probs or value string)]"""
+    from . import pmf as P
+    torch = engine.torch
+    targets = res.target_columns
+    K = len(table.columns)
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    cont_idx = engine.dt.cont_index
+    n_cc = len(cont_idx)
+    cells = engine.cells_of(res, targets)
+    if not cells:
+        return []
+    models = build_models(rm, engine, table, res, continuous)
+    rm.last_run["models"] = models
+    drows, tile, ctile = engine.build_dirty_tile(res, targets)
+    D = int(drows.numel())
+    words = (D + 31) // 32 + 1
+    nullbits = torch.zeros(words, dtype=torch.int32, device=engine.device)
+    all_null = torch.zeros((K, words), dtype=torch.int32, device=engine.device)
+    engine.ctx.tile_null_bitmaps(tile, D, K, words, all_null)
+    kept = {}
+    for y, m in models:
+        ycol = table.by_name[y]
+        if ycol.continuous:
+            engine.ctx.tile_null_bitmap(ctile, D, n_cc, cont_idx[y], nullbits, f64=True)
+            todo = engine.bitmap_rows(nullbits, D)
+            if int(todo.numel()) and m[0] == "forest":
+                m[1].predict(engine.ctx, tile, K, ctile, n_cc, todo, int(todo.numel()), cont_idx[y])
+            continue
+        todo = engine.bitmap_rows(all_null[tile_col[y]], D)
+        n = int(todo.numel())
+        if n == 0:
+            continue
+        if m[0] == "const":
+            kept[y] = (todo.cpu().numpy(), None, [m[1]])
+        else:
+            dm = m[1]
+            margins = torch.empty((n, dm.n_seq), dtype=torch.float64, device=engine.device)
+            dm.predict(engine.ctx, tile, K, ctile, n_cc, todo, n, tile_col[y], margins)
+            kept[y] = (todo.cpu().numpy(), margins.cpu().numpy(), m[2]["spec"]["class_codes"])
+        engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, ycol.dict_size)  # unknown category from here on
+    out = []
+    for a, rows, cur in cells:
+        col = table.by_name[a]
+        d_rows = torch.from_numpy(rows.astype(np.int32)).to(engine.device)
+        dpos = torch.empty(len(rows), dtype=torch.int32, device=engine.device)
+        engine.ctx.lookup_sorted(drows, D, d_rows, len(rows), dpos)
+        ids = table.row_ids[rows].tolist()
+        cur_s = col.decode(cur)
+        if col.continuous:
+            vals = torch.empty(len(rows), dtype=torch.float64, device=engine.device)
+            engine.ctx.tile_gather(ctile, n_cc, cont_idx[a], dpos, len(rows), vals, f64=True)
+            for i, v in enumerate(vals.cpu().numpy().tolist()):
+                out.append((ids[i], a, cur_s[i], None, cell_to_string(col.kind, v)))
+            continue
+        todo_h, margins_h, class_codes = kept[a]
+        at = np.searchsorted(todo_h, dpos.cpu().numpy())
+        if margins_h is None:
+            classes = [None if class_codes[0] is None else col.strings()[class_codes[0]]]
+            for i in range(len(rows)):
+                out.append((ids[i], a, cur_s[i], classes, [1.0]))
+        else:
+            probs = P.probabilities(margins_h[at])
+            strs = col.strings()
+            classes = [strs[c] for c in class_codes]
+            for i in range(len(rows)):
+                out.append((ids[i], a, cur_s[i], classes, probs[i].tolist()))
+    return out
 
 
 def repair_cells_encoded(rm, engine, table, res, models):

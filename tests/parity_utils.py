@@ -79,8 +79,21 @@ def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=Non
     if given is not None:
         rm.setErrorCells(given)
     for k, v in (opts or {}).items():
-        rm.option(k, str(v))
-    if mode == "detect":
+        if k.startswith("_"):
+            rm.opts[k] = v
+        else:
+            rm.option(k, str(v))
+    if mode in ("pmf", "prob", "score", "mlr"):
+        from repair.costs import Levenshtein
+        if mode in ("score", "mlr") or (opts or {}).get("_cost"):
+            rm.setUpdateCostFunction(Levenshtein())
+        if mode in ("score", "mlr"):
+            rm.setRepairDelta(int((opts or {}).get("_delta", 3)))
+        rm.opts.pop("_cost", None), rm.opts.pop("_delta", None)
+        kw = {"pmf": {"compute_repair_candidate_prob": True}, "prob": {"compute_repair_prob": True},
+              "score": {"compute_repair_score": True}, "mlr": {"maximal_likelihood_repair": True}}[mode]
+        out = rm.run(**kw)
+    elif mode == "detect":
         out = rm.run(detect_errors_only=True)
     elif mode == "repair_data":
         out = rm.run(repair_data=True)
@@ -155,3 +168,45 @@ def run_both_synth(n_rows, n_cols, seed=0, n_estimators=20, c4=True, mode="repai
     fmt = (lambda v: None if v is None else "v%03d" % int(v))
     want = sorted([tuple([w[0], w[1]] + [fmt(x) for x in w[2:]]) for w in want], key=lambda t: (t[0], t[1]))
     return got, want, {"gpu_launches": rm.last_run.get("gpu_launches", 0), "rm": rm}
+
+
+def run_both_pmf(df, row_id, specs, mode, targets=None, thres=80, opts=None):
+    """pmf / prob / score / maximal-likelihood modes: product frame vs the oracle's restatement fed
+    with the product's forests.  -> (got rows, want rows) as comparable tuples."""
+    from oracle import repair as OR
+    from oracle.table import from_pandas
+    from repair.table import EncodedTable
+    opts = dict(opts or {})
+    rm, out = run_product(df, row_id, specs, targets, thres, opts, mode=mode)
+    enc = EncodedTable.from_pandas(df, row_id)
+
+    def value_of(attr, code):
+        col = enc.by_name[attr]
+        v = col.dictionary[code]
+        return str(v) if col.kind == "str" else (int(v) if col.kind == "int" else float(v))
+
+    provider = provider_from_product(rm, enc, value_of)
+    o_opts = {k: v for k, v in opts.items() if k in OR.DEFAULT_OPTS}
+    cells = OR.run(from_pandas(df), row_id, specs, targets, thres, None, o_opts, provider, pmf_mode=True)
+    cost = OR.levenshtein if (mode in ("score", "mlr") or opts.get("_cost")) else None
+    pmf_opts = {k: v for k, v in opts.items() if k.startswith("repair.pmf.")}
+    shaped = OR.shape_pmf(cells, pmf_opts, cost)
+    if mode == "pmf":
+        want = [(s[0], s[1], s[2][0], tuple(s[3])) for s in shaped]
+        got = [(str(r[row_id]), r["attribute"], r["current_value"], tuple((d["class"], d["prob"]) for d in r["pmf"]))
+               for r in out.to_dict("records")]
+    elif mode == "prob":
+        want = [(s[0], s[1], s[2][0], s[3][0][0], s[3][0][1]) for s in shaped]
+        got = [(str(r[row_id]), r["attribute"], r["current_value"], r["repaired"], r["prob"])
+               for r in out.to_dict("records")]
+    else:
+        scored = OR.compute_score(shaped, OR.levenshtein)
+        if mode == "score":
+            want = [tuple(s) for s in scored]
+            got = [(str(r[row_id]), r["attribute"], r["current_value"], r["repaired"], r["score"])
+                   for r in out.to_dict("records")]
+        else:
+            want = [tuple(s) for s in OR.maximal_likelihood_repair(scored, int(opts.get("_delta", 3)))]
+            got = [(str(r[row_id]), r["attribute"], r["current_value"], r["repaired"]) for r in out.to_dict("records")]
+    key = lambda t: (t[0], t[1])  # noqa: E731
+    return sorted(got, key=key), sorted(want, key=key)

@@ -205,3 +205,36 @@ def test_encoded_output_with_frozen_models_matches_string_frame():
         for r, c, p in zip(rows.tolist(), col.decode(cur), col.decode(rep)):
             got.append((str(r), a, c, p))
     assert sorted(got, key=lambda t: (t[0], t[1])) == want
+
+
+@pytest.mark.parametrize("mode", ["pmf", "prob", "score", "mlr"])
+def test_adult_pmf_modes_parity(mode):
+    # model.py:1350-1390; schemas as asserted by tests/test_model.py:1008-1119
+    got, want = PU.run_both_pmf(adult(), "tid", [{"type": "null"}], mode, opts=dict(FAST))
+    assert len(got) == (7 if mode != "mlr" else len(want)) and len(want) > 0
+    assert got == want
+
+
+def test_pmf_with_cost_weighting_and_topk():
+    df = adult()
+    df.loc[df.tid == 4, "Sex"] = "Femal"      # a dirty, non-NULL cell so that costs apply
+    specs = [{"type": "null"}, {"type": "domain", "attr": "Sex", "values": ["Male", "Female"]}]
+    # the regex (Male|Female) finds "Female" inside "Femal"? no: "Femal" does not contain either
+    opts = dict(FAST)
+    opts.update({"_cost": 1, "repair.pmf.prob_top_k": 3, "repair.pmf.prob_threshold": 0.05})
+    got, want = PU.run_both_pmf(df, "tid", specs, "pmf", opts=opts)
+    assert got == want
+    assert any(g[2] == "Femal" for g in got)
+
+
+def test_pmf_mixed_types_schema():
+    # tests/test_model.py:1060-1082 shape: continuous targets get a single certain candidate
+    rows = [(1, 0, 1.0, 1.0, "a"), (2, 1, 1.5, 1.5, "b"), (3, 0, 1.4, None, "b"), (4, 1, 1.3, 1.3, "b"),
+            (5, 1, 1.2, 1.1, "b"), (6, 1, 1.1, 1.2, "b"), (7, 0, None, 1.4, "b"), (8, 1, 1.4, 1.0, "b"),
+            (9, 0, 1.2, 1.1, "b"), (10, None, 1.3, 1.2, "b"), (11, 0, 1.0, 1.9, "b"), (12, 0, 1.9, 1.2, "b"),
+            (13, 0, 1.2, 1.3, "b"), (14, 0, 1.8, 1.2, None), (15, 0, 1.3, 1.1, "b"), (16, 1, 1.3, 1.0, "b"),
+            (17, 0, 1.3, 1.0, "b")]
+    df = pd.DataFrame(rows, columns=["tid", "v1", "v2", "v3", "v4"])
+    got, want = PU.run_both_pmf(df, "tid", [{"type": "null"}], "pmf", opts=dict(FAST))
+    assert got == want
+    assert sorted((g[0], g[1]) for g in got) == [("10", "v1"), ("14", "v4"), ("3", "v3"), ("7", "v2")]
