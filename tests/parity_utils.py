@@ -209,4 +209,5 @@ def run_both_pmf(df, row_id, specs, mode, targets=None, thres=80, opts=None):
             want = [tuple(s) for s in OR.maximal_likelihood_repair(scored, int(opts.get("_delta", 3)))]
             got = [(str(r[row_id]), r["attribute"], r["current_value"], r["repaired"]) for r in out.to_dict("records")]
     key = lambda t: (t[0], t[1])  # noqa: E731
+    got = [tuple(None if (isinstance(x, float) and x != x) else x for x in g) for g in got]
     return sorted(got, key=key), sorted(want, key=key)
