@@ -296,6 +296,35 @@ typedef struct dr_forest_ranked {
 int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* forest, int32_t* tile, int n_cols,
                              const int32_t* cells, int64_t n_cells, int target_col, double* out_margin,
                              void* stream);
+/* ---- a12 ("next" #1): repair-model training ------------------------------------------------------
+ * Replaces train.build_model (train.py:89-234: LightGBM under a hyperopt search) with a histogram
+ * GBDT trained on the GPU with the reference's fixed parameters (train.py:102-115; LightGBM defaults
+ * for the rest).  The algorithm is specified in oracle/gbdt.py and reproduced bit for bit: integer
+ * (quantised-gradient) histograms, explicit round-to-nearest arithmetic, level-wise growth under a
+ * num_leaves budget, all class sequences of a boosting round grown together, no host
+ * synchronisation inside the boosting loop.
+ *   bins      device uint8[n_rows][n_features]: value bins 0..n_bins[f]-2, missing = n_bins[f]-1
+ *   n_bins    host int32[n_features]  (sum of bins * 20 bytes must fit in shared memory)
+ *   y_class   device int32[n_rows] (n_classes >= 2) / y_value device double[n_rows] (n_classes == 1)
+ *   weight    device double[n_rows] (class weights; classification only)
+ *   init      host double[S] initial scores, S = 1 for regression / binary, n_classes otherwise
+ *   workspace device scratch of dr_gbdt_workspace_bytes(n_rows, S) bytes
+ *   out_nodes device dr_gbdt_node[n_iter][S][64], out_counts device int32[n_iter][S] (nodes used) */
+typedef struct dr_gbdt_params {
+    int32_t n_rows, n_features, n_classes, n_iter, max_depth, num_leaves, min_data_in_leaf;
+    double learning_rate, min_sum_hessian, qscale;
+} dr_gbdt_params;
+typedef struct dr_gbdt_node {
+    int16_t feature; /* -1 = leaf */
+    uint8_t thr_bin, missing_left, left, right, pad[2];
+    double value; /* leaf value (already scaled by the learning rate) */
+} dr_gbdt_node;
+int64_t dr_gbdt_workspace_bytes(int32_t n_rows, int32_t n_seq);
+int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* params, const uint8_t* bins, const int32_t* n_bins,
+                  const int32_t* y_class, const double* y_value, const double* weight, const double* init,
+                  void* workspace, int64_t workspace_bytes, dr_gbdt_node* out_nodes, int32_t* out_counts,
+                  void* stream);
+
 /* PoorModel (model.py:44-61): constant fill of the listed tile rows. */
 int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int32_t* cells, int64_t n_cells,
                      int32_t value, void* stream);

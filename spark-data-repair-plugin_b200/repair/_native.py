@@ -39,6 +39,12 @@ class dr_forest_ranked(ctypes.Structure):
     ]
 
 
+class dr_gbdt_params(ctypes.Structure):
+    _fields_ = [("n_rows", c_int32), ("n_features", c_int32), ("n_classes", c_int32), ("n_iter", c_int32),
+                ("max_depth", c_int32), ("num_leaves", c_int32), ("min_data_in_leaf", c_int32),
+                ("learning_rate", c_double), ("min_sum_hessian", c_double), ("qscale", c_double)]
+
+
 _PP = POINTER(c_void_p)
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -87,6 +93,9 @@ _SIGNATURES = {
                                   c_int, c_void_p, c_void_p]),
     "dr_forest_predict_ranked": (c_int, [c_void_p, POINTER(dr_forest_ranked), c_void_p, c_int, c_void_p, c_int64,
                                          c_int, c_void_p, c_void_p]),
+    "dr_gbdt_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "dr_gbdt_train": (c_int, [c_void_p, POINTER(dr_gbdt_params), c_void_p, POINTER(c_int32), c_void_p, c_void_p,
+                              c_void_p, POINTER(c_double), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dr_tile_fill_i32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int32, c_void_p]),
 }
 
@@ -299,6 +308,15 @@ class Context:
         self._check(self.lib.dr_forest_predict_ranked(self._h, byref(forest_struct), _dp(tile), n_cols, _dp(cells),
                                                       n_cells, target_col, _dp(out_margin), self._stream()))
 
+    def gbdt_train(self, params, bins, n_bins, y_class, y_value, weight, init, workspace, out_nodes, out_counts):
+        self._check(self.lib.dr_gbdt_train(
+            self._h, byref(params), _dp(bins), _i32_array(n_bins), _dp(y_class), _dp(y_value), _dp(weight),
+            (c_double * len(init))(*[float(v) for v in init]), _dp(workspace), workspace.numel(), _dp(out_nodes),
+            _dp(out_counts), self._stream()))
+
+    def gbdt_workspace_bytes(self, n_rows, n_seq):
+        return int(self.lib.dr_gbdt_workspace_bytes(n_rows, n_seq))
+
     def tile_fill(self, tile, n_cols, col, cells, n_cells, value):
         self._check(self.lib.dr_tile_fill_i32(self._h, _dp(tile), n_cols, col, _dp(cells), n_cells, value,
                                               self._stream()))
@@ -323,7 +341,7 @@ def _profiled(name, fn):
 for _name in ("widen_u8", "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
-              "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill"):
+              "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill", "gbdt_train"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))
 
 

@@ -1,0 +1,116 @@
+"""GPU histogram-GBDT trainer (host side of ``dr_gbdt_train``): pre-bins the encoded training
+sample, computes class weights / initial scores, runs the whole boosting loop on the device and
+flattens the result into the exchange format of ``forest.py``.
+
+Eligibility: every feature discrete (label-encoded attribute behind a sum / ordinal encoder), at most
+128 encoded features and 255 distinct values per feature.  Other models (continuous features) use
+``train.build_model`` (scikit-learn)."""
+import numpy as np
+
+from .forest import encoder_lut
+
+NODE_DTYPE = np.dtype([("feature", np.int16), ("thr_bin", np.uint8), ("missing_left", np.uint8), ("left", np.uint8),
+                       ("right", np.uint8), ("pad", np.uint8, (2,)), ("value", np.float64)])
+MAX_NODES = 64
+QBITS = 24
+
+
+def bin_sample(encoders, sample_codes, dict_sizes):
+    """-> (bins uint8 [n, F'], n_bins int32 [F'], bin_values list of float arrays) or None."""
+    cols, n_bins, values = [], [], []
+    for e in encoders:
+        if e["type"] == "cont":
+            return None
+        lut = encoder_lut(e, dict_sizes[e["attr"]])
+        codes = np.asarray(sample_codes[e["attr"]], dtype=np.int64)
+        for j in range(lut.shape[1]):
+            col = lut[:, j]
+            vals = np.unique(col[~np.isnan(col)])
+            if len(vals) > 254:
+                return None
+            bin_of = np.full(len(col), len(vals), dtype=np.uint8)           # missing bin
+            ok = ~np.isnan(col)
+            bin_of[ok] = np.searchsorted(vals, col[ok]).astype(np.uint8)
+            cols.append(bin_of[codes + 1])
+            n_bins.append(len(vals) + 1)
+            values.append(vals)
+    if not cols or len(cols) > 128:
+        return None
+    return np.stack(cols, axis=1).astype(np.uint8), np.asarray(n_bins, dtype=np.int32), values
+
+
+def class_weights(y_idx, n_classes, balanced):
+    """class_weight='balanced' (train.py:105): n / (C * count[class])."""
+    n = len(y_idx)
+    if not balanced:
+        return np.ones(n)
+    cnt = np.bincount(y_idx, minlength=n_classes).astype(np.float64)
+    return (float(n) / (float(n_classes) * cnt))[y_idx]
+
+
+def initial_scores(y, n_classes, weight):
+    if n_classes == 1:
+        yv = np.asarray(y, dtype=np.float64)
+        return np.array([np.cumsum(yv)[-1] / len(yv)])
+    if n_classes == 2:
+        yv = np.asarray(y, dtype=np.float64)
+        sw, swy = np.cumsum(weight)[-1], np.cumsum(weight * yv)[-1]
+        pavg = min(max(swy / sw, 1e-15), 1.0 - 1e-15)
+        return np.array([np.log(pavg / (1.0 - pavg))])
+    return np.zeros(n_classes)
+
+
+def train_gpu(ctx, device, bins, n_bins, bin_values, y, n_classes, weight, n_iter, learning_rate, max_depth,
+              num_leaves=31, min_data_in_leaf=20, min_sum_hessian=1e-3):
+    """-> flat forest (forest.py layout)."""
+    import torch
+    from ._native import dr_gbdt_params
+    n, F = bins.shape
+    S = 1 if n_classes <= 2 else n_classes
+    init = initial_scores(y, n_classes, weight)
+    if n_classes == 1:
+        yv = np.asarray(y, dtype=np.float64)
+        qscale = float(2 ** QBITS) / max(float(np.abs(yv - init[0]).max()), 1e-300)
+    else:
+        qscale = float(2 ** QBITS) / float(np.max(weight))
+    prm = dr_gbdt_params(n, F, n_classes, n_iter, max_depth, num_leaves, min_data_in_leaf, learning_rate,
+                         min_sum_hessian, qscale)
+    d_bins = torch.from_numpy(np.ascontiguousarray(bins)).to(device)
+    d_yc = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32)).to(device) if n_classes >= 2 else None
+    d_yv = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(device) if n_classes == 1 else None
+    d_w = torch.from_numpy(np.ascontiguousarray(weight, dtype=np.float64)).to(device)
+    ws = torch.empty(ctx.gbdt_workspace_bytes(n, S), dtype=torch.uint8, device=device)
+    out_nodes = torch.zeros(n_iter * S * MAX_NODES * NODE_DTYPE.itemsize, dtype=torch.uint8, device=device)
+    out_counts = torch.zeros(n_iter * S, dtype=torch.int32, device=device)
+    ctx.gbdt_train(prm, d_bins, n_bins, d_yc, d_yv, d_w, init, ws, out_nodes, out_counts)
+    nodes = out_nodes.cpu().numpy().view(NODE_DTYPE).reshape(n_iter, S, MAX_NODES)
+    counts = out_counts.cpu().numpy().reshape(n_iter, S)
+    return flatten(nodes, counts, init, bin_values, F, n_classes)
+
+
+def flatten(nodes, counts, init, bin_values, n_features, n_classes):
+    """device node records -> flat forest; threshold = midpoint between the split bin's value and the
+    next one in the feature's encoded value space."""
+    n_iter, S, _ = nodes.shape
+    sizes = counts.reshape(-1).astype(np.int64)
+    tree_offset = np.zeros(len(sizes) + 1, dtype=np.int64)
+    tree_offset[1:] = np.cumsum(sizes)
+    keep = (np.arange(MAX_NODES)[None, :] < sizes[:, None]).reshape(-1)
+    flat = nodes.reshape(-1)[keep]
+    feat = flat["feature"].astype(np.int32)
+    leaf = feat < 0
+    thr = np.zeros(len(flat))
+    max_bins = max(len(v) for v in bin_values)
+    tab = np.zeros((n_features, max_bins + 1))
+    for f, v in enumerate(bin_values):
+        tab[f, :len(v)] = v
+    fi, ti = np.where(leaf, 0, feat), flat["thr_bin"].astype(np.int64)
+    thr = np.where(leaf, 0.0, (tab[fi, ti] + tab[fi, np.minimum(ti + 1, max_bins)]) / 2.0)
+    return {
+        "n_features": int(n_features), "n_classes": int(n_classes), "baseline": np.asarray(init, dtype=np.float64),
+        "tree_seq": np.tile(np.arange(S, dtype=np.int32), n_iter), "tree_offset": tree_offset,
+        "feature": feat, "threshold": thr, "missing_left": np.where(leaf, 0, flat["missing_left"]).astype(np.uint8),
+        "left": np.where(leaf, 0, flat["left"]).astype(np.int32),
+        "right": np.where(leaf, 0, flat["right"]).astype(np.int32),
+        "value": np.where(leaf, flat["value"], 0.0).astype(np.float64),
+    }

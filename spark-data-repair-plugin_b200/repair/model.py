@@ -89,7 +89,8 @@ class RepairModel():
         self.opts: Dict[str, str] = {}
         # engine knobs (not part of the reference API)
         self.device_index: int = 0
-        self.model_provider = None   # callable(ctx) -> model spec; default trains with train.build_model
+        self.model_provider = None   # callable(ctx) -> model spec; default: _fit (GPU GBDT / scikit-learn)
+        self.trainer = "gpu"         # "gpu": dr_gbdt_train when eligible; "sklearn": always train.build_model
         self.last_run: Dict[str, Any] = {}
 
     # ---- setters (same names / checks / messages as the reference) -------------------------------
@@ -365,6 +366,28 @@ class RepairModel():
                           "current_value": pd.array(curs, dtype=object)})
 
 
+def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class):
+    """Model producer: the GPU histogram GBDT (gbdt.py) when every feature is discrete, else
+    scikit-learn's (train.py).  Both use the reference's fixed parameters (train.py:102-115)."""
+    from . import gbdt as G
+    from .train import _get
+    binned = None
+    if rm.trainer != "sklearn" and is_discrete:
+        binned = G.bin_sample(encoders, {f: codes[:, tile_col[f]] for f in features}, dict_sizes)
+    if binned is not None and int(binned[1].sum()) * 20 <= 200 * 1024:
+        bins, n_bins, values = binned
+        classes = sorted(set(int(v) for v in y_values.tolist()))
+        y_idx = np.searchsorted(np.asarray(classes), y_values).astype(np.int64)
+        w = G.class_weights(y_idx, len(classes), _get(rm.opts, "model.lgb.class_weight") == "balanced")
+        depth = _get(rm.opts, "model.lgb.max_depth")
+        forest = G.train_gpu(engine.ctx, engine.device, bins, n_bins, values, y_idx, len(classes), w,
+                             _get(rm.opts, "model.lgb.n_estimators"), _get(rm.opts, "model.lgb.learning_rate"),
+                             depth if depth > 0 else 31)
+        return {"forest": forest, "class_codes": classes}
+    forest, classes = build_model(X, y_values, is_discrete, num_class, rm.opts)
+    return None if forest is None else {"forest": forest, "class_codes": classes}
+
+
 def _train_model(rm, engine, table, res, y, continuous, tile_col):
     """Bookkeeping of _build_repair_models for one target (model.py:1001-1052, 768-815).
     -> ("const", code or None) | ("forest", DeviceModel, info)"""
@@ -410,8 +433,7 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col):
     if rm.model_provider is not None:
         spec = rm.model_provider(ctx)
     else:
-        forest, classes = build_model(X, y_values, is_discrete, num_class, rm.opts)
-        spec = None if forest is None else {"forest": forest, "class_codes": classes}
+        spec = _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class)
     if spec is None:
         return ("const", None)
     if "const" in spec:

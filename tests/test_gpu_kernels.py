@@ -486,3 +486,33 @@ def test_widen_u8(ctx, n):
     want = np.full(n_pad, -1, dtype=np.int32)
     want[:n] = codes
     assert np.array_equal(dst.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n_classes,n,n_iter", [(3, 1500, 12), (2, 900, 15), (1, 1200, 10), (17, 2500, 6)])
+def test_gbdt_trainer_matches_oracle_bit_for_bit(ctx, n_classes, n, n_iter):
+    """dr_gbdt_train == oracle/gbdt.py: identical tree structures, thresholds and float64 leaf values."""
+    from oracle import gbdt as OG
+    from repair import gbdt as PG
+    rng = np.random.default_rng(n_classes * 31 + n)
+    doms = [4, 9, 3, 6, 30, 2, 12]
+    vals = [np.sort(rng.choice(np.arange(-3, 40), size=d, replace=False)).astype(np.float64) for d in doms]
+    n_bins = np.array([d + 1 for d in doms], dtype=np.int32)
+    bins = np.stack([rng.integers(0, d + 1, size=n) for d in doms], axis=1).astype(np.uint8)
+    sig = (bins[:, 0].astype(int) * 3 + bins[:, 4] + (bins[:, 1] > 4) * 5)
+    if n_classes == 1:
+        y = sig * 0.37 + rng.normal(size=n)
+        w = np.ones(n)
+    else:
+        y = ((sig + rng.integers(0, 2, size=n)) % n_classes).astype(np.int64)
+        w = PG.class_weights(y, n_classes, balanced=True)
+    lr, depth = 0.1, 5
+    want = OG.to_flat_forest(OG.train(bins, n_bins, y, n_classes, w if n_classes > 1 else None, n_iter, lr, depth,
+                                      num_leaves=15, min_data_in_leaf=10), vals, len(doms))
+    got = PG.train_gpu(ctx, torch.device("cuda", 0), bins, n_bins, vals, y, n_classes, w, n_iter, lr, depth,
+                       num_leaves=15, min_data_in_leaf=10)
+    for k in ("tree_seq", "tree_offset", "feature", "missing_left", "left", "right"):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+    assert np.array_equal(got["threshold"], want["threshold"])
+    assert np.array_equal(got["value"], want["value"])          # bit-exact float64 leaves
+    assert np.array_equal(got["baseline"], want["baseline"])
+    assert (np.asarray(want["feature"]) >= 0).sum() > n_iter    # the trees actually split
