@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--cols", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-rows", type=int, default=10000, help="rows of the CPU baseline sample")
+    ap.add_argument("--forests", default="trained", choices=["trained", "random"],
+                    help="trained: dr_gbdt_train on the real 10k-row samples (default); random: random-init "
+                         "forests of the same architecture")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-calls", action="store_true", help="print the per-call timing table to stderr")
@@ -245,13 +248,16 @@ def b200_arm(args):
     engine = Engine(table, local, dist=dist, device_table=dt)
     rm = RepairModel()
     rm.opts = dict(OPTS)
-    rm.model_provider = random_forest_provider(N_ESTIMATORS)
+    if args.forests == "random":
+        rm.model_provider = random_forest_provider(N_ESTIMATORS)
     err_opts = ErrorModelOptions.resolve(rm.opts)
     specs = detector_specs(k)
     continuous = []
 
     # frozen models: bookkeeping + encoders from a real training sample, random-init trees
     res = engine.detect(specs, [], 80, err_opts)
+    torch.cuda.synchronize()
+    t_train = time.time()
     if dist is None:
         models = build_models(rm, engine, table, res, continuous)
     else:
@@ -269,6 +275,8 @@ def b200_arm(args):
         for y, kind, body in payload[0]:
             models.append((y, ("const", body) if kind == "const" else
                            ("forest", DeviceModel(body, tile_col, dict_sizes, {}, device), {"spec": body})))
+    torch.cuda.synchronize()
+    t_train = time.time() - t_train
     n_trees = sum(m[1].n_trees for _, m in models if m[0] == "forest")
 
     stats = {}
@@ -327,14 +335,18 @@ def b200_arm(args):
         "dtype": "int32 codes / f64 margins", "data": "synthetic",
         "config": {"workload": "C4 synthetic {} rows x {} cols per GPU ({} rows total), 1% NULLs + 4 FD denial "
                                "constraints, NULL + Constraint detectors, pairwise_freq_ratio_threshold=1.0, "
-                               "{} frozen repair models ({} trees: 300 rounds x classes, random-init), "
-                               "inputs > L2 (no flush needed)".format(n, k, total_rows, len(models), n_trees),
+                               "{} frozen repair models ({} trees: 300 rounds x classes, {}), "
+                               "inputs > L2 (no flush needed)".format(
+                                   n, k, total_rows, len(models), n_trees,
+                                   "trained by dr_gbdt_train on 10k-row samples" if args.forests == "trained"
+                                   else "random-init"),
                    "rows_per_gpu": n, "cols": k, "parallelism": "rows sharded x{}".format(world)},
         "rows_scanned_per_sec": total_rows / (ms_det / 1e3),
         "cells_repaired_per_sec": int(cells[0]) / max((ms - ms_det) / 1e3, 1e-9),
         "error_cells": int(cells[0]), "repaired_cells_emitted": int(cells[1]),
         "ms_detect_phase": ms_det, "ms_repair_phase": ms - ms_det,
         "gpu_launches": launches, "clocks": clocks,
+        "model_training_s": t_train, "forests": args.forests,
     }
 
     # ---- per-kernel timing (CUDA events on the launching stream) and rooflines ------------------
