@@ -304,7 +304,9 @@ int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* forest, int32_
  * num_leaves budget, all class sequences of a boosting round grown together, no host
  * synchronisation inside the boosting loop.
  *   bins      device uint8[n_rows][n_features]: value bins 0..n_bins[f]-2, missing = n_bins[f]-1
- *   n_bins    host int32[n_features]  (sum of bins * 20 bytes must fit in shared memory)
+ *   n_bins    host int32[n_features]  (sum of bins * 12 bytes must fit in shared memory)
+ *   qscale    gradient quantisation scale; the caller chooses it so that n_rows * max|g| * qscale < 2^31
+ *             (oracle/gbdt.py: 2^min(24, 30 - ceil(log2 n)) / max weight)
  *   y_class   device int32[n_rows] (n_classes >= 2) / y_value device double[n_rows] (n_classes == 1)
  *   weight    device double[n_rows] (class weights; classification only)
  *   init      host double[S] initial scores, S = 1 for regression / binary, n_classes otherwise

@@ -26,7 +26,12 @@ LN2_HI = 6.93147180369123816490e-01
 LN2_LO = 1.90821492927058770002e-10
 INV_LN2 = 1.44269504088896338700e+00
 _COEF = [1.0 / float(np.prod(np.arange(1, k + 1, dtype=np.float64))) if k else 1.0 for k in range(14)]
-QBITS = 24
+
+
+def quant_bits(n_rows):
+    """Quantisation width: every histogram bin (a sum over <= n_rows rows) must fit a signed 32-bit
+    integer, so that the device can use native 32-bit shared-memory atomics."""
+    return int(min(24, 30 - int(np.ceil(np.log2(max(n_rows, 2))))))
 
 
 def exp_det(x):
@@ -64,12 +69,12 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
     n, F = bins.shape
     S = 1 if n_classes <= 2 else n_classes
     w = np.ones(n) if sample_weight is None else np.asarray(sample_weight, dtype=np.float64)
-    qscale = float(2 ** QBITS) / float(w.max())
+    qscale = float(2 ** quant_bits(n)) / float(w.max())
     scores = np.zeros((n, S))
     if n_classes == 1:
         yv = np.asarray(y, dtype=np.float64)
         init = np.array([np.cumsum(yv)[-1] / n])  # sequential sum
-        qscale = float(2 ** QBITS) / max(float(np.abs(yv - init[0]).max()), 1e-300)
+        qscale = float(2 ** quant_bits(n)) / max(float(np.abs(yv - init[0]).max()), 1e-300)
     elif n_classes == 2:
         yv = np.asarray(y, dtype=np.float64)
         sw, swy = np.cumsum(w)[-1], np.cumsum(w * yv)[-1]  # sequential sums

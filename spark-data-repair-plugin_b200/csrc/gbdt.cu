@@ -160,9 +160,11 @@ __global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
     const int cnt = st.sumC[s * kMaxNodes + leaf];
     if (cnt < 2 * st.min_data || H <= 0) return;
     const int total = st.bin_off[st.F];
-    long long* hg = reinterpret_cast<long long*>(smem_raw);
-    long long* hh = hg + total;
-    int* hc = reinterpret_cast<int*>(hh + total);
+    // the host picks the quantisation so that every bin sum fits 32 bits: native shared-memory
+    // atomics (64-bit ones degrade to compare-and-swap loops under the contention of few-valued features)
+    int* hg = reinterpret_cast<int*>(smem_raw);
+    int* hh = hg + total;
+    int* hc = hh + total;
     for (int b = threadIdx.x; b < total; b += kThreads) { hg[b] = 0; hh[b] = 0; hc[b] = 0; }
     __syncthreads();
     const uint8_t* nof = st.node_of + (size_t)s * st.n;
@@ -170,12 +172,12 @@ __global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
     const int32_t* hq = st.hq + (size_t)s * st.n;
     for (int i = threadIdx.x; i < st.n; i += kThreads) {
         if (nof[i] != leaf) continue;
-        const long long g = gq[i], h = hq[i];
+        const int g = gq[i], h = hq[i];
         const uint8_t* row = st.bins + (size_t)i * st.F;
         for (int f = 0; f < st.F; ++f) {
             const int b = st.bin_off[f] + row[f];
-            atomicAdd(reinterpret_cast<unsigned long long*>(hg + b), (unsigned long long)g);
-            atomicAdd(reinterpret_cast<unsigned long long*>(hh + b), (unsigned long long)h);
+            atomicAdd(hg + b, g);
+            atomicAdd(hh + b, h);
             atomicAdd(hc + b, 1);
         }
     }
@@ -361,6 +363,7 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* prm, const uint8_t* bins, c
     DR_REQUIRE(ctx, prm->n_classes == 1 ? y_value != nullptr : (y_class != nullptr && weight != nullptr),
                "missing targets / weights");
     DR_REQUIRE(ctx, workspace_bytes >= dr_gbdt_workspace_bytes(n, S), "workspace too small");
+    DR_REQUIRE(ctx, prm->qscale > 0.0, "qscale must be positive");
     GbdtState st;
     memset(&st, 0, sizeof(st));
     st.bins = bins; st.y_class = y_class; st.y_value = y_value; st.weight = weight;
@@ -376,7 +379,7 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* prm, const uint8_t* bins, c
         total += n_bins[f];
     }
     st.bin_off[F] = total;
-    const size_t smem = (size_t)total * (8 + 8 + 4);
+    const size_t smem = (size_t)total * 12;
     if (smem > 200 * 1024)
         return dr_fail(ctx, DR_ERR_UNSUPPORTED, "%d histogram bins do not fit in shared memory", total);
     unsigned char* w = (unsigned char*)workspace;

@@ -12,7 +12,12 @@ from .forest import encoder_lut
 NODE_DTYPE = np.dtype([("feature", np.int16), ("thr_bin", np.uint8), ("missing_left", np.uint8), ("left", np.uint8),
                        ("right", np.uint8), ("pad", np.uint8, (2,)), ("value", np.float64)])
 MAX_NODES = 64
-QBITS = 24
+
+
+def quant_bits(n_rows):
+    """Quantisation width: every histogram bin (a sum over <= n_rows rows) must fit a signed 32-bit
+    integer, so that the device can use native 32-bit shared-memory atomics."""
+    return int(min(24, 30 - int(np.ceil(np.log2(max(n_rows, 2))))))
 
 
 def bin_sample(encoders, sample_codes, dict_sizes):
@@ -70,9 +75,9 @@ def train_gpu(ctx, device, bins, n_bins, bin_values, y, n_classes, weight, n_ite
     init = initial_scores(y, n_classes, weight)
     if n_classes == 1:
         yv = np.asarray(y, dtype=np.float64)
-        qscale = float(2 ** QBITS) / max(float(np.abs(yv - init[0]).max()), 1e-300)
+        qscale = float(2 ** quant_bits(n)) / max(float(np.abs(yv - init[0]).max()), 1e-300)
     else:
-        qscale = float(2 ** QBITS) / float(np.max(weight))
+        qscale = float(2 ** quant_bits(n)) / float(np.max(weight))
     prm = dr_gbdt_params(n, F, n_classes, n_iter, max_depth, num_leaves, min_data_in_leaf, learning_rate,
                          min_sum_hessian, qscale)
     d_bins = torch.from_numpy(np.ascontiguousarray(bins)).to(device)

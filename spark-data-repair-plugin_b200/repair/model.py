@@ -374,7 +374,7 @@ def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_value
     binned = None
     if rm.trainer != "sklearn" and is_discrete:
         binned = G.bin_sample(encoders, {f: codes[:, tile_col[f]] for f in features}, dict_sizes)
-    if binned is not None and int(binned[1].sum()) * 20 <= 200 * 1024:
+    if binned is not None and int(binned[1].sum()) * 12 <= 200 * 1024:
         bins, n_bins, values = binned
         classes = sorted(set(int(v) for v in y_values.tolist()))
         y_idx = np.searchsorted(np.asarray(classes), y_values).astype(np.int64)
