@@ -76,6 +76,15 @@ class Engine:
     def n_rows_global(self):
         return self.table.n_rows_global
 
+    def pinned_i32(self, n):
+        """Page-locked int32 staging of at least n elements, kept for the life of the engine
+        (cudaHostAlloc of a few hundred MB per run would cost more than the copy it serves)."""
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < n:
+            buf = self.torch.empty(int(n * 1.25) + 1024, dtype=self.torch.int32, pin_memory=True)
+            self._pinned = buf
+        return buf[:n]
+
     def new_bitmap(self):
         return self.torch.zeros(self.n_words, dtype=self.torch.int32, device=self.device)
 

@@ -590,7 +590,7 @@ def repair_cells_encoded(rm, engine, table, res, models):
     engine.ctx.changed_bitmap(cur_all, rep_all, E, keep)
     idx = engine.bitmap_rows(keep, E)
     n_keep = int(idx.numel())
-    host = torch.empty((4, max(n_keep, 1)), dtype=torch.int32, pin_memory=True)
+    host = engine.pinned_i32(4 * max(n_keep, 1)).view(4, max(n_keep, 1))  # reused across runs
     packed = torch.empty((4, max(n_keep, 1)), dtype=torch.int32, device=engine.device)
     if n_keep:
         packed[0, :n_keep].copy_(idx)
@@ -603,7 +603,7 @@ def repair_cells_encoded(rm, engine, table, res, models):
     out = []
     bounds = np.searchsorted(h[0, :n_keep], [o for _, o, _ in seg] + [E])
     for (a, _, _), lo, hi in zip(seg, bounds[:-1], bounds[1:]):
-        out.append((a, h[1, lo:hi], h[2, lo:hi], h[3, lo:hi]))
+        out.append((a, h[1, lo:hi], h[2, lo:hi], h[3, lo:hi]))  # views of the engine's pinned staging buffer
     return out
 
 
