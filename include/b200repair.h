@@ -257,33 +257,39 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  * node is ONE 32-bit word and a cell's feature vector is one byte per feature, which is what lets
  * 16+ warps per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins
  * remain bit-identical to dr_forest_predict / the oracle.
- *   node word (all fields byte aligned): byte 3 = 2 * feature + (NaN goes left), byte 2 = thr_rank + 1,
- *              byte 1 = left child, byte 0 = right child, both as BYTE offsets from the tree root
- *              (4 * node index; trees have at most 64 nodes; at most 127 features).
- *              A LEAF points at itself (left = right = own offset) with byte 3 = 0 and its leaf index
- *              (within the tree) in byte 2, so the walk is branch-free.
+ *   node word: bits 24-31 = 2 * feature + (NaN goes left), bits 8-23 = index of the LEFT child in
+ *              the chunk's node array (the right child is the next word: trees are stored breadth
+ *              first with siblings adjacent), bits 0-7 = 256 - (thr_rank + 1).  Adding the row's
+ *              rank byte to the word carries into the child field exactly when rank >= thr_rank + 1,
+ *              i.e. when the row goes right: a level is load rank, add, load word[bits 8-23].
+ *              A LEAF has bits 0-7 = 0 (never carries), its own index in bits 8-23 (the walk stays
+ *              put, so every tree is walked max_depth levels without a branch) and its leaf number
+ *              within the tree in bits 24-31 (at most 256 leaves per tree, at most 127 features).
  *   rank_lut:  uint8, rank + 1 (1..254) of feature f of a row = rank_lut[rank_lut_off[f] +
- *              tile[row][feat_col[f]] + 1], 255 = NaN; the kernel compares it with thr_rank + 1, NaN
- *              mapped to 0 / 255 according to the node's NaN direction.
- *   max_depth: deepest leaf of any tree (the kernel walks a fixed number of levels).
- *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered),
- *   so every tree's node words are padded to a multiple of 4 and its leaf values to a multiple of 2
- *   (16-byte granules), and the host supplies the chunk table: chunk c = trees
- *   [chunk_tree_off[c], chunk_tree_off[c+1]) of sequence chunk_seq[c], at most DR_RANKED_CHUNK_NODES
- *   node words and DR_RANKED_CHUNK_LEAVES leaf values, never straddling a sequence; every sequence
- *   has at least one tree and a chunk at most 256 trees.  tree_hdr[chunk_hdr_off[c] + j] = (first node word of the chunk's j-th
- *   tree << 16) | its first leaf, both relative to the chunk (chunk_hdr_off is a multiple of 4). */
+ *              tile[row][feat_col[f]] + 1], 255 = NaN; NaN is stored as 255 in the "goes right" copy
+ *              of the feature byte and as 0 in the "goes left" copy.
+ *   max_depth: deepest leaf of any tree.
+ *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered).
+ *   The host supplies the chunk table: chunk c = trees [chunk_tree_off[c], chunk_tree_off[c+1]) of
+ *   sequence chunk_seq[c] (never straddling a sequence; every sequence has at least one tree), at
+ *   most DR_RANKED_CHUNK_TREES trees, DR_RANKED_CHUNK_NODES node words and DR_RANKED_CHUNK_LEAVES leaf
+ *   values; its words are node_word[chunk_node_off[c] .. chunk_node_off[c+1]), its leaf values
+ *   leaf_value[chunk_leaf_off[c] ..), its tree headers tree_hdr[2 * chunk_hdr_off[c] ..): two words
+ *   per tree = (root node word, first leaf value of the tree relative to the chunk).  chunk_node_off
+ *   is a multiple of 4, chunk_leaf_off and chunk_hdr_off multiples of 2 (16-byte TMA granules). */
 #define DR_RANKED_CHUNK_NODES 4096
 #define DR_RANKED_CHUNK_LEAVES 2176
+#define DR_RANKED_CHUNK_TREES 256
 typedef struct dr_forest_ranked {
     int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth, n_chunks;
+    int32_t max_tree_leaves; /* most leaves of any tree (1..256) */
+    int32_t layout;          /* shared-memory feature tile: 0 = choose, 1 = bytes, 2 = one word per rank byte */
     const int32_t* chunk_tree_off;
     const int32_t* chunk_seq;
+    const int32_t* chunk_node_off;
+    const int32_t* chunk_leaf_off;
     const int32_t* chunk_hdr_off;
     const uint32_t* tree_hdr;
-    const int32_t* seq_tree_off;
-    const int32_t* tree_node_off;
-    const int32_t* tree_leaf_off;
     const uint32_t* node_word;
     const double* leaf_value;
     const double* baseline;

@@ -1,19 +1,29 @@
 // dr_forest_predict_ranked: rank-coded forest inference for all-discrete models (see the header).
 //
 // Compared with the generic float64 kernel: a node is one 32-bit word instead of 12 bytes and a
-// cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~40 KB of features
+// cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~17 KB of features
 // and 16 warps stay resident per SM.  The forest is streamed through shared memory in chunks of whole
 // trees by the TMA engine (cp.async.bulk + mbarrier, double buffered: chunk k+1 lands while chunk k is
-// walked).  Each thread walks kIlp trees at a time for a fixed number of levels -- leaves point at
-// themselves, NaN is folded into two rank variants -- so a level is two shared-memory loads and six ALU
-// ops with no data-dependent branch, and the kIlp dependent chains overlap.  Leaf values are float64
-// and are added to the sequence's accumulator in tree order: margins are bit-identical to the generic
-// kernel and to the oracle.
+// walked).  Each thread walks kIlp trees at a time for a fixed number of levels.  The kernel is bound
+// by shared-memory wavefronts (two loads per level: rank byte, node word), so everything else is
+// squeezed out of the level: the node word is carry coded (word + rank overflows into the child index
+// exactly when the row goes right; siblings are adjacent), child indices are absolute within the
+// chunk, leaves point at themselves and NaN is folded into two copies of every rank byte -- a level
+// is LDS.U8, IADD, PRMT, LDS with no compare, select or branch.  Leaf values are float64 and are
+// added to the sequence's accumulator in tree order: margins are bit-identical to the generic kernel
+// and to the oracle.
 #include "common.cuh"
 
 namespace {
 
-constexpr int T = 256;
+// Two feature-tile layouts:
+//  * wide   (512 cells / CTA, 1 CTA / SM): one 32-bit word per rank byte, [feature byte][thread].  Lane
+//           L of a warp always reads bank L, whatever feature its node tests: the rank load is ONE
+//           shared-memory wavefront (the byte layout needs ~3 once the lanes of a warp have spread
+//           over different nodes).  Needs 2 * n_feat * 2 KB of shared memory: up to 37 features.
+//  * bytes  (256 cells / CTA, 2 CTAs / SM): [thread][feature byte], odd word stride.
+constexpr int kWideThreads = 512;
+constexpr int kByteThreads = 256;
 constexpr int kChunkNodes = DR_RANKED_CHUNK_NODES;
 constexpr int kChunkLeaves = DR_RANKED_CHUNK_LEAVES;
 #ifndef DR_FOREST_ILP
@@ -60,33 +70,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// One level: two shared-memory loads (feature rank, next node word) and five ALU ops.  All fields
-// of the node word are byte aligned (PRMT extracts), children are stored as byte offsets from the
-// tree root, leaves point at themselves (left = right = own offset).
-__device__ __forceinline__ uint32_t step_node(const unsigned char* __restrict__ tree, uint32_t w,
-                                              const uint8_t* __restrict__ my_feat) {
-    const uint32_t r = my_feat[w >> 24];                       // rank, NaN-left / NaN-right variant
-    const uint32_t thr = __byte_perm(w, 0, 0x4442);            // byte 2
-    const uint32_t off = __byte_perm(w, 0, r < thr ? 0x4441 : 0x4440);  // byte 1 (left) or byte 0 (right)
-    return *reinterpret_cast<const uint32_t*>(tree + off);
+// One level: two shared-memory loads (rank byte, next node word), one add and one byte extract.
+template <bool kWide>
+__device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, uint32_t w,
+                                              const unsigned char* __restrict__ my_feat) {
+    uint32_t r;
+    if (kWide) r = *reinterpret_cast<const uint32_t*>(my_feat + (w >> 24) * (kWideThreads * 4));
+    else       r = my_feat[w >> 24];
+    const uint32_t w2 = w + r;                          // carries into bit 8 iff rank >= threshold
+    return nodes[__byte_perm(w2, 0, 0x4421)];           // bits 8..23: left child (+1 = right child)
 }
 
-constexpr int kChunkTrees = 256;  // trees per chunk (host caps the chunk table accordingly)
+constexpr int kChunkTrees = DR_RANKED_CHUNK_TREES;
 
 struct __align__(16) ChunkBuf {
     double leaf[kChunkLeaves];
     uint32_t node[kChunkNodes];
-    uint32_t hdr[kChunkTrees];  // per tree of the chunk: (first node word << 16) | first leaf, chunk relative
+    uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, first leaf), chunk relative
 };
 
-__global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
+template <bool kWide>
+__global__ void __launch_bounds__(kWide ? kWideThreads : kByteThreads, kWide ? 1 : 2)
+k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
+    constexpr int T = kWide ? kWideThreads : kByteThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const dr_forest_ranked& F = p.f;
     ChunkBuf* buf = reinterpret_cast<ChunkBuf*>(smem_raw);                       // two chunk buffers
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(ChunkBuf));  // two mbarriers
-    uint8_t* s_feat = smem_raw + 2 * sizeof(ChunkBuf) + 16;
+    unsigned char* s_feat = smem_raw + 2 * sizeof(ChunkBuf) + 16;
     const int t = threadIdx.x;
-    uint8_t* my_feat = s_feat + (size_t)t * p.feat_stride;
+    unsigned char* my_feat = kWide ? s_feat + 4 * t : s_feat + (size_t)t * p.feat_stride;
     const int depth = F.max_depth;
     if (t == 0) {
         mbar_init(&bar[0], 1);
@@ -97,15 +110,14 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
     uint32_t phase0 = 0, phase1 = 0;
 
     auto issue = [&](int c, int b) {  // thread 0: start the TMA copies of chunk c into buffer b
-        const int ta = F.chunk_tree_off[c], tb = F.chunk_tree_off[c + 1];
-        const int n0 = F.tree_node_off[ta], n1 = F.tree_node_off[tb];
-        const int l0 = F.tree_leaf_off[ta], l1 = F.tree_leaf_off[tb];
+        const int n0 = F.chunk_node_off[c], n1 = F.chunk_node_off[c + 1];
+        const int l0 = F.chunk_leaf_off[c], l1 = F.chunk_leaf_off[c + 1];
         const int h0 = F.chunk_hdr_off[c], h1 = F.chunk_hdr_off[c + 1];
-        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u, hb = (uint32_t)(h1 - h0) * 4u;
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u, hb = (uint32_t)(h1 - h0) * 8u;
         mbar_expect_tx(&bar[b], nb + lb + hb);
         bulk_g2s(buf[b].node, F.node_word + n0, nb, &bar[b]);
         bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &bar[b]);
-        bulk_g2s(buf[b].hdr, F.tree_hdr + h0, hb, &bar[b]);
+        bulk_g2s(buf[b].hdr, F.tree_hdr + 2 * (size_t)h0, hb, &bar[b]);
     };
 
     for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
@@ -122,10 +134,15 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
                     const int k = lo + trow[F.feat_col[f]] + 1;
                     if (k >= lo && k < hi) r = __ldg(F.rank_lut + k);
                 }
-                // ranks are stored +1 (1..254); NaN becomes 255 where NaN goes right and 0 where it
-                // goes left, so `rank < thr` needs no special case
-                my_feat[2 * f + 0] = r;
-                my_feat[2 * f + 1] = r == 255 ? 0 : r;
+                // ranks are stored +1 (1..254); NaN is 255 in the copy read by nodes that send NaN
+                // right and 0 in the copy read by nodes that send it left
+                if (kWide) {
+                    reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 0) * T] = r;
+                    reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 1) * T] = r == 255 ? 0 : r;
+                } else {
+                    my_feat[2 * f + 0] = r;
+                    my_feat[2 * f + 1] = r == 255 ? 0 : r;
+                }
             }
         }
         double best = 0.0, margin0 = 0.0, acc = F.baseline[0];
@@ -143,32 +160,35 @@ __global__ void __launch_bounds__(T, 2) k_forest_predict_ranked(const __grid_con
             }
             if (b == 0) { while (!mbar_try_wait(&bar[0], phase0)) {} phase0 ^= 1; }
             else        { while (!mbar_try_wait(&bar[1], phase1)) {} phase1 ^= 1; }
-            const unsigned char* __restrict__ nodes = reinterpret_cast<const unsigned char*>(buf[b].node);
+            const uint32_t* __restrict__ nodes = buf[b].node;
             const double* __restrict__ leaves = buf[b].leaf;
-            const uint32_t* __restrict__ hdr = buf[b].hdr;
+            const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
-            int q = 0;
-            for (; q + kIlp <= n_trees; q += kIlp) {
-                const unsigned char* tree[kIlp];
-                uint32_t w[kIlp];
+            for (int q = 0; q < n_trees; q += kIlp) {
+                uint32_t w[kIlp], lb[kIlp];
 #pragma unroll
-                for (int j = 0; j < kIlp; ++j) {
-                    tree[j] = nodes + (hdr[q + j] >> 16) * 4u;
-                    w[j] = *reinterpret_cast<const uint32_t*>(tree[j]);
+                for (int j = 0; j < kIlp; j += 2) {  // two tree headers per 128-bit broadcast load
+                    const uint4 h = hdr4[(q + j) >> 1];
+                    w[j] = h.x; lb[j] = h.y; w[j + 1] = h.z; lb[j + 1] = h.w;
+                }
+                if (q + kIlp > n_trees) {  // last group of a sequence: surplus slots re-walk tree 0
+#pragma unroll
+                    for (int j = 1; j < kIlp; ++j)
+                        if (q + j >= n_trees) w[j] = w[0];
                 }
                 for (int d = 0; d < depth; ++d) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) w[j] = step_node(tree[j], w[j], my_feat);
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide>(nodes, w[j], my_feat);
                 }
+                if (q + kIlp <= n_trees) {
 #pragma unroll
-                for (int j = 0; j < kIlp; ++j)  // tree order: bit-identical float64 sums
-                    acc += leaves[(hdr[q + j] & 0xFFFFu) + __byte_perm(w[j], 0, 0x4442)];
-            }
-            for (; q < n_trees; ++q) {
-                const unsigned char* tree = nodes + (hdr[q] >> 16) * 4u;
-                uint32_t w0 = *reinterpret_cast<const uint32_t*>(tree);
-                for (int d = 0; d < depth; ++d) w0 = step_node(tree, w0, my_feat);
-                acc += leaves[(hdr[q] & 0xFFFFu) + __byte_perm(w0, 0, 0x4442)];
+                    for (int j = 0; j < kIlp; ++j)  // tree order: bit-identical float64 sums
+                        acc += leaves[lb[j] + (w[j] >> 24)];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kIlp; ++j)
+                        if (q + j < n_trees) acc += leaves[lb[j] + (w[j] >> 24)];
+                }
             }
             __syncthreads();  // buffer b may be refilled (chunk c + 2) only after everybody left it
         }
@@ -192,13 +212,12 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     DR_REQUIRE(ctx, forest && cells && tile, "null pointer");
     const dr_forest_ranked& f = *forest;
     DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 127, "the ranked kernel takes at most 127 features");
-    DR_REQUIRE(ctx, f.seq_tree_off && f.tree_node_off && f.tree_leaf_off && f.baseline && f.feat_col &&
-                        f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq && f.chunk_hdr_off && f.tree_hdr &&
-                        f.node_word &&
+    DR_REQUIRE(ctx, f.baseline && f.feat_col && f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq &&
+                        f.chunk_node_off && f.chunk_leaf_off && f.chunk_hdr_off && f.tree_hdr && f.node_word &&
                         f.leaf_value, "null forest array");
     DR_REQUIRE(ctx, f.n_chunks >= 1, "the ranked forest needs at least one chunk (one tree per sequence)");
-    DR_REQUIRE(ctx, ((uintptr_t)f.node_word & 15) == 0 && ((uintptr_t)f.leaf_value & 15) == 0,
-               "node / leaf arrays must be 16-byte aligned");
+    DR_REQUIRE(ctx, ((uintptr_t)f.node_word & 15) == 0 && ((uintptr_t)f.leaf_value & 15) == 0 &&
+                        ((uintptr_t)f.tree_hdr & 15) == 0, "node / leaf / header arrays must be 16-byte aligned");
     DR_REQUIRE(ctx, f.max_depth >= 0 && f.max_depth <= 63, "bad max_depth");
     DR_REQUIRE(ctx, target_col >= 0 && target_col < n_cols, "bad target column");
     DR_REQUIRE(ctx, f.n_seq == 1 ? f.n_classes >= 2 : f.n_classes == f.n_seq, "class count mismatch");
@@ -210,18 +229,36 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     p.n_cells = n_cells;
     p.target_col = target_col;
     p.out_margin = out_margin;
-    int words = (2 * f.n_feat + 3) / 4;
-    if (words < 1) words = 1;
-    if ((words & 1) == 0) ++words;  // odd word stride: consecutive threads land on different banks
-    p.feat_stride = words * 4;
-    const size_t smem = 2 * sizeof(ChunkBuf) + 16 + (size_t)T * p.feat_stride;
-    if (smem > 200 * 1024)
-        return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d features exceeds shared memory", f.n_feat);
-    DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    const int grid = dr_grid_for(ctx, n_cells, T, per_sm);
-    k_forest_predict_ranked<<<grid, T, smem, (cudaStream_t)stream>>>(p);
+    // a leaf's self-loop reads (and ignores) the rank slot named by its leaf number: the byte tile is
+    // padded by 256 bytes for that, the wide tile is only used when every leaf number is a valid slot
+    const size_t fixed = 2 * sizeof(ChunkBuf) + 16;
+    const int n_slots = 2 * f.n_feat > 0 ? 2 * f.n_feat : 1;
+    const size_t smem_wide = fixed + (size_t)n_slots * kWideThreads * 4;
+    DR_REQUIRE(ctx, f.max_tree_leaves >= 1 && f.max_tree_leaves <= 256, "bad max_tree_leaves");
+    DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 2, "bad layout");
+    const bool wide_ok = smem_wide <= 220 * 1024 && f.max_tree_leaves <= n_slots;
+    if (f.layout == 2 && !wide_ok)
+        return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide feature tile does not fit a forest with %d features", f.n_feat);
+    if (wide_ok && f.layout != 1) {
+        p.feat_stride = 0;
+        DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_wide));
+        const int grid = dr_grid_for(ctx, n_cells, kWideThreads, 1);
+        k_forest_predict_ranked<true><<<grid, kWideThreads, smem_wide, (cudaStream_t)stream>>>(p);
+    } else {
+        int words = (2 * f.n_feat + 3) / 4;
+        if (words < 1) words = 1;
+        if ((words & 1) == 0) ++words;  // odd word stride: consecutive threads land on different banks
+        p.feat_stride = words * 4;
+        const size_t smem = fixed + (size_t)kByteThreads * p.feat_stride + 256;
+        if (smem > 200 * 1024)
+            return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d features exceeds shared memory", f.n_feat);
+        DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        const int grid = dr_grid_for(ctx, n_cells, kByteThreads, per_sm);
+        k_forest_predict_ranked<false><<<grid, kByteThreads, smem, (cudaStream_t)stream>>>(p);
+    }
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

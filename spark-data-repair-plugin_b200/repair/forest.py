@@ -19,6 +19,8 @@ Encoders (one per feature column, in feature order):
                                                     level = -1 row; NULL never seen -> zeros; unseen -> NaN
   categories hold dictionary CODES (-1 = the NULL category).
 """
+import os
+
 import numpy as np
 
 LEAF = 0xFFF
@@ -122,10 +124,46 @@ def group_by_sequence(forest):
     return off, order
 
 
+def bfs_relabel(toff, left, right, is_leaf):
+    """Breadth-first renumbering of every tree at once: root = 0 and the right child of a node is its
+    left child + 1 (what the carry-coded node word needs).  -> (new tree-relative index per node, -1
+    for nodes the root does not reach; nodes kept per tree; deepest leaf of any tree)."""
+    toff = np.asarray(toff, dtype=np.int64)
+    n_trees = len(toff) - 1
+    new = np.full(len(left), -1, dtype=np.int64)
+    kept = np.ones(n_trees, dtype=np.int64)
+    if n_trees == 0:
+        return new, kept, 0
+    frontier, ftree = toff[:-1].copy(), np.arange(n_trees, dtype=np.int64)
+    new[frontier] = 0
+    depth = 0
+    while True:
+        inner = ~is_leaf[frontier]
+        if not inner.any():
+            break
+        fr, tr = frontier[inner], ftree[inner]                 # grouped by tree, level order inside a tree
+        start = np.flatnonzero(np.r_[True, tr[1:] != tr[:-1]])
+        cnt = np.diff(np.r_[start, len(tr)])
+        k = np.arange(len(tr)) - np.repeat(start, cnt)
+        base = kept[tr] + 2 * k
+        lch, rch = toff[tr] + left[fr], toff[tr] + right[fr]
+        new[lch], new[rch] = base, base + 1
+        kept[tr[start]] += 2 * cnt
+        frontier, ftree = np.stack([lch, rch], axis=1).ravel(), np.repeat(tr, 2)
+        depth += 1
+    return new, kept, depth
+
+
 def rank_code(spec, dict_sizes):
     """Rank-coded image of an all-discrete model for dr_forest_predict_ranked, or None when the
-    model does not qualify (continuous feature, > 254 distinct values per feature, a tree with more
-    than 64 nodes, > 2046 features).  Decisions are unchanged: `x <= thr` <=> `rank(x) < #values <= thr`."""
+    model does not qualify (continuous feature, > 253 distinct values per feature, > 127 features, a
+    tree with more than 256 leaves).  Decisions are unchanged: `x <= thr` <=> `rank(x) < #values <= thr`.
+
+    Trees are renumbered breadth first with siblings adjacent (bfs_relabel); `word` holds the node
+    words with TREE-relative child indices (ranked_image rebases them to the chunk):
+      internal  (2*feature + nan_left) << 24 | left child << 8 | (256 - (thr_rank + 1))
+      leaf      leaf number in the tree  << 24 | own index  << 8 | 0
+    so that `word + rank` carries into the child field exactly when the row goes right."""
     f = spec["forest"]
     encoders = spec["encoders"]
     if any(e["type"] == "cont" for e in encoders) or spec.get("class_codes") is None:
@@ -139,10 +177,6 @@ def rank_code(spec, dict_sizes):
     n_feat = len(luts)
     if n_feat != int(f["n_features"]) or n_feat > 127:
         return None
-    toff = np.asarray(f["tree_offset"], dtype=np.int64)
-    sizes = toff[1:] - toff[:-1]
-    if len(sizes) and sizes.max() > 64:
-        return None
     rank_lut, rank_off, values = [], [0], []
     for col in luts:
         vals = np.unique(col[~np.isnan(col)])
@@ -154,94 +188,106 @@ def rank_code(spec, dict_sizes):
         rank_lut.append(r)
         rank_off.append(rank_off[-1] + len(r))
         values.append(vals)
+    toff = np.asarray(f["tree_offset"], dtype=np.int64)
     feat = np.asarray(f["feature"], dtype=np.int64)
     is_leaf = feat < 0
+    left, right = np.asarray(f["left"], dtype=np.int64), np.asarray(f["right"], dtype=np.int64)
+    new, kept, depth = bfs_relabel(toff, left, right, is_leaf)
+    new_toff = np.zeros(len(toff), dtype=np.int64)
+    new_toff[1:] = np.cumsum(kept)
+    old_sizes = toff[1:] - toff[:-1]
+    tree_of = np.repeat(np.arange(len(old_sizes)), old_sizes)
+    live = new >= 0
+    pos = new_toff[tree_of[live]] + new[live]                      # new global slot of every kept node
+    src = np.empty(int(new_toff[-1]), dtype=np.int64)
+    src[pos] = np.flatnonzero(live)                                # old node stored in each new slot
     thr = np.asarray(f["threshold"], dtype=np.float64)
-    thr_rank = np.zeros(len(feat), dtype=np.uint32)
+    thr_rank = np.zeros(len(feat), dtype=np.int64)
     for j in range(n_feat):  # number of distinct values <= threshold, per feature
         m = feat == j
         if m.any():
             thr_rank[m] = np.searchsorted(values[j], thr[m], side="right")
-    tree_of = np.repeat(np.arange(len(sizes)), sizes)
-    leaf_cum = np.cumsum(is_leaf) - is_leaf                      # leaves before each node
-    tree_leaf_off = np.zeros(len(sizes) + 1, dtype=np.int64)
-    tree_leaf_off[:-1] = leaf_cum[toff[:-1]] if len(sizes) else 0
-    tree_leaf_off[-1] = int(is_leaf.sum())
-    leaf_idx = leaf_cum - tree_leaf_off[tree_of] if len(feat) else leaf_cum
-    node_in_tree = (np.arange(len(feat)) - toff[tree_of]).astype(np.uint32) if len(feat) else np.zeros(0, np.uint32)
-    if len(leaf_idx) and leaf_idx.max() > 255:
+    n_leaf = is_leaf[src]
+    n_tree = tree_of[src]
+    leaf_cum = np.cumsum(n_leaf) - n_leaf                          # leaves before each slot
+    tree_leaf_off = np.zeros(len(toff), dtype=np.int64)
+    tree_leaf_off[:-1] = leaf_cum[new_toff[:-1]] if len(old_sizes) else 0
+    tree_leaf_off[-1] = int(n_leaf.sum())
+    leaf_no = leaf_cum - tree_leaf_off[n_tree] if len(src) else leaf_cum
+    if len(leaf_no) and leaf_no[n_leaf].size and leaf_no[n_leaf].max() > 255:
         return None
-    ml = np.asarray(f["missing_left"], dtype=np.uint32) & np.uint32(1)
-    internal = (((np.where(is_leaf, 0, feat).astype(np.uint32) * np.uint32(2) + ml) << np.uint32(24)) |
-                ((thr_rank + np.uint32(1)) << np.uint32(16)) |
-                ((np.asarray(f["left"], dtype=np.uint32) * np.uint32(4)) << np.uint32(8)) |
-                (np.asarray(f["right"], dtype=np.uint32) * np.uint32(4)))
-    leaf = (leaf_idx.astype(np.uint32) << np.uint32(16)) | ((node_in_tree * np.uint32(4)) << np.uint32(8)) | \
-        (node_in_tree * np.uint32(4))
-    word = np.where(is_leaf, leaf, internal).astype(np.uint32)
-    # deepest leaf: breadth-first sweep over all trees at once
-    depth, frontier = 0, toff[:-1].copy()
-    base = toff[:-1].copy()
-    left, right = np.asarray(f["left"], dtype=np.int64), np.asarray(f["right"], dtype=np.int64)
-    while True:
-        inner = ~is_leaf[frontier] if len(frontier) else np.zeros(0, dtype=bool)
-        if not inner.any():
-            break
-        fr, bs = frontier[inner], base[inner]
-        frontier = np.concatenate([bs + left[fr], bs + right[fr]])
-        base = np.concatenate([bs, bs])
-        depth += 1
-    return {"word": word, "leaf_value": np.asarray(f["value"], dtype=np.float64)[is_leaf],
+    own = np.arange(len(src), dtype=np.int64) - new_toff[n_tree]
+    ml = np.asarray(f["missing_left"], dtype=np.int64)[src] & 1
+    child = new[np.where(n_leaf, src, toff[n_tree] + left[src])]   # left child, tree relative
+    cthr = 256 - (thr_rank[src] + 1)                               # thr in 1..254 -> 2..255
+    internal = ((feat[src] * 2 + ml) << 24) | (child << 8) | cthr
+    leaf = (leaf_no << 24) | (own << 8)
+    word = np.where(n_leaf, leaf, internal).astype(np.uint32)
+    return {"word": word, "tree_offset": new_toff, "leaf_value": np.asarray(f["value"], dtype=np.float64)[src][n_leaf],
             "tree_leaf_off": tree_leaf_off, "rank_lut": np.concatenate(rank_lut) if rank_lut else np.zeros(1, np.uint8),
-            "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth}
+            "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth,
+            "max_tree_leaves": int((tree_leaf_off[1:] - tree_leaf_off[:-1]).max()) if len(old_sizes) else 1}
 
 
-RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES = 4096, 2176  # DR_RANKED_CHUNK_* in include/b200repair.h
+# DR_RANKED_CHUNK_* in include/b200repair.h
+RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 4096, 2176, 256, 8
 
 
-def ranked_image(rk, toff, order, seq_tree_off):
-    """Device layout of a rank-coded forest: trees grouped by sequence (`order`), every tree's node
-    words padded to a multiple of 4 and its leaves to a multiple of 2 (16-byte TMA granules), plus the
-    chunk table the kernel streams by (whole trees, never straddling a sequence)."""
-    toff = np.asarray(toff, dtype=np.int64)
+def ranked_image(rk, order, seq_tree_off):
+    """Device layout of a rank-coded forest: trees grouped by sequence (`order`) and cut into chunks
+    of whole trees that fit the kernel's shared-memory buffers (never straddling a sequence; a
+    multiple of RANKED_GROUP trees except at the end of a sequence).  Every chunk starts on a 16-byte
+    boundary of the node / leaf / header arrays (TMA granules); child indices are rebased to the
+    chunk; tree_hdr holds, per tree, (root word, first leaf) relative to the chunk."""
+    toff = np.asarray(rk["tree_offset"], dtype=np.int64)
     lo = np.asarray(rk["tree_leaf_off"], dtype=np.int64)
+    order = np.asarray(order, dtype=np.int64)
     n_sizes = (toff[1:] - toff[:-1])[order]
     l_sizes = (lo[1:] - lo[:-1])[order]
-    n_pad, l_pad = (n_sizes + 3) // 4 * 4, (l_sizes + 1) // 2 * 2
-    node_off = np.zeros(len(order) + 1, dtype=np.int64)
-    leaf_off = np.zeros(len(order) + 1, dtype=np.int64)
-    node_off[1:], leaf_off[1:] = np.cumsum(n_pad), np.cumsum(l_pad)
-    word = np.zeros(int(node_off[-1]), dtype=np.uint32)
-    leaf = np.zeros(int(leaf_off[-1]), dtype=np.float64)
-    # scatter every tree's nodes / leaves to its padded slot (vectorised over all trees)
-    tree_new = np.repeat(np.arange(len(order)), n_sizes)
-    within = np.arange(int(n_sizes.sum())) - np.repeat(np.cumsum(n_sizes) - n_sizes, n_sizes)
-    src = np.repeat(toff[:-1][order], n_sizes) + within
-    word[node_off[tree_new] + within] = rk["word"][src]
-    ltree_new = np.repeat(np.arange(len(order)), l_sizes)
-    lwithin = np.arange(int(l_sizes.sum())) - np.repeat(np.cumsum(l_sizes) - l_sizes, l_sizes)
-    lsrc = np.repeat(lo[:-1][order], l_sizes) + lwithin
-    leaf[leaf_off[ltree_new] + lwithin] = rk["leaf_value"][lsrc]
-    chunk_tree_off, chunk_seq, chunk_hdr_off, hdr = [0], [], [0], []
+    nc, lc = np.r_[0, np.cumsum(n_sizes)], np.r_[0, np.cumsum(l_sizes)]
+    chunk_tree_off, chunk_seq = [0], []
     for s in range(len(seq_tree_off) - 1):
         t, t_end = int(seq_tree_off[s]), int(seq_tree_off[s + 1])
         while t < t_end:
-            # largest hi with node/leaf footprint of trees [t, hi) inside the chunk buffers
-            hi_n = int(np.searchsorted(node_off, node_off[t] + RANKED_CHUNK_NODES, side="right")) - 1
-            hi_l = int(np.searchsorted(leaf_off, leaf_off[t] + RANKED_CHUNK_LEAVES, side="right")) - 1
-            hi = max(t + 1, min(hi_n, hi_l, t_end, t + 256))
+            hi_n = int(np.searchsorted(nc, nc[t] + RANKED_CHUNK_NODES, side="right")) - 1
+            hi_l = int(np.searchsorted(lc, lc[t] + RANKED_CHUNK_LEAVES, side="right")) - 1
+            hi = min(hi_n, hi_l, t + RANKED_CHUNK_TREES)
+            if hi < t_end:
+                hi = t + max((hi - t) // RANKED_GROUP * RANKED_GROUP, 1)
+            hi = max(t + 1, min(hi, t_end))
+            if nc[hi] - nc[t] > RANKED_CHUNK_NODES or lc[hi] - lc[t] > RANKED_CHUNK_LEAVES:
+                raise ValueError("a tree does not fit the ranked kernel's chunk buffers")
             chunk_tree_off.append(hi)
             chunk_seq.append(s)
-            h = ((node_off[t:hi] - node_off[t]) << 16) | (leaf_off[t:hi] - leaf_off[t])
-            pad = (-len(h)) % 4
-            hdr.append(np.concatenate([h, np.zeros(pad, dtype=np.int64)]))
-            chunk_hdr_off.append(chunk_hdr_off[-1] + len(h) + pad)
             t = hi
-    return {"word": word, "leaf": leaf, "node_off": node_off, "leaf_off": leaf_off,
-            "chunk_tree_off": np.asarray(chunk_tree_off, dtype=np.int32),
-            "chunk_seq": np.asarray(chunk_seq, dtype=np.int32),
-            "chunk_hdr_off": np.asarray(chunk_hdr_off, dtype=np.int32),
-            "tree_hdr": np.concatenate(hdr).astype(np.uint32) if hdr else np.zeros(4, dtype=np.uint32)}
+    cto = np.asarray(chunk_tree_off, dtype=np.int64)
+    c_nodes, c_leaves, c_trees = nc[cto[1:]] - nc[cto[:-1]], lc[cto[1:]] - lc[cto[:-1]], cto[1:] - cto[:-1]
+    chunk_node_off = np.r_[0, np.cumsum((c_nodes + 3) // 4 * 4)]
+    chunk_leaf_off = np.r_[0, np.cumsum((c_leaves + 1) // 2 * 2)]
+    chunk_hdr_off = np.r_[0, np.cumsum((c_trees + 1) // 2 * 2)]
+    chunk_of_tree = np.repeat(np.arange(len(c_trees)), c_trees)
+    node_in_chunk = nc[:-1] - nc[cto[:-1]][chunk_of_tree]          # first node of each tree, chunk relative
+    leaf_in_chunk = lc[:-1] - lc[cto[:-1]][chunk_of_tree]
+    word = np.zeros(max(int(chunk_node_off[-1]), 4), dtype=np.uint32)
+    leaf = np.zeros(max(int(chunk_leaf_off[-1]), 2), dtype=np.float64)
+    hdr = np.zeros((max(int(chunk_hdr_off[-1]), 2), 2), dtype=np.uint32)
+    tree_new = np.repeat(np.arange(len(order)), n_sizes)
+    within = np.arange(int(n_sizes.sum())) - np.repeat(nc[:-1], n_sizes)
+    src = np.repeat(toff[:-1][order], n_sizes) + within
+    rebased = rk["word"][src].astype(np.int64) + (node_in_chunk[tree_new] << 8)
+    word[chunk_node_off[chunk_of_tree[tree_new]] + node_in_chunk[tree_new] + within] = rebased.astype(np.uint32)
+    ltree_new = np.repeat(np.arange(len(order)), l_sizes)
+    lwithin = np.arange(int(l_sizes.sum())) - np.repeat(lc[:-1], l_sizes)
+    lsrc = np.repeat(lo[:-1][order], l_sizes) + lwithin
+    leaf[chunk_leaf_off[chunk_of_tree[ltree_new]] + leaf_in_chunk[ltree_new] + lwithin] = rk["leaf_value"][lsrc]
+    slot = chunk_hdr_off[chunk_of_tree] + (np.arange(len(order)) - cto[:-1][chunk_of_tree])
+    roots = chunk_node_off[chunk_of_tree] + node_in_chunk
+    hdr[slot, 0] = word[roots] if len(order) else 0
+    hdr[slot, 1] = leaf_in_chunk
+    return {"word": word, "leaf": leaf, "tree_hdr": hdr.reshape(-1),
+            "chunk_tree_off": cto.astype(np.int32), "chunk_seq": np.asarray(chunk_seq, dtype=np.int32),
+            "chunk_node_off": chunk_node_off.astype(np.int32), "chunk_leaf_off": chunk_leaf_off.astype(np.int32),
+            "chunk_hdr_off": chunk_hdr_off.astype(np.int32)}
 
 
 class DeviceModel:
@@ -312,14 +358,14 @@ class DeviceModel:
         rk = rank_code(spec, dict_sizes) if self.kind == 0 else None
         if rk is not None and len(order) and np.all(np.diff(off) > 0):
             from ._native import dr_forest_ranked
-            img = ranked_image(rk, toff, order, off)
+            img = ranked_image(rk, order, off)
             self._keep.update({
                 "r_node_word": dev(img["word"].view(np.int32), np.int32),
                 "r_leaf_value": dev(img["leaf"], np.float64),
-                "r_tree_node_off": dev(img["node_off"], np.int32),
-                "r_tree_leaf_off": dev(img["leaf_off"], np.int32),
                 "r_chunk_tree_off": dev(img["chunk_tree_off"], np.int32),
                 "r_chunk_seq": dev(img["chunk_seq"], np.int32),
+                "r_chunk_node_off": dev(img["chunk_node_off"], np.int32),
+                "r_chunk_leaf_off": dev(img["chunk_leaf_off"], np.int32),
                 "r_chunk_hdr_off": dev(img["chunk_hdr_off"], np.int32),
                 "r_tree_hdr": dev(img["tree_hdr"].view(np.int32), np.int32),
                 "r_rank_lut": dev(rk["rank_lut"], np.uint8),
@@ -329,11 +375,14 @@ class DeviceModel:
             r = dr_forest_ranked()
             r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, len(img["word"]), len(img["leaf"])
             r.n_feat, r.max_depth, r.n_chunks = n_feat, int(rk["max_depth"]), len(img["chunk_seq"])
+            # DR_RANKED_LAYOUT=bytes|wide pins the shared-memory feature tile (profiling aid)
+            r.max_tree_leaves = int(rk["max_tree_leaves"])
+            r.layout = {"": 0, "bytes": 1, "wide": 2}[os.environ.get("DR_RANKED_LAYOUT", "")]
             for field, key in (("chunk_tree_off", "r_chunk_tree_off"), ("chunk_seq", "r_chunk_seq"),
+                               ("chunk_node_off", "r_chunk_node_off"), ("chunk_leaf_off", "r_chunk_leaf_off"),
                                ("chunk_hdr_off", "r_chunk_hdr_off"), ("tree_hdr", "r_tree_hdr"),
-                               ("seq_tree_off", "seq_tree_off"), ("tree_node_off", "r_tree_node_off"),
-                               ("tree_leaf_off", "r_tree_leaf_off"), ("node_word", "r_node_word"),
-                               ("leaf_value", "r_leaf_value"), ("baseline", "baseline"), ("feat_col", "r_feat_col"),
+                               ("node_word", "r_node_word"), ("leaf_value", "r_leaf_value"),
+                               ("baseline", "baseline"), ("feat_col", "r_feat_col"),
                                ("rank_lut_off", "r_rank_lut_off"), ("rank_lut", "r_rank_lut"),
                                ("class_code", "class_code")):
                 setattr(r, field, self._keep[key].data_ptr())

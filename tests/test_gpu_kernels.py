@@ -431,12 +431,14 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
     cells = np.sort(rng.choice(n, size=n * 2 // 3, replace=False)).astype(np.int32)
     X = encode_matrix(encoders, {nm: tile_np[cells, tile_cols[nm]] for nm in names[1:]}, {}, dict_sizes)
     want_m, want = forest_margins(forest, X), forest_predict(forest, X)
-    for generic in (False, True):
+    assert dm.ranked.max_tree_leaves <= 2 * n_feat          # so that the wide feature tile is exercised too
+    for variant in ("auto", "bytes", "wide", "generic"):
+        dm.ranked.layout = {"auto": 0, "bytes": 1, "wide": 2, "generic": 0}[variant]
         tile = dev(tile_np)
         margins = torch.empty((len(cells), dm.n_seq), dtype=torch.float64, device="cuda")
-        dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=generic)
-        assert np.array_equal(margins.cpu().numpy(), want_m), generic
-        assert np.array_equal(tile.cpu().numpy()[cells, 0], want.astype(np.int32))
+        dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=variant == "generic")
+        assert np.array_equal(margins.cpu().numpy(), want_m), variant
+        assert np.array_equal(tile.cpu().numpy()[cells, 0], want.astype(np.int32)), variant
 
 
 def test_tile_null_bitmaps_and_rows_after_count(ctx):

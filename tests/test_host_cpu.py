@@ -394,24 +394,32 @@ def test_synthetic_generator_is_shardable_and_deterministic():
     assert any(len(set(dep[(det == v)].tolist())) > 1 for v in range(spec.dom[5] - 3, spec.dom[5]))
 
 
+def _walk_ranked(words, base, w, ranks_of_row, depth):
+    """One tree of the carry-coded layout for one row: -> leaf number within the tree."""
+    for _ in range(depth):
+        fsel = w >> 24
+        r = 0
+        if w & 0xFF:                                     # internal node (a leaf never reads its rank)
+            r = int(ranks_of_row[fsel >> 1])
+            r = (0 if (fsel & 1) else 255) if r == 255 else r
+        w2 = w + r                                       # carries into bit 8 iff rank >= threshold
+        w = int(words[base + ((w2 >> 8) & 0xFFFF)])
+    assert (w & 0xFF) == 0                               # a leaf: never carries ...
+    return w >> 24, (w >> 8) & 0xFFFF                    # ... and points at itself
+
+
 def _eval_ranked(rk, forest, codes_by_feat):
     """Reference evaluation of the rank-coded layout (what k_forest_predict_ranked does)."""
     n = len(codes_by_feat[0])
-    toff = np.asarray(forest["tree_offset"])
-    S = len(forest["baseline"])
+    toff = np.asarray(rk["tree_offset"])
     raw = np.tile(np.asarray(forest["baseline"], dtype=np.float64), (n, 1))
-    ranks = [rk["rank_lut"][rk["rank_lut_off"][j] + codes_by_feat[j] + 1] for j in range(len(codes_by_feat))]
+    ranks = np.stack([rk["rank_lut"][rk["rank_lut_off"][j] + codes_by_feat[j] + 1]
+                      for j in range(len(codes_by_feat))], axis=1)
     for t in range(len(toff) - 1):
         for i in range(n):
-            w = int(rk["word"][toff[t]])
-            for _ in range(rk["max_depth"]):
-                fidx = w >> 24
-                r = int(ranks[fidx >> 1][i])
-                r = (0 if (fidx & 1) else 255) if r == 255 else r
-                go_left = r < ((w >> 16) & 0xFF)
-                w = int(rk["word"][toff[t] + (((w >> 8) & 0xFF) if go_left else (w & 0xFF)) // 4])
-            assert ((w >> 8) & 0xFF) == (w & 0xFF)  # a leaf points at itself
-            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + ((w >> 16) & 0xFF)]
+            leaf_no, own = _walk_ranked(rk["word"], toff[t], int(rk["word"][toff[t]]), ranks[i], rk["max_depth"])
+            assert int(rk["word"][toff[t] + own]) >> 24 == leaf_no
+            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + leaf_no]
     return raw
 
 
@@ -440,8 +448,9 @@ def test_rank_coded_forest_makes_the_same_decisions():
 
 
 def test_ranked_image_padding_and_chunks():
-    from repair.forest import (RANKED_CHUNK_LEAVES, RANKED_CHUNK_NODES, encoder_width, group_by_sequence,
-                               rank_code, ranked_image)
+    from oracle.forest import forest_margins
+    from repair.forest import (RANKED_CHUNK_LEAVES, RANKED_CHUNK_NODES, RANKED_CHUNK_TREES, RANKED_GROUP,
+                               encode_matrix, encoder_width, group_by_sequence, rank_code, ranked_image)
     from repair.train import random_forest
     rng = np.random.default_rng(8)
     dict_sizes = {"a": 6, "b": 20}
@@ -451,18 +460,29 @@ def test_ranked_image_padding_and_chunks():
     forest = random_forest(n_feat, 7, 120, [[-0.5, 0.5]] * 5 + [[j + 0.5 for j in range(1, 20)]], rng)
     rk = rank_code({"forest": forest, "encoders": encoders, "class_codes": list(range(7))}, dict_sizes)
     off, order = group_by_sequence(forest)
-    img = ranked_image(rk, forest["tree_offset"], order, off)
-    assert np.all(img["node_off"] % 4 == 0) and np.all(img["leaf_off"] % 2 == 0)
+    img = ranked_image(rk, order, off)
     cto, cs = img["chunk_tree_off"], img["chunk_seq"]
+    cn, cl, ch = img["chunk_node_off"], img["chunk_leaf_off"], img["chunk_hdr_off"]
+    assert np.all(cn % 4 == 0) and np.all(cl % 2 == 0) and np.all(ch % 2 == 0)
     assert cto[0] == 0 and cto[-1] == len(order) and np.all(np.diff(cto) > 0) and len(cs) == len(cto) - 1
     for c in range(len(cs)):
         assert off[cs[c]] <= cto[c] and cto[c + 1] <= off[cs[c] + 1]                    # inside one sequence
-        assert img["node_off"][cto[c + 1]] - img["node_off"][cto[c]] <= RANKED_CHUNK_NODES
-        assert img["leaf_off"][cto[c + 1]] - img["leaf_off"][cto[c]] <= RANKED_CHUNK_LEAVES
+        assert cn[c + 1] - cn[c] <= RANKED_CHUNK_NODES and cl[c + 1] - cl[c] <= RANKED_CHUNK_LEAVES
+        assert cto[c + 1] - cto[c] <= RANKED_CHUNK_TREES
+        assert (cto[c + 1] - cto[c]) % RANKED_GROUP == 0 or cto[c + 1] == off[cs[c] + 1]
     assert list(cs) == sorted(cs) and set(cs) == set(range(7))
-    # every tree's words survive the move
-    t_new = 37
-    t_old = order[t_new]
-    n = forest["tree_offset"][t_old + 1] - forest["tree_offset"][t_old]
-    assert np.array_equal(img["word"][img["node_off"][t_new]:img["node_off"][t_new] + n],
-                          rk["word"][forest["tree_offset"][t_old]:forest["tree_offset"][t_old + 1]])
+    # walking the chunked image (chunk-absolute child indices, root words in the headers) gives the
+    # oracle's margins
+    n = 40
+    codes = {a: rng.integers(-1, d, size=n) for a, d in dict_sizes.items()}
+    X = encode_matrix(encoders, codes, {}, dict_sizes)
+    ranks = np.stack([rk["rank_lut"][rk["rank_lut_off"][j] + codes[a] + 1] for j, a in enumerate(rk["feat_attr"])], 1)
+    raw = np.tile(np.asarray(forest["baseline"], dtype=np.float64), (n, 1))
+    hdr = img["tree_hdr"].reshape(-1, 2)
+    for c in range(len(cs)):
+        for j in range(cto[c + 1] - cto[c]):
+            root, first_leaf = int(hdr[ch[c] + j, 0]), int(hdr[ch[c] + j, 1])
+            for i in range(n):
+                leaf_no, _ = _walk_ranked(img["word"], cn[c], root, ranks[i], rk["max_depth"])
+                raw[i, cs[c]] += img["leaf"][cl[c] + first_leaf + leaf_no]
+    assert np.array_equal(raw, forest_margins(forest, X))
