@@ -1,5 +1,6 @@
 """``Delphi`` facade (same surface as ``python/repair/api.py:26-63``): ``delphi.repair`` hands out
-a fresh :class:`RepairModel`."""
+a fresh :class:`RepairModel`, ``delphi.misc`` a fresh :class:`RepairMisc`."""
+from .misc import RepairMisc
 from .model import RepairModel
 
 
@@ -19,6 +20,10 @@ class Delphi():
     @property
     def repair(self) -> RepairModel:
         return RepairModel()
+
+    @property
+    def misc(self) -> RepairMisc:
+        return RepairMisc()
 
     @staticmethod
     def version() -> str:

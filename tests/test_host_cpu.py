@@ -486,3 +486,24 @@ def test_ranked_image_padding_and_chunks():
                 leaf_no, _ = _walk_ranked(img["word"], cn[c], root, ranks[i], rk["max_depth"])
                 raw[i, cs[c]] += img["leaf"][cl[c] + first_leaf + leaf_no]
     assert np.array_equal(raw, forest_margins(forest, X))
+
+
+def test_misc_repair_applies_updates_like_the_reference():
+    """RepairMiscSuite.scala:125-155 (repairAttrsFrom) known answers + misc.py:87-89 option check."""
+    import pandas as pd
+    from repair import delphi
+    from repair.utils import AnalysisException
+    inp = pd.DataFrame({"tid": [1, 2, 3], "x": pd.array([None, None, 1], dtype="Int64"),
+                        "y": ["test-1", None, "test-2"], "z": [1.0, 2.0, None]})
+    upd = pd.DataFrame({"tid": [1, 2, 2, 3], "attribute": ["x", "x", "y", "z"],
+                        "repaired": ["2.4", "2.6", "test-3", "3.1D"]})
+    delphi.register_table("inputView", inp)
+    delphi.register_table("repairUpdates", upd)
+    out = delphi.misc.options({"repair_updates": "repairUpdates", "table_name": "inputView", "row_id": "tid"}).repair()
+    assert out["tid"].tolist() == [1, 2, 3] and out["x"].tolist() == [2, 3, 1]
+    assert out["y"].tolist() == ["test-1", "test-3", "test-2"] and out["z"].tolist() == [1.0, 2.0, 3.1]
+    assert inp["y"].isna().tolist() == [False, True, False]         # the input is left alone
+    with pytest.raises(AnalysisException, match="Table 'inputView' must have 'tid', 'attribute', and 'repaired' columns"):
+        delphi.misc.options({"repair_updates": "inputView", "table_name": "inputView", "row_id": "tid"}).repair()
+    with pytest.raises(ValueError, match="Required options not found: repair_updates, table_name, row_id"):
+        delphi.misc.option("table_name", "inputView").repair()
