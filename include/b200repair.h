@@ -333,6 +333,24 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* params, const uint8_t* bins
                   void* workspace, int64_t workspace_bytes, dr_gbdt_node* out_nodes, int32_t* out_counts,
                   void* stream);
 
+/* ---- 8f #4: rule-based repairs -----------------------------------------------------------------
+ * dr_scatter_*: col[rows[i]] = vals[i] -- repairs decided by a rule join the repair base
+ *   (RepairModel._repair_attrs, model.py:1250-1257 -> RepairMiscApi.repairAttrsFrom :184-247).
+ * dr_fd_map_build: the map behind FunctionalDepModel (model.py:64-100), replacing
+ *   DepGraph.computeFunctionalDepMap (DepGraph.scala:300-316: GROUP BY x HAVING size(collect_set(y)) = 1).
+ *   For every row whose x and y are non-NULL and not masked (x_mask / y_mask: error-cell bitmaps, may be
+ *   NULL): lo[x] = min(lo[x], y), hi[x] = max(hi[x], y); lo/hi are device int32[dom_x], caller
+ *   initialises lo = INT32_MAX, hi = INT32_MIN.  x determines y iff lo[x] == hi[x]; both reductions are
+ *   idempotent, so per-GPU tables combine with one MIN / MAX all-reduce.
+ * dr_tile_lut_fill: FunctionalDepModel.predict on the dirty-row tile:
+ *   tile[cells[i]][y_col] = lut[tile[cells[i]][x_col] + 1]  (lut[0] = what a NULL x maps to, -1 = NULL). */
+int dr_scatter_i32(dr_ctx* ctx, int32_t* col, const int32_t* rows, const int32_t* vals, int64_t n, void* stream);
+int dr_scatter_f64(dr_ctx* ctx, double* col, const int32_t* rows, const double* vals, int64_t n, void* stream);
+int dr_fd_map_build(dr_ctx* ctx, const int32_t* x_col, const uint32_t* x_mask, const int32_t* y_col,
+                    const uint32_t* y_mask, int64_t n_rows, int32_t dom_x, int32_t* lo, int32_t* hi, void* stream);
+int dr_tile_lut_fill(dr_ctx* ctx, int32_t* tile, int n_cols, int x_col, int y_col, const int32_t* cells,
+                     int64_t n_cells, const int32_t* lut, int32_t lut_size, void* stream);
+
 /* PoorModel (model.py:44-61): constant fill of the listed tile rows. */
 int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int32_t* cells, int64_t n_cells,
                      int32_t value, void* stream);

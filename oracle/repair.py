@@ -239,14 +239,108 @@ def maximal_likelihood_repair(scored, delta):
     return [s[:4] for s in scored if s[4] >= thres]
 
 
+# --------------------------------------------------------------------------------------
+# Rule-based repairs (model.py:583-673, 731-753, 928-953; DepGraph.scala:257-317)
+# --------------------------------------------------------------------------------------
+def cost_of(cost_fn, x, y):
+    """UpdateCostFunction.compute (costs.py:33-34): NULL unless both operands are truthy."""
+    return cost_fn(str(x), str(y)) if x and y else None
+
+
+def repair_by_nearest_values(base, error_cells, target_columns, cost_fn, cost_targets, merge_threshold):
+    """_repair_by_nearest_values (model.py:583-626): an error cell whose current value is within
+    `merge_threshold` of exactly one nearest value of the attribute's (masked) domain takes that value.
+    Candidates whose cost is NULL can never win and never count as the runner-up (Spark's comparator
+    treats them as equal to everything, which leaves their position unspecified; `cost < NULL` is
+    never true either way).
+    -> (remaining error cells, [(row, attr, current_value, repaired typed value)])"""
+    targets = [c for c in target_columns if c in cost_targets] if cost_targets else list(target_columns)
+    domains = {}
+    for a in targets:
+        seen = []
+        for v in column_values(base, a):
+            if v is not None and v not in seen:
+                seen.append(v)
+        domains[a] = seen
+    remaining, repaired, memo = [], [], {}
+    for (r, a, cur) in error_cells:
+        best = None
+        if a in domains and domains[a] and cur:
+            if (a, cur) not in memo:  # same current value, same answer
+                costs = [(cost_of(cost_fn, cur, v), v) for v in domains[a]]
+                known = sorted([c for c in costs if c[0] is not None], key=lambda c: c[0])
+                ok = len(known) >= 2 and known[0][0] <= merge_threshold and known[0][0] < known[1][0]
+                memo[(a, cur)] = known[0][1] if ok else None
+            best = memo[(a, cur)]
+        if best is None:
+            remaining.append((r, a, cur))
+        else:
+            repaired.append((r, a, cur, best))
+    return remaining, repaired
+
+
+def functional_deps(table_attrs, constraint_path, constraints, target_attrs):
+    """DepGraph.computeFunctionalDeps (:257-298): {y: sorted [x]} for every constraint made of exactly
+    one EQ and one IQ predicate over a single attribute each, in statement order, skipping a
+    dependency whose reverse is already there."""
+    stmts = D.load_constraint_stmts(constraint_path, constraints)
+    pred_lists, _ = D.parse_and_verify_constraints(stmts, table_attrs) if stmts else ([], [])
+    fd = {}
+    for preds in pred_lists:
+        if len(preds) != 2 or {p.sign for p in preds} != {"EQ", "IQ"}:
+            continue
+        if any(len(p.references) != 1 for p in preds):
+            continue
+        x = [p for p in preds if p.sign == "EQ"][0].references[0]
+        y = [p for p in preds if p.sign == "IQ"][0].references[0]
+        no_cycle = y not in fd.get(x, set()) and x not in fd.get(y, set())
+        if y in target_attrs and no_cycle:
+            fd.setdefault(y, set()).add(x)
+    return {y: sorted(xs) for y, xs in fd.items()}
+
+
+def functional_dep_map(tbl, x, y):
+    """DepGraph.computeFunctionalDepMap (:300-316): x value -> the single y value it occurs with
+    (NULL y ignored by collect_set; the NULL x group is dropped)."""
+    groups = {}
+    for xv, yv in zip(column_values(tbl, x), column_values(tbl, y)):
+        if xv is None:
+            continue
+        g = groups.setdefault(xv, [])
+        if yv is not None and yv not in g:
+            g.append(yv)
+    return {xv: g[0] for xv, g in groups.items() if len(g) == 1}
+
+
+def resolve_prediction_order(models, target_columns):
+    """_resolve_prediction_order (model.py:928-953): statistical models first, then every
+    functional-dependency model once its determinant is no longer waiting for a repair."""
+    by_y = {m[0]: m for m in models}
+    ordered, waiting = [], list(target_columns)
+    for y in target_columns:
+        if "fd" not in by_y[y][1]:
+            ordered.append(by_y[y])
+            waiting.remove(y)
+    while waiting:
+        before = len(waiting)
+        for y in list(waiting):
+            if by_y[y][1]["fd"]["x"] not in waiting:
+                ordered.append(by_y[y])
+                waiting.remove(y)
+        assert len(waiting) < before
+    return ordered
+
+
 def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stats, continuous, opts,
-           model_provider, repair_data=False, pmf_mode=False):
+           model_provider, repair_data=False, pmf_mode=False, rules=None):
     """RepairModel._run phases 2-3 (model.py:1311-1408), default mode.
 
     ``model_provider(ctx) -> spec`` is called once per target that needs a statistical model with
     ctx = {y, features, encoders (fitted categories), X (encoded training matrix), y_values,
     is_discrete, num_class, train_rows};  spec = {"forest": flat forest, "classes": [labels
     ascending] or None}  or  {"const": value}.
+    ``rules`` (setRepairByRules(True)): {"cost_fn", "cost_targets", "nearest_values": bool,
+    "merge_threshold", "functional_deps": bool, "max_domain_size", "constraints": [detector specs]}.
     -> list of (row_id_string, attribute, current_value, repaired)."""
     if not error_cells:
         return []
@@ -255,9 +349,32 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
                          "but no such feature found")
     error_cells = [c for c in error_cells if c[1] in target_columns]  # model.py:1316
     base = convert_error_cells_to_null(tbl, error_cells, target_columns)
+    by_rules = []
+    if rules and rules.get("nearest_values") and rules.get("cost_fn") is not None:  # model.py:1326-1328
+        error_cells, by_rules = repair_by_nearest_values(
+            base, error_cells, target_columns, rules["cost_fn"], rules.get("cost_targets") or [],
+            rules.get("merge_threshold", 2.0))
+        for (r, a, _, v) in by_rules:  # _repair_attrs: the repaired cells join the repair base
+            if base.cols[a].dtype == object or base.kinds[a] == "str":
+                base.cols[a][r] = v
+            else:
+                base.cols[a][r] = float(v)
+    if by_rules and not error_cells:
+        # nothing left for the statistical models (the reference still trains them; their output
+        # would be empty)
+        if repair_data:
+            return base
+        return [(cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r)), a, cur, cast_to_string(tbl.kinds[a], v))
+                for (r, a, cur, v) in by_rules]
     dirty_pos = sorted({c[0] for c in error_cells})
     columns = [c for c in base.names if c != row_id]  # train_df.drop(row_id) (model.py:985)
     integral = {c for c in base.names if base.kinds[c] == "int"}
+    fdeps = None
+    if rules and rules.get("functional_deps"):  # _get_functional_deps (model.py:735-753)
+        ceds = rules.get("constraints") or []
+        if len(ceds) == 1:
+            ct = [c for c in target_columns if c in ceds[0]["targets"]] if ceds[0].get("targets") else target_columns
+            fdeps = functional_deps(columns, ceds[0].get("path", ""), ceds[0].get("constraints", ""), ct)
     models = []
     for y in target_columns:  # model.py:1001-1052
         is_discrete = y not in continuous
@@ -268,6 +385,15 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
             v = next((v for v in y_all if v is not None), None) if num_class == 1 else None
             models.append((y, {"const": v}, input_columns, None))
             continue
+        if fdeps is not None and y in fdeps:  # model.py:1018-1029
+            fx = [x for x in fdeps[y] if int(domain_stats[x]) < int(rules.get("max_domain_size", 1000))]
+            if fx:
+                if base.kinds[y] != "str":
+                    raise NotImplementedError("functional-dependency models only repair string attributes "
+                                              "(the reference's FunctionalDepModel predicts strings)")
+                fmap = functional_dep_map(base, fx[0], y) if base.kinds[fx[0]] == "str" else {}
+                models.append((y, {"fd": {"x": fx[0], "map": fmap}}, [fx[0]], None))
+                continue
         features = select_features(pairwise_stats, y, input_columns, _opt(opts, "model.max_training_column_num"))
         cand = [r for r in range(base.n_rows) if y_all[r] is not None]
         if len(cand) == 0:
@@ -288,6 +414,8 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
                "num_class": num_class, "train_rows": rows}
         spec = model_provider(ctx)
         models.append((y, spec, features, encoders))
+    if any("fd" in m[1] for m in models):
+        models = resolve_prediction_order(models, target_columns)
     # ---- repair UDF (model.py:1096-1135): sequential chain over targets on the dirty rows ----
     dirty = base.take(np.array(dirty_pos, dtype=np.int64))
     for c in dirty.names:  # pmf mode parks JSON strings in repaired cells: needs object columns
@@ -301,16 +429,24 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
             from .forest import forest_proba
             if "const" in spec:
                 classes, probs = [spec["const"]], [[1.0]] * n
+            elif "fd" in spec:  # FunctionalDepModel.predict_proba (model.py:89-100): one-hot or nothing
+                classes = sorted(set(spec["fd"]["map"].values()))
+                xs = column_values(dirty, spec["fd"]["x"])
+                probs = [[1.0 if c == spec["fd"]["map"][xv] else 0.0 for c in classes]
+                         if xv in spec["fd"]["map"] else None for xv in xs]
             else:
                 X = encode_rows(encoders, {f: column_values(dirty, f) for f in features})
                 classes, probs = spec["classes"], forest_proba(spec["forest"], X)
             for i in range(n):
                 if dirty.value(y, i) is None:
-                    pmf_of[(dirty_pos[i], y)] = (classes, list(probs[i]))
+                    pmf_of[(dirty_pos[i], y)] = (classes, list(probs[i])) if probs[i] is not None else ([], [])
                     ycol[i] = UNKNOWN
             continue
         if "const" in spec:
             pred = [spec["const"]] * n
+        elif "fd" in spec:  # FunctionalDepModel.predict (model.py:86-87)
+            pred = [spec["fd"]["map"].get(xv) if xv is not UNKNOWN else None
+                    for xv in column_values(dirty, spec["fd"]["x"])]
         else:
             X = encode_rows(encoders, {f: column_values(dirty, f) for f in features})
             p = forest_predict(spec["forest"], X)
@@ -354,11 +490,13 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
         if rep is None or cur is None or str(cur) != str(rep):  # repaired IS NULL OR NOT(cur <=> repaired)
             rid = cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r))
             out.append((rid, a, cur, rep))
+    for (r, a, cur, v) in by_rules:  # model.py:1403-1404: rule repairs are appended unfiltered
+        out.append((cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r)), a, cur, cast_to_string(tbl.kinds[a], v)))
     return out
 
 
 def run(tbl, row_id, detectors=None, targets=None, discrete_thres=80, given_error_cells=None, opts=None,
-        model_provider=None, detect_errors_only=False, repair_data=False, pmf_mode=False):
+        model_provider=None, detect_errors_only=False, repair_data=False, pmf_mode=False, rules=None):
     """RepairModel.run, default / detect_errors_only / repair_data modes."""
     continuous = S.check_input_table(tbl, row_id)
     targets = targets or []
@@ -370,5 +508,8 @@ def run(tbl, row_id, detectors=None, targets=None, discrete_thres=80, given_erro
         return [(cast_to_string(tbl.kinds[row_id], tbl.value(row_id, r)), a, cur) for (r, a, cur) in cells]
     if not cells:
         return tbl if repair_data else []
+    if rules is not None:
+        rules = dict(rules)
+        rules.setdefault("constraints", [d for d in (detectors or []) if d["type"] == "constraint"])
     return repair(tbl, row_id, cells, target_columns, pairwise, domain_stats, continuous, opts,
-                  model_provider, repair_data=repair_data, pmf_mode=pmf_mode)
+                  model_provider, repair_data=repair_data, pmf_mode=pmf_mode, rules=rules)

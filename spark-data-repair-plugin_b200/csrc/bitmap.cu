@@ -299,6 +299,61 @@ __global__ void __launch_bounds__(kThreads) k_tile_fill(int32_t* __restrict__ ti
         tile[(int64_t)cells[i] * K + col] = value;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_scatter(T* __restrict__ col, const int32_t* __restrict__ rows,
+                                                      const T* __restrict__ vals, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) col[rows[i]] = vals[i];
+}
+
+// tile[cells[i]][y_col] = lut[tile[cells[i]][x_col] + 1]: the functional-dependency model X -> Y
+__global__ void __launch_bounds__(kThreads) k_tile_lut_fill(int32_t* __restrict__ tile, int K, int x_col, int y_col,
+                                                            const int32_t* __restrict__ cells, int64_t n,
+                                                            const int32_t* __restrict__ lut, int32_t lut_size) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t* row = tile + (int64_t)cells[i] * K;
+        const int32_t x = row[x_col];
+        row[y_col] = (x >= -1 && x + 1 < lut_size) ? __ldg(lut + x + 1) : -1;
+    }
+}
+
+// per key x (NULL and masked cells skipped): min / max of the non-NULL, unmasked y codes
+__global__ void __launch_bounds__(kThreads) k_fd_map_build(const int32_t* __restrict__ x_col,
+                                                           const uint32_t* __restrict__ x_mask,
+                                                           const int32_t* __restrict__ y_col,
+                                                           const uint32_t* __restrict__ y_mask, int64_t n_rows,
+                                                           int32_t dom_x, int32_t* __restrict__ lo,
+                                                           int32_t* __restrict__ hi) {
+    extern __shared__ int32_t s_tab[];  // [2][dom_x] when it fits, else straight to global
+    const bool use_smem = dom_x <= 8192;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < dom_x; i += blockDim.x) { s_tab[i] = INT32_MAX; s_tab[dom_x + i] = INT32_MIN; }
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const int32_t x = x_col[r], y = y_col[r];
+        if (x < 0 || y < 0 || x >= dom_x) continue;
+        if (x_mask && (x_mask[r >> 5] >> (r & 31)) & 1u) continue;
+        if (y_mask && (y_mask[r >> 5] >> (r & 31)) & 1u) continue;
+        if (use_smem) {
+            if (y < s_tab[x]) atomicMin(&s_tab[x], y);
+            if (y > s_tab[dom_x + x]) atomicMax(&s_tab[dom_x + x], y);
+        } else {
+            if (y < lo[x]) atomicMin(&lo[x], y);
+            if (y > hi[x]) atomicMax(&hi[x], y);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < dom_x; i += blockDim.x) {
+            if (s_tab[i] != INT32_MAX) atomicMin(&lo[i], s_tab[i]);
+            if (s_tab[dom_x + i] != INT32_MIN) atomicMax(&hi[i], s_tab[dom_x + i]);
+        }
+    }
+}
+
 inline int grid_rows(const dr_ctx* ctx, int64_t n) { return dr_grid_for(ctx, n, kThreads, kCtasPerSm); }
 
 }  // namespace
@@ -562,6 +617,50 @@ int dr_tile_fill_i32(dr_ctx* ctx, int32_t* tile, int n_cols, int col, const int3
     DR_REQUIRE(ctx, tile && cells && col >= 0 && col < n_cols, "bad tile column");
     k_tile_fill<<<grid_rows(ctx, n_cells), kThreads, 0, (cudaStream_t)stream>>>(tile, n_cols, col, cells, n_cells,
                                                                                value);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_scatter_i32(dr_ctx* ctx, int32_t* col, const int32_t* rows, const int32_t* vals, int64_t n, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, col && rows && vals, "null pointer");
+    k_scatter<int32_t><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(col, rows, vals, n);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_scatter_f64(dr_ctx* ctx, double* col, const int32_t* rows, const double* vals, int64_t n, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n <= 0) return DR_OK;
+    DR_REQUIRE(ctx, col && rows && vals, "null pointer");
+    k_scatter<double><<<grid_rows(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(col, rows, vals, n);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_tile_lut_fill(dr_ctx* ctx, int32_t* tile, int n_cols, int x_col, int y_col, const int32_t* cells,
+                     int64_t n_cells, const int32_t* lut, int32_t lut_size, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n_cells <= 0) return DR_OK;
+    DR_REQUIRE(ctx, tile && cells && lut && lut_size >= 1, "null pointer");
+    DR_REQUIRE(ctx, x_col >= 0 && x_col < n_cols && y_col >= 0 && y_col < n_cols && x_col != y_col, "bad tile column");
+    k_tile_lut_fill<<<grid_rows(ctx, n_cells), kThreads, 0, (cudaStream_t)stream>>>(tile, n_cols, x_col, y_col, cells,
+                                                                                   n_cells, lut, lut_size);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_fd_map_build(dr_ctx* ctx, const int32_t* x_col, const uint32_t* x_mask, const int32_t* y_col,
+                    const uint32_t* y_mask, int64_t n_rows, int32_t dom_x, int32_t* lo, int32_t* hi, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n_rows <= 0 || dom_x <= 0) return DR_OK;
+    DR_REQUIRE(ctx, x_col && y_col && lo && hi, "null pointer");
+    const size_t smem = dom_x <= 8192 ? (size_t)dom_x * 2 * sizeof(int32_t) : 0;
+    if (smem > 48 * 1024)
+        DR_CUDA(ctx, cudaFuncSetAttribute(k_fd_map_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fd_map_build<<<grid_rows(ctx, n_rows), kThreads, smem, (cudaStream_t)stream>>>(x_col, x_mask, y_col, y_mask,
+                                                                                     n_rows, dom_x, lo, hi);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

@@ -98,6 +98,12 @@ _SIGNATURES = {
     "dr_gbdt_train": (c_int, [c_void_p, POINTER(dr_gbdt_params), c_void_p, POINTER(c_int32), c_void_p, c_void_p,
                               c_void_p, POINTER(c_double), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dr_tile_fill_i32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int32, c_void_p]),
+    "dr_scatter_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dr_scatter_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dr_fd_map_build": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                c_void_p, c_void_p]),
+    "dr_tile_lut_fill": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int32,
+                                 c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
@@ -321,6 +327,18 @@ class Context:
     def tile_fill(self, tile, n_cols, col, cells, n_cells, value):
         self._check(self.lib.dr_tile_fill_i32(self._h, _dp(tile), n_cols, col, _dp(cells), n_cells, value,
                                               self._stream()))
+
+    def scatter(self, col, rows, vals, n, f64=False):
+        fn = self.lib.dr_scatter_f64 if f64 else self.lib.dr_scatter_i32
+        self._check(fn(self._h, _dp(col), _dp(rows), _dp(vals), n, self._stream()))
+
+    def fd_map_build(self, x_col, x_mask, y_col, y_mask, n_rows, dom_x, lo, hi):
+        self._check(self.lib.dr_fd_map_build(self._h, _dp(x_col), _dp(x_mask), _dp(y_col), _dp(y_mask), n_rows,
+                                             dom_x, _dp(lo), _dp(hi), self._stream()))
+
+    def tile_lut_fill(self, tile, n_cols, x_col, y_col, cells, n_cells, lut, lut_size):
+        self._check(self.lib.dr_tile_lut_fill(self._h, _dp(tile), n_cols, x_col, y_col, _dp(cells), n_cells,
+                                              _dp(lut), lut_size, self._stream()))
 
 
 def _profiled(name, fn):

@@ -18,6 +18,7 @@ import pandas as pd
 from pandas import DataFrame
 
 from . import catalog
+from . import rules as R
 from .costs import UpdateCostFunction
 from .errors import ErrorDetector, ErrorModelOptions, default_detectors
 from .forest import DeviceModel, encode_matrix, encoder_type, first_seen
@@ -271,8 +272,7 @@ class RepairModel():
         validate_options(self.opts)
         for key in _MODEL_OPT:
             self._opt(key)
-        if self.repair_by_rules:
-            raise NotImplementedError("rule-based repairs are not built yet (SURVEY.md 8f)")
+        R.check_supported(self)
 
         from .engine import Engine
         engine = Engine(table, self.device_index)
@@ -388,9 +388,9 @@ def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_value
     return None if forest is None else {"forest": forest, "class_codes": classes}
 
 
-def _train_model(rm, engine, table, res, y, continuous, tile_col):
+def _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps=None):
     """Bookkeeping of _build_repair_models for one target (model.py:1001-1052, 768-815).
-    -> ("const", code or None) | ("forest", DeviceModel, info)"""
+    -> ("const", code or None) | ("fd", x, lut, map) | ("forest", DeviceModel, info)"""
     col = table.by_name[y]
     is_discrete = not col.continuous
     input_columns = [c for c in table.names if c != y]
@@ -408,6 +408,11 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col):
             return ("const", int(present[0]) if num_class == 1 else None)
     else:
         num_class = 0
+    if fdeps is not None and y in fdeps:  # model.py:1018-1029: y follows a clean attribute by rule
+        fx = [x for x in fdeps[y] if int(res.domain_stats[x]) < int(rm._opt("model.rule.max_domain_size"))]
+        if fx:
+            _logger.info("Building model... type=rule(FD: X->y) y={} X={}".format(y, fx[0]))
+            return R.build_fd_model(engine, table, res, fx[0], y)
     features = select_features(res.pairwise_stats, y, input_columns, rm._opt("model.max_training_column_num"))
     rows, n_valid = engine.valid_training_rows(res, y, rm._opt("model.max_training_row_num"))
     if n_valid == 0:
@@ -448,7 +453,11 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col):
 def build_models(rm, engine, table, res, continuous):
     """Training phase: one model per target column, in target order (model.py:1001-1052)."""
     tile_col = {c.name: i for i, c in enumerate(table.columns)}
-    return [(y, _train_model(rm, engine, table, res, y, continuous, tile_col)) for y in res.target_columns]
+    fdeps = R.functional_deps(rm, table, res.target_columns)
+    models = [(y, _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps)) for y in res.target_columns]
+    if any(m[0] == "fd" for _, m in models):
+        models = R.resolve_prediction_order(models, res.target_columns)
+    return models
 
 
 def run_chain(engine, table, models, tile, ctile, D):
@@ -477,6 +486,9 @@ def run_chain(engine, table, models, tile, ctile, D):
         if m[0] == "const":
             if m[1] is not None and not ycol.continuous:
                 engine.ctx.tile_fill(tile, K, tile_col[y], todo, n, int(m[1]))
+            continue
+        if m[0] == "fd":  # FunctionalDepModel.predict (model.py:86-87)
+            engine.ctx.tile_lut_fill(tile, K, tile_col[m[1]], tile_col[y], todo, n, m[2], int(m[2].numel()))
             continue
         m[1].predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
 
@@ -519,6 +531,13 @@ def repair_cells_pmf(rm, engine, table, res, continuous):
             continue
         if m[0] == "const":
             kept[y] = (todo.cpu().numpy(), None, [m[1]])
+        elif m[0] == "fd":  # FunctionalDepModel.predict_proba (model.py:89-100): one-hot, or nothing
+            xs = torch.empty(n, dtype=torch.int32, device=engine.device)
+            engine.ctx.tile_gather(tile, K, tile_col[m[1]], todo, n, xs)
+            pred = torch.empty(n, dtype=torch.int32, device=engine.device)
+            # an x that is itself a parked pmf cell (code = dict size) maps to nothing
+            engine.ctx.gather(m[2][1:], torch.where(xs < int(m[2].numel()) - 1, xs, torch.full_like(xs, -1)), n, pred)
+            kept[y] = (todo.cpu().numpy(), ("onehot", pred.cpu().numpy()), sorted(set(m[3].values())))
         else:
             dm = m[1]
             margins = torch.empty((n, dm.n_seq), dtype=torch.float64, device=engine.device)
@@ -545,6 +564,14 @@ def repair_cells_pmf(rm, engine, table, res, continuous):
             classes = [None if class_codes[0] is None else col.strings()[class_codes[0]]]
             for i in range(len(rows)):
                 out.append((ids[i], a, cur_s[i], classes, [1.0]))
+        elif isinstance(margins_h, tuple):
+            strs = col.strings()
+            classes = [strs[c] for c in class_codes]
+            for i, p in enumerate(margins_h[1][at].tolist()):
+                if p < 0:
+                    out.append((ids[i], a, cur_s[i], [], []))
+                else:
+                    out.append((ids[i], a, cur_s[i], classes, [1.0 if c == p else 0.0 for c in class_codes]))
         else:
             probs = P.probabilities(margins_h[at])
             strs = col.strings()
@@ -621,8 +648,40 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
     cont_idx = engine.dt.cont_index
     if encoded_output and models is not None and not engine.dt.cont_index:
         return repair_cells_encoded(rm, engine, table, res, models)
+    by_rules, undo = [], []
+    if rm._repair_by_nearest_values_enabled:        # model.py:1326-1328
+        by_rules, undo = R.repair_by_nearest_values(rm, engine, table, res)
+    try:
+        return _repair_cells(rm, engine, table, res, continuous, repair_data, models, encoded_output, by_rules)
+    finally:
+        R.restore(engine, undo)
+
+
+def _rule_repairs_frame(table, by_rules):
+    """Cells decided by a rule as output rows: appended unfiltered (model.py:1403-1404)."""
+    ids, attrs, curs, reps = [], [], [], []
+    for a, rows, old, new in by_rules:
+        col = table.by_name[a]
+        ids.append(table.row_ids[rows])
+        attrs += [a] * len(rows)
+        curs += col.decode(old)
+        reps += col.decode(new)
+    return DataFrame({table.row_id: np.concatenate(ids) if ids else [], "attribute": attrs,
+                      "current_value": pd.array(curs, dtype=object), "repaired": pd.array(reps, dtype=object)})
+
+
+def _repair_cells(rm, engine, table, res, continuous, repair_data, models, encoded_output, by_rules):
+    torch = engine.torch
+    targets = res.target_columns
+    K = len(table.columns)
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    cont_idx = engine.dt.cont_index
     cells = engine.cells_of(res, targets)           # (attr, rows, current codes), table order
     if not cells:
+        if by_rules and not repair_data:
+            return _rule_repairs_frame(table, by_rules)
+        if by_rules:
+            return _apply_repairs(rm, table, _rule_cells_for_apply(table, by_rules))
         return rm._input_frame(table) if repair_data else rm._empty_frame(table, repaired=True)
     # models (training phase)
     t0 = time.time()
@@ -675,13 +734,26 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
     if encoded_output:
         return repaired_cells
     if repair_data:
-        return _apply_repairs(rm, table, repaired_cells)
+        return _apply_repairs(rm, table, repaired_cells + _rule_cells_for_apply(table, by_rules))
     frame = DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs,
                        "current_value": pd.array(curs, dtype=object), "repaired": pd.array(reps, dtype=object)})
     # repaired IS NULL OR NOT(current_value <=> repaired)   (model.py:1401)
     cur_a, rep_a = frame["current_value"].to_numpy(dtype=object), frame["repaired"].to_numpy(dtype=object)
     keep = np.array([r is None or c is None or c != r for c, r in zip(cur_a, rep_a)], dtype=bool)
-    return frame[keep].reset_index(drop=True)
+    frame = frame[keep].reset_index(drop=True)
+    if by_rules:
+        frame = pd.concat([frame, _rule_repairs_frame(table, by_rules)], ignore_index=True)
+    return frame
+
+
+def _rule_cells_for_apply(table, by_rules):
+    """(attr, rows, repaired) in the form _apply_repairs takes: codes for discrete attributes, values
+    for numeric ones."""
+    out = []
+    for a, rows, _, new in by_rules:
+        col = table.by_name[a]
+        out.append((a, rows, np.asarray(col.dictionary, dtype=np.float64)[new] if col.continuous else new))
+    return out
 
 
 def _apply_repairs(rm, table, repaired_cells):

@@ -63,9 +63,32 @@ def provider_from_product(rm, table, value_of):
     return provider
 
 
-def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=None, mode="repair", encoded=False):
+def oracle_rules(rules):
+    """parity-test rule settings -> the oracle's `rules` argument."""
+    if not rules:
+        return None
+    from oracle import repair as OR
+    return {"nearest_values": bool(rules.get("nearest")), "cost_targets": list(rules.get("cf_targets", [])),
+            "cost_fn": (lambda a, b: float(OR.levenshtein(a, b))) if rules.get("nearest") else None,
+            "merge_threshold": float(rules.get("threshold", 2.0)), "functional_deps": rules.get("fd", True),
+            "max_domain_size": int(rules.get("max_domain_size", 1000))}
+
+
+def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=None, mode="repair", encoded=False,
+                rules=None):
     from repair import RepairModel
     rm = RepairModel()
+    if rules:
+        from repair.costs import Levenshtein
+        rm.setRepairByRules(True)
+        if rules.get("nearest"):
+            rm.setUpdateCostFunction(Levenshtein(targets=list(rules.get("cf_targets", []))))
+            rm.option("model.rule.repair_by_nearest_values.disabled", "")
+            rm.option("model.rule.merge_threshold", str(rules.get("threshold", 2.0)))
+        if not rules.get("fd", True):
+            rm.option("model.rule.repair_by_functional_deps.disabled", "1")
+        if "max_domain_size" in rules:
+            rm.option("model.rule.max_domain_size", str(rules["max_domain_size"]))
     if encoded:
         rm.setEncodedInput(inp)
     else:
@@ -114,12 +137,13 @@ def frame_tuples(df, row_id):
     return sorted(out, key=lambda t: (t[0], t[1]))
 
 
-def run_both_frame(df, row_id, specs, targets=None, thres=80, opts=None, mode="repair", kinds=None):
+def run_both_frame(df, row_id, specs, targets=None, thres=80, opts=None, mode="repair", kinds=None, rules=None,
+                   given=None):
     """pandas input: product through RepairModel, oracle through oracle.repair.run."""
     from oracle import repair as OR
     from oracle.table import from_pandas
     from repair.table import EncodedTable
-    rm, out = run_product(df, row_id, specs, targets, thres, opts, mode=mode)
+    rm, out = run_product(df, row_id, specs, targets, thres, opts, given=given, mode=mode, rules=rules)
     got = frame_tuples(out, row_id)
     otbl = from_pandas(df)
     enc = EncodedTable.from_pandas(df, row_id)
@@ -133,7 +157,9 @@ def run_both_frame(df, row_id, specs, targets=None, thres=80, opts=None, mode="r
 
     provider = provider_from_product(rm, enc, value_of) if mode == "repair" else None
     o_opts = {k: v for k, v in (opts or {}).items() if k.startswith("error.") or k in OR.DEFAULT_OPTS}
-    want = OR.run(otbl, row_id, specs, targets, thres, None, o_opts, provider, detect_errors_only=(mode == "detect"))
+    o_given = None if given is None else [tuple(x) for x in given[[row_id, "attribute"]].itertuples(index=False)]
+    want = OR.run(otbl, row_id, specs, targets, thres, o_given, o_opts, provider,
+                  detect_errors_only=(mode == "detect"), rules=oracle_rules(rules))
     want = sorted([tuple(w) for w in want], key=lambda t: (t[0], t[1]))
     return got, want, {"gpu_launches": rm.last_run.get("gpu_launches", 0), "rm": rm}
 

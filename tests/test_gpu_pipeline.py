@@ -238,3 +238,65 @@ def test_pmf_mixed_types_schema():
     got, want = PU.run_both_pmf(df, "tid", [{"type": "null"}], "pmf", opts=dict(FAST))
     assert got == want
     assert sorted((g[0], g[1]) for g in got) == [("10", "v1"), ("14", "v4"), ("3", "v3"), ("7", "v2")]
+
+
+# ---- rule-based repairs (setRepairByRules) --------------------------------------------------------
+def test_repair_by_functional_deps_reference_kat(tmp_path):
+    # tests/test_model.py:892-927: y follows x by the constraint; no statistical model is involved
+    df = pd.DataFrame({"tid": [1, 2, 3, 4, 5, 6], "x": ["1", "2", "1", "2", "2", "3"],
+                       "y": ["test-1", "test-2", None, "test-2", None, None]})
+    path = str(tmp_path / "c.txt")
+    with open(path, "w") as f:
+        f.write("t1&t2&EQ(t1.x,t2.x)&IQ(t1.y,t2.y)")
+    specs = [{"type": "null"}, {"type": "constraint", "path": path}]
+    given = pd.DataFrame({"tid": [3, 5, 6], "attribute": ["y", "y", "y"]})
+    got, want, info = PU.run_both_frame(df, "tid", specs, given=given, rules={"fd": True})
+    assert got == want == [("3", "y", None, "test-1"), ("5", "y", None, "test-2"), ("6", "y", None, None)]
+    assert info["gpu_launches"] > 0
+
+
+def test_repair_by_nearest_values_reference_kat():
+    # tests/test_model.py:929-973
+    df = pd.DataFrame({"tid": [1, 3, 4, 5, 6], "v0": ["100%", "32%", "1xx%", "100x", "12x"],
+                       "v1": [100, 101, 1, 2, 300], "v2": ["a", "b", "a", "b", "a"], "v3": [1.0, 1.1, 1.3, 0.6, 0.8]})
+    given = pd.DataFrame({"tid": [4, 5, 6, 3, 5, 6, 5], "attribute": ["v0", "v0", "v0", "v1", "v1", "v1", "v2"]})
+    rules = {"nearest": True, "cf_targets": ["v0", "v1"], "threshold": 2.0}
+    kat = [("3", "v1", "101", "100"), ("4", "v0", "1xx%", "100%"), ("5", "v0", "100x", "100%"),
+           ("5", "v1", "2", "1"), ("6", "v0", "12x", "32%"), ("6", "v1", "300", "100")]
+    got, want, _ = PU.run_both_frame(df, "tid", [], targets=["v0", "v1"], given=given, rules=rules)
+    assert got == want == kat
+    # (5, v2) is left to the statistical model (the reference's golden says 'a')
+    got, want, _ = PU.run_both_frame(df, "tid", [], given=given, rules=rules, opts=FAST)
+    assert got == want
+    assert [g for g in got if g[1] != "v2"] == kat and [g[:3] for g in got if g[1] == "v2"] == [("5", "v2", "b")]
+    # repair_data: rule repairs and model repairs both land in the table
+    rm, out = PU.run_product(df, "tid", [], given=given, rules=rules, opts=FAST, mode="repair_data")
+    assert out["v0"].tolist() == ["100%", "32%", "100%", "100%", "32%"] and out["v1"].tolist() == [100, 100, 1, 1, 100]
+    # nearest values cannot be combined with the pmf modes (model.py:1501-1507)
+    with pytest.raises(ValueError, match="Cannot repair data by nearest values"):
+        PU.run_product(df, "tid", [], given=given, rules=rules, mode="pmf")
+
+
+def test_hospital_rule_based_repair_parity():
+    # the reference's best hospital configuration turns the rules on (tests/test_model_perf.py:296-309)
+    specs = [{"type": "null"}, {"type": "constraint", "path": os.path.join(GOLDEN, "hospital_constraints.txt")}]
+    opts = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": 5}
+    targets = ["City", "State", "ZipCode", "EmergencyService", "HospitalType", "CountyName"]
+    rules = {"nearest": True, "threshold": 2.0, "fd": True}
+    got, want, info = PU.run_both_frame(hospital(), "tid", specs, opts=opts, targets=targets, rules=rules)
+    assert got == want
+    kinds = {m[0] for _, m in info["rm"].last_run["models"]}
+    assert "fd" in kinds and len(got) > 100
+
+
+def test_rule_based_pmf_with_fd_model():
+    # FunctionalDepModel.predict_proba (model.py:89-100): one-hot for a known determinant, nothing otherwise
+    df = pd.DataFrame({"tid": list(range(1, 13)), "x": ["1", "2", "1", "2", "2", "3"] * 2,
+                       "y": ["p", "q", None, "q", None, None] * 2, "z": ["a", "b", "a", "b", "b", "a"] * 2})
+    specs = [{"type": "null"}, {"type": "constraint", "constraints": "x->y"}]
+    given = pd.DataFrame({"tid": [3, 5, 6, 9, 11, 12], "attribute": ["y"] * 6})
+    rm, out = PU.run_product(df, "tid", specs, given=given, rules={"fd": True}, mode="prob")
+    none = lambda v: None if v is None or v != v else v  # noqa: E731
+    got = sorted((int(r["tid"]), r["attribute"], none(r["repaired"]), none(r["prob"])) for r in out.to_dict("records"))
+    assert got == [(3, "y", "p", 1.0), (5, "y", "q", 1.0), (6, "y", None, None), (9, "y", "p", 1.0),
+                   (11, "y", "q", 1.0), (12, "y", None, None)]

@@ -498,3 +498,70 @@ def test_hospital_constraint_cell_count():
                                os.path.join(GOLDEN, "hospital_constraints.txt"), "")
     assert len(cells) == 11038
     assert len(D.null_cells(t, "tid", t.names)) == 2227
+
+
+# ------------------------------------------------------------------ rule-based repairs
+def test_functional_deps_hospital():
+    # DepGraphSuite.scala:230-266
+    t = from_csv(os.path.join(GOLDEN, "hospital.csv"))
+    path = os.path.join(GOLDEN, "hospital_constraints.txt")
+    attrs = [c for c in t.names if c != "tid"]
+    targets = ["HospitalOwner", "Condition", "CountyName", "HospitalName", "EmergencyService", "ZipCode", "MeasureCode"]
+    assert R.functional_deps(attrs, path, "City->ZipCode", targets) == {
+        "HospitalOwner": ["HospitalName"], "Condition": ["MeasureCode"], "CountyName": ["City"],
+        "HospitalName": ["ProviderNumber"], "EmergencyService": ["ZipCode"], "ZipCode": ["City", "HospitalName"],
+        "MeasureCode": ["MeasureName"]}
+    assert R.functional_deps(attrs, path, "City->ZipCode", ["CountyName", "HospitalName", "ZipCode"]) == {
+        "ZipCode": ["City", "HospitalName"], "CountyName": ["City"], "HospitalName": ["ProviderNumber"]}
+
+
+def test_functional_dep_map():
+    # DepGraphSuite.scala:268-289
+    t = from_rows(["tid", "x", "y"], [(1, "1", "test-1"), (2, "2", "test-2"), (3, "3", "test-3"), (4, "2", "test-2"),
+                                      (5, "1", "test-1"), (6, "1", "test-1"), (7, "3", "test-3"), (8, "3", "test-3"),
+                                      (9, "2", "test-2a")])
+    assert R.functional_dep_map(t, "x", "y") == {"3": "test-3", "1": "test-1"}
+
+
+def test_repair_by_functional_deps(tmp_path):
+    # tests/test_model.py:892-927
+    t = from_rows(["tid", "x", "y"], [(1, "1", "test-1"), (2, "2", "test-2"), (3, "1", None), (4, "2", "test-2"),
+                                      (5, "2", None), (6, "3", None)])
+    path = str(tmp_path / "c.txt")
+    with open(path, "w") as f:
+        f.write("t1&t2&EQ(t1.x,t2.x)&IQ(t1.y,t2.y)")
+    dets = [{"type": "null"}, {"type": "constraint", "path": path}]
+    rules = {"functional_deps": True, "max_domain_size": 1000}
+    out = R.run(t, "tid", dets, given_error_cells=[(3, "y"), (5, "y"), (6, "y")], rules=rules,
+                model_provider=lambda ctx: pytest.fail("no statistical model is needed"))
+    assert sorted(out) == [("3", "y", None, "test-1"), ("5", "y", None, "test-2"), ("6", "y", None, None)]
+
+
+def test_repair_by_nearest_values():
+    # tests/test_model.py:929-973 (second run: every cell of v0 / v1 is decided by the rule)
+    t = from_rows(["tid", "v0", "v1", "v2", "v3"], [(1, "100%", 100, "a", 1.0), (3, "32%", 101, "b", 1.1),
+                                                    (4, "1xx%", 1, "a", 1.3), (5, "100x", 2, "b", 0.6),
+                                                    (6, "12x", 300, "a", 0.8)])
+    cells = [(4, "v0"), (5, "v0"), (6, "v0"), (3, "v1"), (5, "v1"), (6, "v1"), (5, "v2")]
+    rules = {"nearest_values": True, "cost_fn": lambda a, b: float(R.levenshtein(a, b)), "cost_targets": ["v0", "v1"],
+             "merge_threshold": 2.0, "functional_deps": True}
+    want = [("3", "v1", "101", "100"), ("4", "v0", "1xx%", "100%"), ("5", "v0", "100x", "100%"),
+            ("5", "v1", "2", "1"), ("6", "v0", "12x", "32%"), ("6", "v1", "300", "100")]
+    out = R.run(t, "tid", [], targets=["v0", "v1"], given_error_cells=cells, rules=rules,
+                model_provider=lambda ctx: pytest.fail("no statistical model is needed"))
+    assert sorted(out) == want
+    # first run: (5, v2) is left to the statistical model, everything else is the same
+    seen = []
+
+    def provider(ctx):
+        seen.append(ctx["y"])
+        return {"const": "a"}
+
+    out = R.run(t, "tid", [], given_error_cells=cells, rules=rules, model_provider=provider)
+    assert sorted(out) == sorted(want + [("5", "v2", "b", "a")]) and "v2" in seen
+
+
+def test_rule_based_prediction_order():
+    # model.py:928-953: statistical models first, then FD models whose determinant is settled
+    models = [("a", {"fd": {"x": "b"}}), ("b", {"fd": {"x": "c"}}), ("c", {"forest": 1}), ("d", {"fd": {"x": "z"}})]
+    assert [m[0] for m in R.resolve_prediction_order(models, ["a", "b", "c", "d"])] == ["c", "b", "d", "a"]
