@@ -16,20 +16,17 @@
 
 namespace {
 
-// Two feature-tile layouts:
-//  * wide   (512 cells / CTA, 1 CTA / SM): one 32-bit word per rank byte, [feature byte][thread].  Lane
-//           L of a warp always reads bank L, whatever feature its node tests: the rank load is ONE
-//           shared-memory wavefront (the byte layout needs ~3 once the lanes of a warp have spread
-//           over different nodes).  Needs 2 * n_feat * 2 KB of shared memory: up to 37 features.
+// The kernel runs at ~92 % of the shared-memory pipe (ncu: 0.92 wavefronts / cycle / SM), so what
+// counts is wavefronts per level.  Two feature-tile layouts:
+//  * wide   (1 CTA / SM): one 32-bit word per rank byte, [feature byte][thread].  Lane L of a warp
+//           always reads bank L, whatever feature its node tests: the rank load is ONE wavefront (the
+//           byte layout measures 1.96 once the lanes of a warp have spread over different nodes).
+//           512 cells / CTA when 2 * n_feat * 2 KB fits beside the chunk buffers (<= 37 features),
+//           else 256 cells / CTA (<= 75 features), then with more trees in flight per thread.
 //  * bytes  (256 cells / CTA, 2 CTAs / SM): [thread][feature byte], odd word stride.
-constexpr int kWideThreads = 512;
 constexpr int kByteThreads = 256;
 constexpr int kChunkNodes = DR_RANKED_CHUNK_NODES;
 constexpr int kChunkLeaves = DR_RANKED_CHUNK_LEAVES;
-#ifndef DR_FOREST_ILP
-#define DR_FOREST_ILP 8
-#endif
-constexpr int kIlp = DR_FOREST_ILP;  // trees walked concurrently per thread
 
 struct RankedParams {
     dr_forest_ranked f;
@@ -71,11 +68,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // One level: two shared-memory loads (rank byte, next node word), one add and one byte extract.
-template <bool kWide>
+template <bool kWide, int T>
 __device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, uint32_t w,
                                               const unsigned char* __restrict__ my_feat) {
     uint32_t r;
-    if (kWide) r = *reinterpret_cast<const uint32_t*>(my_feat + (w >> 24) * (kWideThreads * 4));
+    if (kWide) r = *reinterpret_cast<const uint32_t*>(my_feat + (w >> 24) * (T * 4));
     else       r = my_feat[w >> 24];
     const uint32_t w2 = w + r;                          // carries into bit 8 iff rank >= threshold
     return nodes[__byte_perm(w2, 0, 0x4421)];           // bits 8..23: left child (+1 = right child)
@@ -89,10 +86,9 @@ struct __align__(16) ChunkBuf {
     uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, first leaf), chunk relative
 };
 
-template <bool kWide>
-__global__ void __launch_bounds__(kWide ? kWideThreads : kByteThreads, kWide ? 1 : 2)
+template <bool kWide, int T, int kIlp>
+__global__ void __launch_bounds__(T, kWide ? 1 : 2)
 k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
-    constexpr int T = kWide ? kWideThreads : kByteThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const dr_forest_ranked& F = p.f;
     ChunkBuf* buf = reinterpret_cast<ChunkBuf*>(smem_raw);                       // two chunk buffers
@@ -178,7 +174,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 }
                 for (int d = 0; d < depth; ++d) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide>(nodes, w[j], my_feat);
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
                 }
                 if (q + kIlp <= n_trees) {
 #pragma unroll
@@ -233,18 +229,26 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     // padded by 256 bytes for that, the wide tile is only used when every leaf number is a valid slot
     const size_t fixed = 2 * sizeof(ChunkBuf) + 16;
     const int n_slots = 2 * f.n_feat > 0 ? 2 * f.n_feat : 1;
-    const size_t smem_wide = fixed + (size_t)n_slots * kWideThreads * 4;
     DR_REQUIRE(ctx, f.max_tree_leaves >= 1 && f.max_tree_leaves <= 256, "bad max_tree_leaves");
-    DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 2, "bad layout");
-    const bool wide_ok = smem_wide <= 220 * 1024 && f.max_tree_leaves <= n_slots;
-    if (f.layout == 2 && !wide_ok)
+    DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 3, "bad layout");
+    const size_t smem_512 = fixed + (size_t)n_slots * 512 * 4, smem_256 = fixed + (size_t)n_slots * 256 * 4;
+    const bool leaves_ok = f.max_tree_leaves <= n_slots;
+    const bool wide_ok = leaves_ok && smem_256 <= 220 * 1024;
+    if (f.layout >= 2 && !wide_ok)
         return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide feature tile does not fit a forest with %d features", f.n_feat);
+    auto launch = [&](auto kernel, int threads, size_t smem, int per_sm) -> int {
+        DR_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = dr_grid_for(ctx, n_cells, threads, per_sm);
+        kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
+        return DR_OK;
+    };
     if (wide_ok && f.layout != 1) {
         p.feat_stride = 0;
-        DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem_wide));
-        const int grid = dr_grid_for(ctx, n_cells, kWideThreads, 1);
-        k_forest_predict_ranked<true><<<grid, kWideThreads, smem_wide, (cudaStream_t)stream>>>(p);
+        int rc;
+        if (smem_512 <= 220 * 1024) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
+        else if (f.layout == 2)     rc = launch(k_forest_predict_ranked<true, 256, 8>, 256, smem_256, 1);
+        else                        rc = launch(k_forest_predict_ranked<true, 256, 16>, 256, smem_256, 1);
+        if (rc != DR_OK) return rc;
     } else {
         int words = (2 * f.n_feat + 3) / 4;
         if (words < 1) words = 1;
@@ -253,11 +257,9 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
         const size_t smem = fixed + (size_t)kByteThreads * p.feat_stride + 256;
         if (smem > 200 * 1024)
             return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d features exceeds shared memory", f.n_feat);
-        DR_CUDA(ctx, cudaFuncSetAttribute(k_forest_predict_ranked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-        const int grid = dr_grid_for(ctx, n_cells, kByteThreads, per_sm);
-        k_forest_predict_ranked<false><<<grid, kByteThreads, smem, (cudaStream_t)stream>>>(p);
+        const int rc = launch(k_forest_predict_ranked<false, kByteThreads, 8>, kByteThreads, smem,
+                              smem <= 110 * 1024 ? 2 : 1);
+        if (rc != DR_OK) return rc;
     }
     DR_LAUNCHED(ctx);
     return DR_OK;

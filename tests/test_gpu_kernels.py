@@ -399,14 +399,17 @@ def test_domain_score_matches_oracle(ctx):
             assert bool(wk[i]) == ((r, "t") in weak_want)
 
 
-@pytest.mark.parametrize("n_classes,n_iter,n", [(2, 9, 300), (5, 33, 2000), (64, 300, 1500)])
-def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter, n):
-    """All-discrete model: rank-coded kernel == generic kernel == oracle, margins bit-exact."""
+@pytest.mark.parametrize("n_classes,n_iter,n,extra", [(2, 9, 300, []), (5, 33, 2000, []), (64, 300, 1500, []),
+                                                        (3, 40, 3000, [11, 10, 9, 8, 7])])
+def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter, n, extra):
+    """All-discrete model: rank-coded kernel == generic kernel == oracle, margins bit-exact.
+    `extra` attributes push the feature count past what the 512-cell wide tile holds, so that the
+    256-cell wide kernels run."""
     from oracle.forest import forest_margins, forest_predict
     from repair.forest import DeviceModel, encode_matrix, encoder_width
     from repair.train import random_forest
     rng = np.random.default_rng(n_classes + n)
-    doms = [7, 4, 30, 3, 9, 64, 2, 12]
+    doms = [7, 4, 30, 3, 9, 64, 2, 12] + extra
     k = len(doms)
     tile_np = np.stack(rand_cols(rng, n, doms, null_p=0.08), axis=1).astype(np.int32)
     names = ["a%d" % i for i in range(k)]
@@ -432,8 +435,9 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
     X = encode_matrix(encoders, {nm: tile_np[cells, tile_cols[nm]] for nm in names[1:]}, {}, dict_sizes)
     want_m, want = forest_margins(forest, X), forest_predict(forest, X)
     assert dm.ranked.max_tree_leaves <= 2 * n_feat          # so that the wide feature tile is exercised too
-    for variant in ("auto", "bytes", "wide", "generic"):
-        dm.ranked.layout = {"auto": 0, "bytes": 1, "wide": 2, "generic": 0}[variant]
+    assert (n_feat > 37) == bool(extra) and n_feat <= 75
+    for variant in ("auto", "bytes", "wide8", "wide16", "generic"):
+        dm.ranked.layout = {"auto": 0, "bytes": 1, "wide8": 2, "wide16": 3, "generic": 0}[variant]
         tile = dev(tile_np)
         margins = torch.empty((len(cells), dm.n_seq), dtype=torch.float64, device="cuda")
         dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=variant == "generic")
