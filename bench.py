@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-calls", action="store_true", help="print the per-call timing table to stderr")
+    ap.add_argument("--trace", action="store_true",
+                    help="one extra step with device-synchronised split points of the repair phase on stderr")
     return ap.parse_args()
 
 
@@ -398,6 +400,13 @@ def b200_arm(args):
     if args.profile_calls and rank == 0:
         for kname, v in kernels.items():
             print(kname, v, file=sys.stderr)
+    if args.trace:
+        engine.trace = []
+        step(False)
+        if rank == 0:
+            for label, dt_s in engine.trace:
+                print("trace %-24s %8.2f ms" % (label, dt_s * 1e3), file=sys.stderr)
+        engine.trace = None
 
     # ---- end to end: host buffers in, host frame out, every step --------------------------------
     if host is not None:

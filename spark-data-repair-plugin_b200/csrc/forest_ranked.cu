@@ -228,12 +228,13 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     // a leaf's self-loop reads (and ignores) the rank slot named by its leaf number: the byte tile is
     // padded by 256 bytes for that, the wide tile is only used when every leaf number is a valid slot
     const size_t fixed = 2 * sizeof(ChunkBuf) + 16;
+    constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
     const int n_slots = 2 * f.n_feat > 0 ? 2 * f.n_feat : 1;
     DR_REQUIRE(ctx, f.max_tree_leaves >= 1 && f.max_tree_leaves <= 256, "bad max_tree_leaves");
     DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 3, "bad layout");
     const size_t smem_512 = fixed + (size_t)n_slots * 512 * 4, smem_256 = fixed + (size_t)n_slots * 256 * 4;
     const bool leaves_ok = f.max_tree_leaves <= n_slots;
-    const bool wide_ok = leaves_ok && smem_256 <= 220 * 1024;
+    const bool wide_ok = leaves_ok && smem_256 <= kMaxSmem;
     if (f.layout >= 2 && !wide_ok)
         return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide feature tile does not fit a forest with %d features", f.n_feat);
     auto launch = [&](auto kernel, int threads, size_t smem, int per_sm) -> int {
@@ -245,7 +246,7 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (wide_ok && f.layout != 1) {
         p.feat_stride = 0;
         int rc;
-        if (smem_512 <= 220 * 1024) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
+        if (smem_512 <= kMaxSmem) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
         else if (f.layout == 2)     rc = launch(k_forest_predict_ranked<true, 256, 8>, 256, smem_256, 1);
         else                        rc = launch(k_forest_predict_ranked<true, 256, 16>, 256, smem_256, 1);
         if (rc != DR_OK) return rc;

@@ -9,6 +9,8 @@ and model bookkeeping.
 import logging
 import re
 
+import time
+
 import numpy as np
 
 from . import constraints as DC
@@ -70,6 +72,7 @@ class Engine:
         self.disc_cols = {}      # attr -> device int32 column of the discretised table
         self.disc_dom = {}       # attr -> domain size of that column
         self.timings = {}
+        self.trace = None        # list of (label, seconds since the previous mark) when tracing
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -84,6 +87,15 @@ class Engine:
             buf = self.torch.empty(int(n * 1.25) + 1024, dtype=self.torch.int32, pin_memory=True)
             self._pinned = buf
         return buf[:n]
+
+    def mark(self, label):
+        """Tracing aid (bench.py --trace): device-synchronised wall-clock split points."""
+        if self.trace is None:
+            return
+        self.torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.trace.append((label, now - getattr(self, "_t_mark", now)))
+        self._t_mark = now
 
     def new_bitmap(self):
         return self.torch.zeros(self.n_words, dtype=self.torch.int32, device=self.device)

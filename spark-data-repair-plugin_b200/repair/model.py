@@ -473,6 +473,7 @@ def run_chain(engine, table, models, tile, ctile, D):
     # NULL cells of every discrete column in one pass (a model only fills its own column)
     all_null = torch.zeros((K, words), dtype=torch.int32, device=engine.device)
     engine.ctx.tile_null_bitmaps(tile, D, K, words, all_null)
+    engine.mark("chain:null bitmaps")
     for y, m in models:
         ycol = table.by_name[y]
         if ycol.continuous:
@@ -481,6 +482,7 @@ def run_chain(engine, table, models, tile, ctile, D):
         else:
             todo = engine.bitmap_rows(all_null[tile_col[y]], D)
         n = int(todo.numel())
+        engine.mark("chain:cells of " + y)
         if n == 0:
             continue
         if m[0] == "const":
@@ -491,6 +493,7 @@ def run_chain(engine, table, models, tile, ctile, D):
             engine.ctx.tile_lut_fill(tile, K, tile_col[m[1]], tile_col[y], todo, n, m[2], int(m[2].numel()))
             continue
         m[1].predict(engine.ctx, tile, K, ctile, n_cc, todo, n, cont_idx[y] if ycol.continuous else tile_col[y])
+        engine.mark("chain:predict " + y)
 
 
 def repair_cells_pmf(rm, engine, table, res, continuous):
@@ -595,6 +598,7 @@ def repair_cells_encoded(rm, engine, table, res, models):
     if E == 0:
         rm.last_run["n_dirty_rows"] = 0
         return []
+    engine.mark("repair:start")
     rows_all = torch.empty(E, dtype=torch.int32, device=engine.device)
     cur_all = torch.empty(E, dtype=torch.int32, device=engine.device)
     rep_all = torch.empty(E, dtype=torch.int32, device=engine.device)
@@ -605,10 +609,13 @@ def repair_cells_encoded(rm, engine, table, res, models):
         engine.ctx.gather(engine.dt.col(a), rows, n, cur_all[off:off + n])
         seg.append((a, off, n))
         off += n
+    engine.mark("repair:cell lists")
     drows, tile, ctile = engine.build_dirty_tile(res, targets)
     D = int(drows.numel())
     rm.last_run["n_dirty_rows"] = D
+    engine.mark("repair:dirty tile")
     run_chain(engine, table, [(y, m) for y, m in models if y in targets], tile, ctile, D)
+    engine.mark("repair:chain")
     dpos = torch.empty(E, dtype=torch.int32, device=engine.device)
     engine.ctx.lookup_sorted(drows, D, rows_all, E, dpos)
     for a, o, n in seg:
@@ -624,8 +631,10 @@ def repair_cells_encoded(rm, engine, table, res, models):
         engine.ctx.gather(rows_all, idx, n_keep, packed[1])
         engine.ctx.gather(cur_all, idx, n_keep, packed[2])
         engine.ctx.gather(rep_all, idx, n_keep, packed[3])
+    engine.mark("repair:collect")
     host.copy_(packed, non_blocking=True)
     torch.cuda.current_stream().synchronize()
+    engine.mark("repair:d2h")
     h = host.numpy()
     out = []
     bounds = np.searchsorted(h[0, :n_keep], [o for _, o, _ in seg] + [E])

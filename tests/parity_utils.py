@@ -39,7 +39,7 @@ def _nan_equal(a, b):
 def provider_from_product(rm, table, value_of):
     """Oracle model_provider that hands back the product's forests and cross-checks the training
     bookkeeping both sides derived independently (features, encoders, encoded sample)."""
-    models = dict(rm.last_run["models"])
+    models = dict(rm.last_run.get("models", []))  # no models when the rules decided every cell
 
     def provider(ctx):
         m = models[ctx["y"]]
