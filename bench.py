@@ -382,20 +382,53 @@ def b200_arm(args):
     dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
     line["kernels"] = kernels
     fp = [v for kname, v in prof.items() if kname.startswith("forest_predict")]
+    ncu = {}
+    try:  # per-launch figures taken from ncu --set full captures of this very command (profiles/)
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_per_launch.json")))
+    except Exception:
+        pass
+
+    def ncu_for(kernel):
+        e = ncu.get(kernel)
+        ok = e and e.get("rows_per_gpu") == n and e.get("cols") == k
+        return e if ok else None
     if fp:
-        # forest inference is bounded by dependent shared-memory look-ups, not HBM: report tree levels walked
+        # forest inference is bounded by the shared-memory pipe, not HBM (profiles/r1_ncu_forest_*.md): the
+        # roofline that explains it counts shared-memory wavefronts.  Algorithmic minimum per warp: two
+        # loads per tree level (rank byte, node word) + per tree one header broadcast and a 64-bit leaf
+        # value (two wavefronts); peak = one wavefront per cycle per SM.
+        f_ms = sum(v[1] for v in fp)
         levels = sum((m[1].n_trees * (m[1].ranked.max_depth if m[1].ranked is not None else 5)) *
                      res_cells.get(y, 0) for y, m in models if m[0] == "forest")
-        line["forest_tree_levels_per_sec"] = levels / (sum(v[1] for v in fp) / 1e3)
+        tree_cells = sum(m[1].n_trees * res_cells.get(y, 0) for y, m in models if m[0] == "forest")
+        line["forest_tree_levels_per_sec"] = levels / (f_ms / 1e3)
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        sm_count = torch.cuda.get_device_properties(device).multi_processor_count
+        wf = (2.0 * levels + 3.0 * tree_cells) / 32.0
+        e = ncu_for("k_forest_predict_ranked")
+        line["roofline_forest"] = {
+            "kernel": "k_forest_predict_ranked", "bound": "shared-memory wavefronts",
+            "achieved": wf / (f_ms / 1e3) / 1e9, "peak": sm_count * sm_hz / 1e9, "unit": "Gwavefront/s",
+            "frac": wf / (f_ms / 1e3) / (sm_count * sm_hz),
+            "measured_pipe_utilisation": e.get("smem_wavefronts_per_cycle_per_sm") if e else None,
+            "note": "achieved = algorithmic wavefronts (2 per warp-level + 3 per warp-tree) / kernel time; "
+                    "measured_pipe_utilisation counts bank-conflict replays too (ncu)"}
     if dominant:
         d = kernels[dominant]
         ach = d.get("achieved_gbs")
+        e = ncu_for("k_" + dominant)
         line["roofline"] = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src}
+                            "frac": (ach / peak) if ach else None,
+                            "traffic": e.get("dram_bytes_per_launch") if e else None, "peak_source": peak_src,
+                            "note": "this kernel is not HBM bound, see roofline_forest; the HBM-bound kernel of "
+                                    "the path is k_scan_hist (roofline_scan)"
+                            if dominant.startswith("forest_predict") else None}
     sh = kernels.get("scan_hist")
     if sh:
+        e = ncu_for("k_scan_hist")
         line["roofline_scan"] = {"kernel": "k_scan_hist", "bound": "hbm", "achieved": sh.get("achieved_gbs"),
-                                 "peak": peak, "unit": "GB/s", "frac": sh.get("frac_of_hbm_peak"), "traffic": None,
+                                 "peak": peak, "unit": "GB/s", "frac": sh.get("frac_of_hbm_peak"),
+                                 "traffic": e.get("dram_bytes_per_launch") if e else None,
                                  "peak_source": peak_src}
     if args.profile_calls and rank == 0:
         for kname, v in kernels.items():
