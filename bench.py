@@ -172,33 +172,38 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md): ONE
+    `nvidia-smi -lms 200` process started before the region and stopped after it (spawning a process per
+    sample from a parent with GBs of pinned memory stalls the launching thread for tens of ms)."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
+    def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
             "clocks_event_reasons.sw_power_cap"
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 7:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
                                    r[3:7]):
@@ -290,11 +295,14 @@ def b200_arm(args):
         if e2e:
             stage.copy_(host, non_blocking=True)
             engine.ctx.widen_u8(stage, stage.numel(), dt.codes)
+        engine.mark("step:begin")
         engine.reset()
         r = engine.detect(specs, [], 80, err_opts)
         ev[1].record()
+        engine.mark("step:detect")
         out = repair_cells(rm, engine, table, r, continuous, models=models, encoded_output=True)
         ev[2].record()
+        engine.mark("step:repair returned")
         for a_, n_ in r.n_cells.items():
             res_cells[a_] = n_
         stats["cells"] = rm.last_run["n_error_cells"]
@@ -311,11 +319,12 @@ def b200_arm(args):
     def timed(e2e, steps, warmup):
         for _ in range(warmup):
             step(e2e)
-        barrier()
-        l0 = engine.ctx.launch_count
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
+            time.sleep(0.3)  # let nvidia-smi finish initialising before the timed region starts
+        barrier()
+        l0 = engine.ctx.launch_count
         evs = [step(e2e) for _ in range(steps)]
         barrier()
         clocks = sampler.stop() if sampler else None

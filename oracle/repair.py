@@ -7,6 +7,8 @@ Restates ``errors.py:389-461,545-582`` (detection pipeline), ``RepairApi.scala:6
 ``:1398-1401`` (output shaping).  Model *training* is delegated to a ``model_provider`` callback
 (the reference delegates it to LightGBM, ``train.py:89-229``).
 """
+import re
+
 import numpy as np
 
 from . import detect as D
@@ -279,6 +281,27 @@ def repair_by_nearest_values(base, error_cells, target_columns, cost_fn, cost_ta
     return remaining, repaired
 
 
+def repair_by_regexs(error_cells, regexs):
+    """_repair_by_regexs (model.py:633-651) over RepairApi.repairByRegularExpression (:677-706): the
+    error cells of `attr` whose current value can be rebuilt from the detector's regex take the
+    rebuilt value; a regex the lexer rejects repairs nothing.
+    -> (remaining error cells, [(row, attr, current_value, repaired string)])"""
+    from .regex_repair import RegexStructureRepair
+    done = {}
+    for attr, regex in regexs:
+        try:
+            fix = RegexStructureRepair(regex)
+        except (ValueError, re.error):  # lexer error / uncompilable pattern: logged, nothing repaired
+            continue
+        for (r, a, cur) in error_cells:
+            if a == attr and (r, a) not in done:
+                rep = fix(cur)
+                if rep is not None:
+                    done[(r, a)] = (r, a, cur, rep)
+    remaining = [c for c in error_cells if (c[0], c[1]) not in done]
+    return remaining, list(done.values())
+
+
 def functional_deps(table_attrs, constraint_path, constraints, target_attrs):
     """DepGraph.computeFunctionalDeps (:257-298): {y: sorted [x]} for every constraint made of exactly
     one EQ and one IQ predicate over a single attribute each, in statement order, skipping a
@@ -340,7 +363,8 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
     is_discrete, num_class, train_rows};  spec = {"forest": flat forest, "classes": [labels
     ascending] or None}  or  {"const": value}.
     ``rules`` (setRepairByRules(True)): {"cost_fn", "cost_targets", "nearest_values": bool,
-    "merge_threshold", "functional_deps": bool, "max_domain_size", "constraints": [detector specs]}.
+    "merge_threshold", "functional_deps": bool, "max_domain_size", "constraints": [detector specs],
+    "regexs": [(attr, regex)] when repair-by-regex is enabled}.
     -> list of (row_id_string, attribute, current_value, repaired)."""
     if not error_cells:
         return []
@@ -350,11 +374,21 @@ def repair(tbl, row_id, error_cells, target_columns, pairwise_stats, domain_stat
     error_cells = [c for c in error_cells if c[1] in target_columns]  # model.py:1316
     base = convert_error_cells_to_null(tbl, error_cells, target_columns)
     by_rules = []
+    if rules and rules.get("regexs"):  # model.py:662-665 (regex repairs come first)
+        error_cells, by_regex = repair_by_regexs(error_cells, rules["regexs"])
+        for (r, a, cur, v) in by_regex:
+            if base.kinds[a] != "str":
+                raise NotImplementedError("regex structure repair of a numeric attribute")
+            if base.cols[a].dtype != object:
+                raise NotImplementedError("regex structure repair needs string values, not codes")
+            base.cols[a][r] = v
+        by_rules += by_regex
     if rules and rules.get("nearest_values") and rules.get("cost_fn") is not None:  # model.py:1326-1328
-        error_cells, by_rules = repair_by_nearest_values(
+        error_cells, by_nv = repair_by_nearest_values(
             base, error_cells, target_columns, rules["cost_fn"], rules.get("cost_targets") or [],
             rules.get("merge_threshold", 2.0))
-        for (r, a, _, v) in by_rules:  # _repair_attrs: the repaired cells join the repair base
+        by_rules += by_nv
+        for (r, a, _, v) in by_nv:  # _repair_attrs: the repaired cells join the repair base
             if base.cols[a].dtype == object or base.kinds[a] == "str":
                 base.cols[a][r] = v
             else:

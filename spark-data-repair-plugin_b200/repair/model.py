@@ -272,7 +272,6 @@ class RepairModel():
         validate_options(self.opts)
         for key in _MODEL_OPT:
             self._opt(key)
-        R.check_supported(self)
 
         from .engine import Engine
         engine = Engine(table, self.device_index)
@@ -501,6 +500,14 @@ def repair_cells_pmf(rm, engine, table, res, continuous):
     every predicted cell, and the cell itself becomes "neither NULL nor a known category" for the
     later models (the reference parks a JSON string there).
     -> [(row id, attribute, current_value, classes or None, probs or value string)]"""
+    _, undo = R.apply_rules(rm, engine, table, res) if rm.repair_by_rules else ([], [])  # model.py:1326-1328
+    try:
+        return _repair_cells_pmf(rm, engine, table, res, continuous)
+    finally:
+        R.restore(engine, undo)
+
+
+def _repair_cells_pmf(rm, engine, table, res, continuous):
     from . import pmf as P
     torch = engine.torch
     targets = res.target_columns
@@ -657,9 +664,7 @@ def repair_cells(rm, engine, table, res, continuous, repair_data=False, models=N
     cont_idx = engine.dt.cont_index
     if encoded_output and models is not None and not engine.dt.cont_index:
         return repair_cells_encoded(rm, engine, table, res, models)
-    by_rules, undo = [], []
-    if rm._repair_by_nearest_values_enabled:        # model.py:1326-1328
-        by_rules, undo = R.repair_by_nearest_values(rm, engine, table, res)
+    by_rules, undo = R.apply_rules(rm, engine, table, res) if rm.repair_by_rules else ([], [])  # model.py:1326-1328
     try:
         return _repair_cells(rm, engine, table, res, continuous, repair_data, models, encoded_output, by_rules)
     finally:

@@ -63,12 +63,13 @@ def provider_from_product(rm, table, value_of):
     return provider
 
 
-def oracle_rules(rules):
+def oracle_rules(rules, specs=()):
     """parity-test rule settings -> the oracle's `rules` argument."""
     if not rules:
         return None
     from oracle import repair as OR
-    return {"nearest_values": bool(rules.get("nearest")), "cost_targets": list(rules.get("cf_targets", [])),
+    return {"regexs": [(s["attr"], s["regex"]) for s in specs if s["type"] == "regex"] if rules.get("regex") else [],
+            "nearest_values": bool(rules.get("nearest")), "cost_targets": list(rules.get("cf_targets", [])),
             "cost_fn": (lambda a, b: float(OR.levenshtein(a, b))) if rules.get("nearest") else None,
             "merge_threshold": float(rules.get("threshold", 2.0)), "functional_deps": rules.get("fd", True),
             "max_domain_size": int(rules.get("max_domain_size", 1000))}
@@ -85,6 +86,8 @@ def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=Non
             rm.setUpdateCostFunction(Levenshtein(targets=list(rules.get("cf_targets", []))))
             rm.option("model.rule.repair_by_nearest_values.disabled", "")
             rm.option("model.rule.merge_threshold", str(rules.get("threshold", 2.0)))
+        if rules.get("regex"):
+            rm.option("model.rule.repair_by_regex.disabled", "")
         if not rules.get("fd", True):
             rm.option("model.rule.repair_by_functional_deps.disabled", "1")
         if "max_domain_size" in rules:
@@ -159,7 +162,7 @@ def run_both_frame(df, row_id, specs, targets=None, thres=80, opts=None, mode="r
     o_opts = {k: v for k, v in (opts or {}).items() if k.startswith("error.") or k in OR.DEFAULT_OPTS}
     o_given = None if given is None else [tuple(x) for x in given[[row_id, "attribute"]].itertuples(index=False)]
     want = OR.run(otbl, row_id, specs, targets, thres, o_given, o_opts, provider,
-                  detect_errors_only=(mode == "detect"), rules=oracle_rules(rules))
+                  detect_errors_only=(mode == "detect"), rules=oracle_rules(rules, specs))
     want = sorted([tuple(w) for w in want], key=lambda t: (t[0], t[1]))
     return got, want, {"gpu_launches": rm.last_run.get("gpu_launches", 0), "rm": rm}
 

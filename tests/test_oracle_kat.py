@@ -565,3 +565,29 @@ def test_rule_based_prediction_order():
     # model.py:928-953: statistical models first, then FD models whose determinant is settled
     models = [("a", {"fd": {"x": "b"}}), ("b", {"fd": {"x": "c"}}), ("c", {"forest": 1}), ("d", {"fd": {"x": "z"}})]
     assert [m[0] for m in R.resolve_prediction_order(models, ["a", "b", "c", "d"])] == ["c", "b", "d", "a"]
+
+
+def test_regex_structure_repair_kats():
+    # RegexStructureRepairSuite.scala:24-60
+    from oracle.regex_repair import RegexStructureRepair, parse
+    assert parse("^[0-9]{1,3} patients$") == [("Other", "^"), ("Pattern", "[0-9]{1,3}"), ("Constant", " patients"),
+                                              ("Other", "$")]
+    assert parse("^[0-9]{1,3}%$") == [("Other", "^"), ("Pattern", "[0-9]{1,3}"), ("Constant", "%"), ("Other", "$")]
+    for regex, cases in [("^[0-9]{1,3} patients$", [("32 patixxts", "32 patients"), ("619 paxienxs", "619 patients"),
+                                                    ("x2 patixxts", None)]),
+                         ("^[0-9]{1,3}%", [("33x", "33%"), ("x2%", None)]),
+                         ("^[0-9]{2}-[0-9]{2}-[0-9]{2}-[0-9]{2}$", [("23.39.23.11", "23-39-23-11"),
+                                                                    ("23.x9.2x.1x", None)])]:
+        fix = RegexStructureRepair(regex)
+        for value, want in cases:
+            assert fix(value) == want
+    assert RegexStructureRepair("^[0-9]{2}$")(None) is None
+
+
+def test_repair_by_regular_expression_kat():
+    # RepairSuite.scala:514-547: only the cells of the target attribute, a broken regex repairs nothing
+    cells = [(0, "xx", "32 patxxnts"), (1, "xx", "1xx patients"), (2, "xx", None), (2, "yy", "yyy1"), (5, "yy", "yyy2")]
+    rest, done = R.repair_by_regexs(cells, [("xx", "^[0-9]{1,3} patients$")])
+    assert done == [(0, "xx", "32 patxxnts", "32 patients")] and rest == cells[1:]
+    rest, done = R.repair_by_regexs(cells, [("xx", "^[0-9]{1,")])
+    assert done == [] and rest == cells
