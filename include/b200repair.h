@@ -184,6 +184,11 @@ int dr_domain_score(dr_ctx* ctx, const int32_t* rows, int64_t n_cells, const int
 int dr_gather_rows_masked(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
                           const int32_t* rows, int64_t n, int32_t* out, void* stream);
 /* Same for float64 side arrays of continuous attributes (NaN where masked). */
+/* Same, and on the way: null_out[c * null_words_per_col + w] bit i = (out[32 * w + i][c] < 0), the NULL
+ * bitmap of every tile column (what dr_tile_null_bitmaps computes with a second pass over the tile). */
+int dr_gather_rows_masked_nulls(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
+                                const int32_t* rows, int64_t n, int32_t* out, uint32_t* null_out,
+                                int64_t null_words_per_col, void* stream);
 int dr_gather_rows_masked_f64(dr_ctx* ctx, const double* const* cols, uint32_t* const* bitmaps, int n_cols,
                               const int32_t* rows, int64_t n, double* out, void* stream);
 /* out bit i = (tile[i][col] < 0): the cells model `col` has to fill (model.py:1128-1133). */

@@ -157,28 +157,52 @@ struct GatherParams {
 
 // A warp gathers 32 rows: lane = row while reading (each column read is a 32-row gather from one
 // column array), then the 32 x K tile is written out contiguously (coalesced) through shared memory.
+// Columns are taken eight at a time with all sixteen loads (mask word + value) issued before any is
+// used -- the gather is latency bound otherwise.  Optionally the NULL bitmap of every tile column is
+// produced on the way (one ballot per column and row group), which saves a pass over the tile.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_gather_rows_masked(const __grid_constant__ GatherParams p,
                                                                  const int32_t* __restrict__ rows, int64_t n,
-                                                                 T* __restrict__ out, T null_value) {
+                                                                 T* __restrict__ out, T null_value,
+                                                                 uint32_t* __restrict__ null_out,
+                                                                 int64_t null_words_per_col) {
     extern __shared__ unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
     const int K = p.n_cols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* my = tile + (size_t)warp * 32 * (K + 1);
     const int64_t n_groups = (n + 31) >> 5;
+    constexpr int kBatch = 8;
     for (int64_t grp = (int64_t)blockIdx.x * (kThreads / 32) + warp; grp < n_groups;
          grp += (int64_t)gridDim.x * (kThreads / 32)) {
         const int64_t i = (grp << 5) + lane;
         const int r = i < n ? rows[i] : -1;
-        for (int c = 0; c < K; ++c) {
-            T v = null_value;
-            if (r >= 0) {
+        const int rr = r < 0 ? 0 : r;  // always a readable row
+        for (int c0 = 0; c0 < K; c0 += kBatch) {
+            T v[kBatch];
+            uint32_t mw[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int c = c0 + j < K ? c0 + j : K - 1;
                 const uint32_t* bm = p.bitmaps[c];
-                const bool masked = bm != nullptr && ((__ldg(bm + (r >> 5)) >> (r & 31)) & 1u);
-                if (!masked) v = reinterpret_cast<const T*>(p.cols[c])[r];
+                mw[j] = bm != nullptr ? __ldg(bm + (rr >> 5)) : 0u;
+                v[j] = reinterpret_cast<const T*>(p.cols[c])[rr];
             }
-            my[lane * (K + 1) + c] = v;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int c = c0 + j;
+                if (c < K) {  // warp uniform
+                    T x = v[j];
+                    if (r < 0 || ((mw[j] >> (rr & 31)) & 1u)) x = null_value;
+                    my[lane * (K + 1) + c] = x;
+                    if (null_out != nullptr) {
+                        bool isnull;
+                        if constexpr (sizeof(T) == 8) isnull = x != x; else isnull = x < 0;
+                        const unsigned bits = __ballot_sync(0xffffffffu, isnull && r >= 0);
+                        if (lane == 0) null_out[(int64_t)c * null_words_per_col + grp] = bits;
+                    }
+                }
+            }
         }
         __syncwarp();
         const int64_t first = grp << 5;
@@ -508,10 +532,12 @@ int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, con
 
 template <typename T>
 static int gather_rows_masked(dr_ctx* ctx, const T* const* cols, uint32_t* const* bitmaps, int n_cols,
-                              const int32_t* rows, int64_t n, T* out, T null_value, void* stream) {
+                              const int32_t* rows, int64_t n, T* out, T null_value, uint32_t* null_out,
+                              int64_t null_words_per_col, void* stream) {
     if (!ctx) return DR_ERR_INVALID;
     if (n <= 0 || n_cols == 0) return DR_OK;
     DR_REQUIRE(ctx, cols && rows && out, "null pointer");
+    DR_REQUIRE(ctx, null_out == nullptr || null_words_per_col >= (n + 31) / 32, "null bitmap rows too short");
     DR_REQUIRE(ctx, n_cols >= 1 && n_cols <= DR_MAX_COLS, "n_cols must be in [1, 64]");
     GatherParams p;
     memset(&p, 0, sizeof(p));
@@ -525,7 +551,8 @@ static int gather_rows_masked(dr_ctx* ctx, const T* const* cols, uint32_t* const
     DR_CUDA(ctx, cudaFuncSetAttribute(k_gather_rows_masked<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const int grid = dr_grid_for(ctx, (n + 31) / 32, kThreads / 32, 2);
-    k_gather_rows_masked<T><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p, rows, n, out, null_value);
+    k_gather_rows_masked<T><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p, rows, n, out, null_value, null_out,
+                                                                            null_words_per_col);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }
@@ -534,12 +561,19 @@ extern "C" {
 
 int dr_gather_rows_masked(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
                           const int32_t* rows, int64_t n, int32_t* out, void* stream) {
-    return gather_rows_masked<int32_t>(ctx, cols, bitmaps, n_cols, rows, n, out, -1, stream);
+    return gather_rows_masked<int32_t>(ctx, cols, bitmaps, n_cols, rows, n, out, -1, nullptr, 0, stream);
+}
+
+int dr_gather_rows_masked_nulls(dr_ctx* ctx, const int32_t* const* cols, uint32_t* const* bitmaps, int n_cols,
+                                const int32_t* rows, int64_t n, int32_t* out, uint32_t* null_out,
+                                int64_t null_words_per_col, void* stream) {
+    return gather_rows_masked<int32_t>(ctx, cols, bitmaps, n_cols, rows, n, out, -1, null_out, null_words_per_col,
+                                       stream);
 }
 
 int dr_gather_rows_masked_f64(dr_ctx* ctx, const double* const* cols, uint32_t* const* bitmaps, int n_cols,
                               const int32_t* rows, int64_t n, double* out, void* stream) {
-    return gather_rows_masked<double>(ctx, cols, bitmaps, n_cols, rows, n, out, (double)NAN, stream);
+    return gather_rows_masked<double>(ctx, cols, bitmaps, n_cols, rows, n, out, (double)NAN, nullptr, 0, stream);
 }
 
 int dr_tile_null_bitmap(dr_ctx* ctx, const int32_t* tile, int64_t n, int n_cols, int col, uint32_t* out,

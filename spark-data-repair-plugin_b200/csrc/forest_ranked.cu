@@ -145,22 +145,40 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         const bool live = i < p.n_cells;
         const int64_t row = live ? p.cells[i] : 0;
         {
+            // feature tile of this thread's cell: rank bytes of its encoded features (eight features at a
+            // time, loads first: the tile row and the rank look-ups are dependent global loads)
             const int32_t* trow = p.tile + row * p.n_cols;
-            for (int f = 0; f < F.n_feat; ++f) {
-                uint8_t r = 255;  // NaN
-                if (live) {
-                    const int lo = F.rank_lut_off[f], hi = F.rank_lut_off[f + 1];
-                    const int kk = lo + trow[F.feat_col[f]] + 1;
-                    if (kk >= lo && kk < hi) r = __ldg(F.rank_lut + kk);
+            constexpr int kFill = 8;
+            for (int f0 = 0; f0 < F.n_feat; f0 += kFill) {
+                int code[kFill], lo[kFill], hi[kFill];
+#pragma unroll
+                for (int j = 0; j < kFill; ++j) {
+                    const int f = f0 + j < F.n_feat ? f0 + j : F.n_feat - 1;
+                    lo[j] = F.rank_lut_off[f];
+                    hi[j] = F.rank_lut_off[f + 1];
+                    code[j] = live ? trow[F.feat_col[f]] : -1;
                 }
-                // ranks are stored +1 (1..254); NaN is 255 in the copy read by nodes that send NaN
-                // right and 0 in the copy read by nodes that send it left
-                if (kWide) {
-                    reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 0) * T] = r;
-                    reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 1) * T] = r == 255 ? 0 : r;
-                } else {
-                    my_feat[2 * f + 0] = r;
-                    my_feat[2 * f + 1] = r == 255 ? 0 : r;
+                uint8_t r[kFill];
+#pragma unroll
+                for (int j = 0; j < kFill; ++j) {
+                    const int kk = lo[j] + code[j] + 1;
+                    r[j] = (live && kk >= lo[j] && kk < hi[j]) ? __ldg(F.rank_lut + kk) : (uint8_t)255;  // 255 = NaN
+                }
+#pragma unroll
+                for (int j = 0; j < kFill; ++j) {
+                    const int f = f0 + j;
+                    if (f < F.n_feat) {
+                        // ranks are stored +1 (1..254); NaN is 255 in the copy read by nodes that send
+                        // NaN right and 0 in the copy read by nodes that send it left
+                        const uint8_t rl = r[j] == 255 ? 0 : r[j];
+                        if (kWide) {
+                            reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 0) * T] = r[j];
+                            reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 1) * T] = rl;
+                        } else {
+                            my_feat[2 * f + 0] = r[j];
+                            my_feat[2 * f + 1] = rl;
+                        }
+                    }
                 }
             }
         }
@@ -181,6 +199,11 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             const double* __restrict__ leaves = buf[b].leaf;
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
+            // The leaf values of a group are only added (in tree order: bit-identical float64 sums)
+            // while the NEXT group walks its first level, so that the serial DADD chain hides behind
+            // shared-memory latency instead of idling the warp.
+            double pend[kIlp];
+            int n_pend = 0;
             for (int q = 0; q < n_trees; q += kIlp) {
                 uint32_t w[kIlp], lb[kIlp];
 #pragma unroll
@@ -191,22 +214,30 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 if (q + kIlp > n_trees) {  // last group of a sequence: surplus slots re-walk tree 0
 #pragma unroll
                     for (int j = 1; j < kIlp; ++j)
-                        if (q + j >= n_trees) w[j] = w[0];
+                        if (q + j >= n_trees) { w[j] = w[0]; lb[j] = lb[0]; }
                 }
-                for (int d = 0; d < depth; ++d) {
+                if (depth > 0) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
-                }
-                if (q + kIlp <= n_trees) {
-#pragma unroll
-                    for (int j = 0; j < kIlp; ++j)  // tree order: bit-identical float64 sums
-                        acc += leaves[lb[j] + (w[j] >> 24)];
+                    for (int j = 0; j < kIlp; ++j) {
+                        w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
+                        if (j < n_pend) acc += pend[j];
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < kIlp; ++j)
-                        if (q + j < n_trees) acc += leaves[lb[j] + (w[j] >> 24)];
+                        if (j < n_pend) acc += pend[j];
                 }
+                for (int d = 1; d < depth; ++d) {
+#pragma unroll
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
+                }
+#pragma unroll
+                for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (w[j] >> 24)];
+                n_pend = n_trees - q < kIlp ? n_trees - q : kIlp;
             }
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j)  // the chunk's last group
+                if (j < n_pend) acc += pend[j];
             __syncwarp();
             if ((t & 31) == 0) mbar_arrive(&empty[b]);  // this warp is done with buffer b
         }

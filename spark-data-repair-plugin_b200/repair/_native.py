@@ -83,6 +83,8 @@ _SIGNATURES = {
                                 c_void_p]),
     "dr_gather_rows_masked": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_gather_rows_masked_f64": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_gather_rows_masked_nulls": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+                                            c_int64, c_void_p]),
     "dr_tile_null_bitmap": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "dr_tile_null_bitmap_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "dr_gather_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -285,9 +287,15 @@ class Context:
                                              _dp(out_top1), _dp(out_prob), _dp(out_weak), self._stream()))
 
     # ---- repair base / tile ----------------------------------------------------------------------
-    def gather_rows_masked(self, cols, bitmaps, rows, n, out, f64=False):
+    def gather_rows_masked(self, cols, bitmaps, rows, n, out, f64=False, null_out=None):
+        """null_out (int32 codes only): int32 [K][words] that receives the NULL bitmap of every tile column."""
         cp, _k1 = _ptr_array([c.data_ptr() for c in cols])
         bp, _k2 = _ptr_array([0 if b is None else b.data_ptr() for b in bitmaps])
+        if null_out is not None:
+            assert not f64
+            self._check(self.lib.dr_gather_rows_masked_nulls(self._h, cp, bp, len(cols), _dp(rows), n, _dp(out),
+                                                             _dp(null_out), int(null_out.shape[1]), self._stream()))
+            return
         fn = self.lib.dr_gather_rows_masked_f64 if f64 else self.lib.dr_gather_rows_masked
         self._check(fn(self._h, cp, bp, len(cols), _dp(rows), n, _dp(out), self._stream()))
 

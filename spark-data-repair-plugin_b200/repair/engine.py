@@ -513,7 +513,10 @@ class Engine:
         K = len(self.table.columns)
         masks = [res.bitmaps.get(c.name) if c.name in target_columns else None for c in self.table.columns]
         tile = self.torch.empty((max(D, 1), K), dtype=self.torch.int32, device=self.device)
-        self.ctx.gather_rows_masked([self.dt.col(c.name) for c in self.table.columns], masks, drows, D, tile)
+        # NULL bitmap of every tile column, taken while gathering (the chain's work lists)
+        self.tile_nulls = self.torch.zeros((K, (D + 31) // 32 + 1), dtype=self.torch.int32, device=self.device)
+        self.ctx.gather_rows_masked([self.dt.col(c.name) for c in self.table.columns], masks, drows, D, tile,
+                                    null_out=self.tile_nulls)
         cont = [c for c in self.table.columns if c.continuous]
         ctile = None
         if cont:

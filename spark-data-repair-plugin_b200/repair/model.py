@@ -470,8 +470,8 @@ def run_chain(engine, table, models, tile, ctile, D):
     words = (D + 31) // 32 + 1
     nullbits = torch.zeros(words, dtype=torch.int32, device=engine.device)
     # NULL cells of every discrete column in one pass (a model only fills its own column)
-    all_null = torch.zeros((K, words), dtype=torch.int32, device=engine.device)
-    engine.ctx.tile_null_bitmaps(tile, D, K, words, all_null)
+    all_null = engine.tile_nulls  # [K][words], produced by build_dirty_tile together with the tile
+    assert tuple(all_null.shape) == (K, words)
     engine.mark("chain:null bitmaps")
     for y, m in models:
         ycol = table.by_name[y]
@@ -524,8 +524,8 @@ def _repair_cells_pmf(rm, engine, table, res, continuous):
     D = int(drows.numel())
     words = (D + 31) // 32 + 1
     nullbits = torch.zeros(words, dtype=torch.int32, device=engine.device)
-    all_null = torch.zeros((K, words), dtype=torch.int32, device=engine.device)
-    engine.ctx.tile_null_bitmaps(tile, D, K, words, all_null)
+    all_null = engine.tile_nulls  # [K][words], produced by build_dirty_tile together with the tile
+    assert tuple(all_null.shape) == (K, words)
     kept = {}
     for y, m in models:
         ycol = table.by_name[y]
@@ -644,7 +644,8 @@ def repair_cells_encoded(rm, engine, table, res, models):
     engine.mark("repair:d2h")
     h = host.numpy()
     out = []
-    bounds = np.searchsorted(h[0, :n_keep], [o for _, o, _ in seg] + [E])
+    # (int32 needles: a wider type would make numpy convert the whole 10^7-element haystack first)
+    bounds = np.searchsorted(h[0, :n_keep], np.asarray([o for _, o, _ in seg] + [E], dtype=np.int32))
     for (a, _, _), lo, hi in zip(seg, bounds[:-1], bounds[1:]):
         out.append((a, h[1, lo:hi], h[2, lo:hi], h[3, lo:hi]))  # views of the engine's pinned staging buffer
     return out

@@ -242,3 +242,46 @@ class DeviceTable:
 
     def val(self, name):
         return self.values[self.cont_index[name]]
+
+
+class ByteStager:
+    """Ingest of successive batches of an all-small-dictionary table (every dictionary <= 254 entries,
+    one byte per cell in pinned host memory, 255 = NULL) into ONE resident DeviceTable: the host->device
+    copy of batch i + 1 runs on its own stream into the other of two device staging buffers while
+    batch i is being processed, so PCIe time leaves the critical path; what stays on it is the
+    widening pass (dr_widen_u8: 1 B read + 4 B written per cell)."""
+
+    def __init__(self, device_table, ctx):
+        import torch
+        self.torch, self.dt, self.ctx = torch, device_table, ctx
+        shape = tuple(device_table.codes.shape)
+        self.stage = [torch.empty(shape, dtype=torch.uint8, device=device_table.device) for _ in range(2)]
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of the buffer finished
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]   # widening pass read the buffer
+        self.stream = torch.cuda.Stream(device=device_table.device)
+        self.pending = [False, False]
+        self.n = 0                                                  # batches handed to the table so far
+
+    def prefetch(self, host_bytes):
+        """Start copying the NEXT batch (pinned uint8 [K][n_pad]) to the device."""
+        j = (self.n + (1 if self.pending[self.n % 2] else 0)) % 2
+        assert not self.pending[j], "both staging buffers are in flight"
+        self.stream.wait_event(self.consumed[j])
+        with self.torch.cuda.stream(self.stream):
+            self.stage[j].copy_(host_bytes, non_blocking=True)
+            self.copied[j].record(self.stream)
+        self.pending[j] = True
+
+    def next_batch(self, host_bytes=None):
+        """Make the oldest prefetched batch (or `host_bytes`, copied now) the table's content."""
+        j = self.n % 2
+        if not self.pending[j]:
+            assert host_bytes is not None, "nothing prefetched"
+            self.prefetch(host_bytes)
+        main = self.torch.cuda.current_stream()
+        main.wait_event(self.copied[j])
+        self.ctx.widen_u8(self.stage[j], self.stage[j].numel(), self.dt.codes)
+        self.consumed[j].record(main)
+        self.pending[j] = False
+        self.n += 1
+

@@ -7,7 +7,7 @@ mkdir -p $out
 python -m pytest tests -x -q -m gpu > $out/pytest_$tag.log 2>&1; echo "pytest exit $?" >> $out/pytest_$tag.log
 tail -3 $out/pytest_$tag.log
 B="python bench.py --forests random --steps 3 --warmup 1 --no-e2e --no-cpu-baseline"
-for lay in wide32 wide16 bytes; do
+for lay in wide16 bytes; do
   DR_RANKED_LAYOUT=$lay $B > $out/bench_${tag}_$lay.json 2> $out/bench_${tag}_$lay.err; echo "bench $lay exit $?"
 done
 python bench.py --steps 5 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $?"
