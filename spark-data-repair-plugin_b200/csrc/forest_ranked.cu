@@ -73,14 +73,32 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // One level: two shared-memory loads (rank byte, next node word), one add and one byte extract.
+// Addresses are 32-bit shared-window offsets (no generic-address arithmetic): in the wide layout
+// feat = own column of the [slot][thread] word tile, so slot s sits at feat + s * 4 * T.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 template <bool kWide, int T>
-__device__ __forceinline__ uint32_t step_node(const uint32_t* __restrict__ nodes, uint32_t w,
-                                              const unsigned char* __restrict__ my_feat) {
+__device__ __forceinline__ uint32_t step_node(uint32_t nodes, uint32_t w, uint32_t feat, uint32_t lane_off) {
     uint32_t r;
-    if (kWide) r = *reinterpret_cast<const uint32_t*>(my_feat + (w >> 24) * (T * 4));
-    else       r = my_feat[w >> 24];
-    const uint32_t w2 = w + r;                          // carries into bit 8 iff rank >= threshold
-    return nodes[__byte_perm(w2, 0, 0x4421)];           // bits 8..23: left child (+1 = right child)
+    if (kWide) {
+        // slot * (4 * T) + own column, as ONE multiply-add (left to itself the compiler turns the
+        // shift pair into shift + mask and needs a third instruction for the add)
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(w >> 24), "n"(T * 4), "r"(feat + lane_off));
+        r = lds_u32(addr);
+    } else {
+        r = lds_u8((w >> 24) + feat);
+    }
+    const uint32_t w2 = w + r;                                   // carries into bit 8 iff rank >= threshold
+    return lds_u32(__byte_perm(w2, 0, 0x4421) * 4u + nodes);     // bits 8..23: left child (+1 = right child)
 }
 
 constexpr int kChunkTrees = DR_RANKED_CHUNK_TREES;
@@ -121,7 +139,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 const int b = k & 1;
                 if (k >= 2) {  // wait until the previous tenant of this buffer (chunk k - 2) was released
                     const uint32_t parity = ((k >> 1) - 1) & 1;
-                    while (!mbar_try_wait(&empty[b], parity)) {}
+                    while (!mbar_try_wait(&empty[b], parity)) __nanosleep(256);  // do not steal issue slots
                 }
                 const int n0 = F.chunk_node_off[c], n1 = F.chunk_node_off[c + 1];
                 const int l0 = F.chunk_leaf_off[c], l1 = F.chunk_leaf_off[c + 1];
@@ -139,6 +157,9 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
 
     // ---- consumer warps: one cell per thread; the feature tile is private to the thread ----
     unsigned char* my_feat = kWide ? s_feat + 4 * t : s_feat + (size_t)t * p.feat_stride;
+    // wide: feat = the tile's base (uniform), lane_off = this thread's column; bytes: feat = own row
+    const uint32_t feat = kWide ? smem_u32(s_feat) : smem_u32(my_feat);
+    const uint32_t lane_off = 4u * (uint32_t)t;
     uint32_t k = 0;
     for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
         const int64_t i = base + t;
@@ -194,8 +215,8 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 cur_s = s;
                 acc = F.baseline[s];
             }
-            while (!mbar_try_wait(&full[b], (k >> 1) & 1)) {}
-            const uint32_t* __restrict__ nodes = buf[b].node;
+            while (!mbar_try_wait(&full[b], (k >> 1) & 1)) __nanosleep(32);
+            const uint32_t nodes = smem_u32(buf[b].node);
             const double* __restrict__ leaves = buf[b].leaf;
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
@@ -219,7 +240,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 if (depth > 0) {
 #pragma unroll
                     for (int j = 0; j < kIlp; ++j) {
-                        w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
+                        w[j] = step_node<kWide, T>(nodes, w[j], feat, lane_off);
                         if (j < n_pend) acc += pend[j];
                     }
                 } else {
@@ -229,7 +250,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 }
                 for (int d = 1; d < depth; ++d) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], my_feat);
+                    for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], feat, lane_off);
                 }
 #pragma unroll
                 for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (w[j] >> 24)];

@@ -279,6 +279,14 @@ def test_gather_rows_masked_and_tile_ops(ctx, n, k):
     want = np.stack([np.where(masks[i][rows], -1, cols[i][rows]) if masks[i] is not None else cols[i][rows]
                      for i in range(k)], axis=1)
     assert np.array_equal(tile.cpu().numpy(), want)
+    # the same gather producing the NULL bitmap of every tile column on the way
+    words = (n + 31) // 32 + 1
+    tile2 = torch.empty((n, k), dtype=torch.int32, device="cuda")
+    nulls = torch.zeros((k, words), dtype=torch.int32, device="cuda")
+    ctx.gather_rows_masked([dev(c) for c in cols], dbms, dev(rows), n, tile2, null_out=nulls)
+    assert np.array_equal(tile2.cpu().numpy(), want)
+    for c in range(k):
+        assert np.array_equal(bits_of(nulls[c], n), want[:, c] < 0)
     ctile = torch.empty((n, 2), dtype=torch.float64, device="cuda")
     ctx.gather_rows_masked([dev(v) for v in vals], [dbms[0], None], dev(rows), n, ctile, f64=True)
     w0 = np.where(masks[0][rows], np.nan, vals[0][rows])
@@ -522,3 +530,32 @@ def test_gbdt_trainer_matches_oracle_bit_for_bit(ctx, n_classes, n, n_iter):
     assert np.array_equal(got["value"], want["value"])          # bit-exact float64 leaves
     assert np.array_equal(got["baseline"], want["baseline"])
     assert (np.asarray(want["feature"]) >= 0).sum() > n_iter    # the trees actually split
+
+
+def test_byte_stager_double_buffering(ctx):
+    """Successive byte batches reach the resident table in order, with the next copy in flight."""
+    from repair.table import ByteStager, DeviceTable, EncodedTable
+    rng = np.random.default_rng(5)
+    n, k = 1000, 5
+    table = EncodedTable.from_codes("tid", ["a%d" % i for i in range(k)], [np.zeros(0, np.int32)] * k, [200] * k,
+                                    row_ids=np.arange(n, dtype=np.int64))
+    table.n_rows = n
+    dt = DeviceTable(table, torch.device("cuda", 0), codes=torch.zeros((k, 1024), dtype=torch.int32, device="cuda"))
+    stager = ByteStager(dt, ctx)
+    batches = []
+    for _ in range(4):
+        b = rng.integers(0, 256, size=(k, 1024)).astype(np.uint8)
+        batches.append(torch.from_numpy(b).pin_memory())
+    stager.prefetch(batches[0])
+    for i in range(4):
+        stager.next_batch()
+        if i + 1 < 4:
+            stager.prefetch(batches[i + 1])      # overlaps whatever is done with batch i
+        got = dt.codes.cpu().numpy()
+        want = batches[i].numpy().astype(np.int32)
+        want[want == 255] = -1
+        assert np.array_equal(got, want), i
+    stager.next_batch(batches[2])                # nothing prefetched: copied on the spot
+    want = batches[2].numpy().astype(np.int32)
+    want[want == 255] = -1
+    assert np.array_equal(dt.codes.cpu().numpy(), want)
