@@ -46,14 +46,25 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ Pair
         if (last > p.n_rows) last = p.n_rows;
         const int64_t r = first + threadIdx.x;
         const bool live = r < last;
-        for (int c = 0; c < p.n_used; ++c) {
-            const int col = p.used[c];
-            int s = 0;
-            if (live) {
-                const unsigned v = (unsigned)(__ldcs(p.cols[col] + r) + 1);
-                s = v > (unsigned)p.dom[col] ? p.dom[col] : (int)v;
+        // stage the row's codes, eight columns at a time with all loads issued before any is used
+        constexpr int kBatch = 8;
+        const int64_t rr = live ? r : first;  // always a readable row
+        for (int c0 = 0; c0 < p.n_used; c0 += kBatch) {
+            int v[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int c = c0 + j < p.n_used ? c0 + j : p.n_used - 1;
+                v[j] = __ldcs(p.cols[p.used[c]] + rr);
             }
-            codes[c * kTile + threadIdx.x] = (uint16_t)s;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int c = c0 + j;
+                if (c < p.n_used) {
+                    const int dom = p.dom[p.used[c]];
+                    const unsigned u = (unsigned)(v[j] + 1);
+                    codes[c * kTile + threadIdx.x] = (uint16_t)(live ? (u > (unsigned)dom ? dom : (int)u) : 0);
+                }
+            }
         }
         // each thread only reads back its own column of `codes`: no barrier needed
         if (live) {

@@ -15,16 +15,21 @@ python bench.py --steps 5 --warmup 3 > $out/bench_$tag.json 2> $out/bench_$tag.e
 B="python bench.py --forests random --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_' -c 3000 --csv \
     --log-file $out/launches_$tag.csv $B > $out/ncu_launch_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_scan_hist|k_gather_rows_masked|k_pairs|k_tile_null_bitmaps' -s 3 -c 6 -f -o $out/prof_stream_$tag \
-    $B > $out/ncu_stream_$tag.log 2>&1
+# (kernel regex, launches of the untimed set-up to skip, launches to capture)
+cap() {
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f \
+      -o $out/prof_$1_$tag $B > $out/ncu_$1_$tag.log 2>&1
+  ncu -i $out/prof_$1_$tag.ncu-rep --page raw --csv > $out/prof_$1_$tag.csv 2>/dev/null
+}
+cap scan 'k_scan_hist' 1 1
+cap pairs 'k_pairs' 2 2
+cap gather 'k_gather_rows_masked' 32 1
+cap domain 'k_domain_score' 16 2
+cap forest1 'k_forest_predict_ranked' 38 1
 timeout 1200 ncu --set full --clock-control none -k regex:'k_forest_predict_ranked' -s 32 -c 32 -f \
     -o $out/prof_forest_$tag $B > $out/ncu_forest_$tag.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_forest_predict_ranked' -s 40 -c 1 -f \
-    -o $out/prof_forest1_$tag $B > $out/ncu_forest1_$tag.log 2>&1
-for r in stream forest; do
-  ncu -i $out/prof_${r}_$tag.ncu-rep --page raw --csv > $out/prof_${r}_$tag.csv 2>/dev/null
-done
+ncu -i $out/prof_forest_$tag.ncu-rep --page raw --csv > $out/prof_forest_$tag.csv 2>/dev/null
+ncu -i $out/prof_forest1_$tag.ncu-rep --page source --csv > $out/prof_forest1_${tag}_src.csv 2>/dev/null
 rm -f $out/prof_forest_$tag.ncu-rep
 find $out -size +20M -delete
-du -sh $out; ls -la $out | tail -20
+du -sh $out; ls -la $out | tail -30
