@@ -127,6 +127,14 @@ int dr_bitmap_to_rows(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32
  * dr_bitmap_count on the SAME bitmap (it reuses the per-block offsets left in the context scratch). */
 int dr_bitmap_rows_after_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows,
                                int64_t capacity, void* stream);
+/* Fewer host round trips: the popcounts of up to DR_MAX_COUNT_MANY bitmaps with ONE synchronisation, and
+ * the ordered compaction of a bitmap whose count the caller already knows (no synchronisation; writes
+ * at most `count` indices).  Both use the context scratch like dr_bitmap_count. */
+#define DR_MAX_COUNT_MANY 128
+int dr_bitmap_count_many(dr_ctx* ctx, const uint32_t* const* bitmaps, int n_bitmaps, int64_t n_rows,
+                         int64_t* out_counts, void* stream);
+int dr_bitmap_to_rows_async(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t count,
+                            void* stream);
 int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int64_t n, uint32_t* out,
                      void* stream);
 int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,

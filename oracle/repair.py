@@ -15,7 +15,7 @@ from . import detect as D
 from . import domain as DM
 from . import stats as S
 from .forest import (encode_rows, encoder_kind, first_seen_categories, forest_predict)
-from .table import OTable, cast_to_string
+from .table import cast_to_string
 
 DEFAULT_OPTS = {  # errors.py:321-338, model.py:115-123
     "error.attr_freq_ratio_threshold": 0.0,

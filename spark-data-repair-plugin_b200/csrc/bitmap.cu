@@ -378,6 +378,24 @@ __global__ void __launch_bounds__(kThreads) k_fd_map_build(const int32_t* __rest
     }
 }
 
+// popcount of many bitmaps in one launch: blockIdx.y = bitmap, blocks of a row stride over its words
+struct ManyBitmaps {
+    const uint32_t* bm[DR_MAX_COUNT_MANY];
+};
+__global__ void __launch_bounds__(kThreads) k_popc_many(const __grid_constant__ ManyBitmaps p, int64_t n_rows,
+                                                        unsigned long long* __restrict__ totals) {
+    const uint32_t* bm = p.bm[blockIdx.y];
+    const int64_t n_words = (n_rows + 31) >> 5;
+    unsigned long long local = 0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = bm[w];
+        if (w == n_words - 1 && (n_rows & 31)) v &= (1u << (n_rows & 31)) - 1u;  // bits past the last row
+        local += __popc(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(totals + blockIdx.y, local);
+}
+
 inline int grid_rows(const dr_ctx* ctx, int64_t n) { return dr_grid_for(ctx, n, kThreads, kCtasPerSm); }
 
 }  // namespace
@@ -434,6 +452,51 @@ int dr_bitmap_count(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int64_t
                                  st));
     DR_CUDA(ctx, cudaStreamSynchronize(st));
     *out_count = (int64_t) * (unsigned long long*)ctx->pinned;
+    return DR_OK;
+}
+
+int dr_bitmap_count_many(dr_ctx* ctx, const uint32_t* const* bitmaps, int n_bitmaps, int64_t n_rows,
+                         int64_t* out_counts, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n_bitmaps <= 0) return DR_OK;
+    DR_REQUIRE(ctx, bitmaps && out_counts, "null pointer");
+    DR_REQUIRE(ctx, n_bitmaps <= DR_MAX_COUNT_MANY, "too many bitmaps for one call");
+    for (int i = 0; i < n_bitmaps; ++i) out_counts[i] = 0;
+    if (n_rows <= 0) return DR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ManyBitmaps p;
+    for (int i = 0; i < n_bitmaps; ++i) {
+        DR_REQUIRE(ctx, bitmaps[i] != nullptr, "null bitmap");
+        p.bm[i] = bitmaps[i];
+    }
+    unsigned long long* totals = (unsigned long long*)ctx->scratch;  // (clobbers the compaction offsets)
+    DR_CUDA(ctx, cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * n_bitmaps, st));
+    const int64_t n_words = (n_rows + 31) >> 5;
+    int per_row = (int)((n_words + kThreads * 8 - 1) / (kThreads * 8));
+    const int cap = ctx->sm_count * 8 / n_bitmaps + 1;
+    if (per_row > cap) per_row = cap;
+    if (per_row < 1) per_row = 1;
+    k_popc_many<<<dim3(per_row, n_bitmaps), kThreads, 0, st>>>(p, n_rows, totals);
+    DR_LAUNCHED(ctx);
+    DR_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, totals, sizeof(unsigned long long) * n_bitmaps, cudaMemcpyDeviceToHost,
+                                 st));
+    DR_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < n_bitmaps; ++i) out_counts[i] = (int64_t)((unsigned long long*)ctx->pinned)[i];
+    return DR_OK;
+}
+
+int dr_bitmap_to_rows_async(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t count,
+                            void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, bitmap && (out_rows || count == 0), "null pointer");
+    if (n_rows <= 0 || count <= 0) return DR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_blocks = 0;
+    int rc = compaction_counts(ctx, bitmap, n_rows, &n_blocks, st);
+    if (rc) return rc;
+    k_write_rows<<<n_blocks, kThreads, 0, st>>>(bitmap, n_rows, (n_rows + 31) >> 5,
+                                                (const unsigned long long*)ctx->scratch, out_rows, count);
+    DR_LAUNCHED(ctx);
     return DR_OK;
 }
 

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "dr_bitmap_or": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dr_bitmap_andnot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dr_bitmap_count": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
+    "dr_bitmap_count_many": (c_int, [c_void_p, _PP, c_int, c_int64, POINTER(c_int64), c_void_p]),
+    "dr_bitmap_to_rows_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "dr_bitmap_to_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dr_bitmap_rows_after_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "dr_tile_null_bitmaps": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
@@ -240,6 +242,22 @@ class Context:
         self._check(self.lib.dr_bitmap_count(self._h, _dp(bitmap), n_rows, byref(n), self._stream()))
         return int(n.value)
 
+    def bitmap_count_many(self, bitmaps, n_rows):
+        """Popcounts of several bitmaps with one host synchronisation."""
+        out = []
+        for i in range(0, len(bitmaps), 128):
+            part = bitmaps[i:i + 128]
+            bp, _keep = _ptr_array([b.data_ptr() for b in part])
+            counts = (c_int64 * len(part))()
+            self._check(self.lib.dr_bitmap_count_many(self._h, bp, len(part), n_rows, counts, self._stream()))
+            out += [int(c) for c in counts]
+        return out
+
+    def bitmap_to_rows_async(self, bitmap, n_rows, out_rows, count):
+        """Ordered compaction of a bitmap whose popcount is known: no host synchronisation."""
+        self._check(self.lib.dr_bitmap_to_rows_async(self._h, _dp(bitmap), n_rows, _dp(out_rows), count,
+                                                     self._stream()))
+
     def bitmap_to_rows(self, bitmap, n_rows, out_rows, capacity):
         n = c_int64()
         self._check(self.lib.dr_bitmap_to_rows(self._h, _dp(bitmap), n_rows, _dp(out_rows), capacity, byref(n),
@@ -366,7 +384,7 @@ def _profiled(name, fn):
 
 
 for _name in ("widen_u8", "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
-              "bitmap_andnot", "bitmap_count", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
+              "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill", "gbdt_train"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))

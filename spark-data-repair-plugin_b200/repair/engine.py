@@ -16,7 +16,6 @@ import numpy as np
 from . import constraints as DC
 from . import stats_host as SH
 from ._native import DR_OP, Context
-from .forest import DeviceModel, encode_matrix, encoder_type, first_seen
 from .table import DeviceTable
 
 _logger = logging.getLogger("repair")
@@ -103,9 +102,17 @@ class Engine:
     def _sync(self):
         self.torch.cuda.current_stream().synchronize()
 
-    def bitmap_rows(self, bitmap, n=None, out=None):
-        """Ascending row indices (device int32 tensor) of the set bits (written into `out` if given)."""
+    def bitmap_rows(self, bitmap, n=None, out=None, count=None):
+        """Ascending row indices (device int32 tensor) of the set bits (written into `out` if given).
+        With `count` (the popcount, e.g. from ctx.bitmap_count_many) there is no host round trip."""
         n = self.n_rows if n is None else n
+        if count is not None:
+            rows = out if out is not None else \
+                self.torch.empty(max(count, 1), dtype=self.torch.int32, device=self.device)
+            assert rows.numel() >= count
+            if count:
+                self.ctx.bitmap_to_rows_async(bitmap, n, rows, count)
+            return rows[:count]
         cnt = self.ctx.bitmap_count(bitmap, n)
         rows = out if out is not None else \
             self.torch.empty(max(cnt, 1), dtype=self.torch.int32, device=self.device)
@@ -453,7 +460,7 @@ class Engine:
         # one fused pass: NULL bits of the discretised targets + every histogram
         self.scan_hist([a for a in res.disc_attrs if a not in self._hist_cache], fused)
         res.bitmaps = bitmaps
-        res.n_cells = {a: self.ctx.bitmap_count(b, self.n_rows) for a, b in bitmaps.items()}
+        res.n_cells = dict(zip(bitmaps.keys(), self.ctx.bitmap_count_many(list(bitmaps.values()), self.n_rows)))
         total = sum(res.n_cells.values())
         if self.dist is not None:
             t = self.torch.tensor([total], dtype=self.torch.int64, device=self.device)
@@ -481,7 +488,8 @@ class Engine:
         if given_cells is None:
             self.prune_weak_labels(res, tables, having, continuous, opts["error.max_attrs_to_compute_domains"],
                                    opts["error.domain_threshold_alpha"], opts["error.domain_threshold_beta"])
-            res.n_cells = {a: self.ctx.bitmap_count(b, self.n_rows) for a, b in res.bitmaps.items()}
+            res.n_cells = dict(zip(res.bitmaps.keys(),
+                                   self.ctx.bitmap_count_many(list(res.bitmaps.values()), self.n_rows)))
         return res
 
     # ---- cell frames -----------------------------------------------------------------------------

@@ -24,7 +24,7 @@ from .errors import ErrorDetector, ErrorModelOptions, default_detectors
 from .forest import DeviceModel, encode_matrix, encoder_type, first_seen
 from .table import EncodedTable
 from .train import build_model, train_option_keys, validate_options
-from .utils import AnalysisException, argtype_check, cell_to_string, get_option_value, to_list_str
+from .utils import argtype_check, cell_to_string, get_option_value, to_list_str
 
 _logger = logging.getLogger("repair")
 
@@ -472,6 +472,8 @@ def run_chain(engine, table, models, tile, ctile, D):
     # NULL cells of every discrete column in one pass (a model only fills its own column)
     all_null = engine.tile_nulls  # [K][words], produced by build_dirty_tile together with the tile
     assert tuple(all_null.shape) == (K, words)
+    # a model only fills its own column, so the work-list sizes can all be taken now, in one round trip
+    null_counts = engine.ctx.bitmap_count_many([all_null[i] for i in range(K)], D)
     engine.mark("chain:null bitmaps")
     for y, m in models:
         ycol = table.by_name[y]
@@ -479,7 +481,7 @@ def run_chain(engine, table, models, tile, ctile, D):
             engine.ctx.tile_null_bitmap(ctile, D, n_cc, cont_idx[y], nullbits, f64=True)
             todo = engine.bitmap_rows(nullbits, D)
         else:
-            todo = engine.bitmap_rows(all_null[tile_col[y]], D)
+            todo = engine.bitmap_rows(all_null[tile_col[y]], D, count=null_counts[tile_col[y]])
         n = int(todo.numel())
         engine.mark("chain:cells of " + y)
         if n == 0:
@@ -612,7 +614,7 @@ def repair_cells_encoded(rm, engine, table, res, models):
     seg, off = [], 0
     for a in attrs:
         n = res.n_cells[a]
-        rows = engine.bitmap_rows(res.bitmaps[a], out=rows_all[off:off + n])
+        rows = engine.bitmap_rows(res.bitmaps[a], out=rows_all[off:off + n], count=n)
         engine.ctx.gather(engine.dt.col(a), rows, n, cur_all[off:off + n])
         seg.append((a, off, n))
         off += n

@@ -185,6 +185,12 @@ def test_bitmap_ops(ctx, n):
     cnt = ctx.bitmap_to_rows(da, n, rows, int(bits_a.sum()))
     assert cnt == int(bits_a.sum())
     assert np.array_equal(rows[:cnt].cpu().numpy(), np.nonzero(bits_a)[0].astype(np.int32))
+    # several popcounts with one round trip, then compaction with the count already known
+    bits_b0 = np.unpackbits(b.view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert ctx.bitmap_count_many([da, db, da], n) == [int(bits_a.sum()), int(bits_b0.sum()), int(bits_a.sum())]
+    rows2 = torch.full((max(cnt, 1),), -7, dtype=torch.int32, device="cuda")
+    ctx.bitmap_to_rows_async(da, n, rows2, cnt)
+    assert np.array_equal(rows2[:cnt].cpu().numpy(), np.nonzero(bits_a)[0].astype(np.int32))
     d2 = da.clone()
     ctx.bitmap_or(d2, db, n)
     if n:  # whole words are combined; n == 0 touches nothing
