@@ -3,10 +3,11 @@
 // Compared with the generic float64 kernel: a node is one 32-bit word instead of 12 bytes and a
 // cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~17 KB of features
 // and 16 warps stay resident per SM.  The forest is streamed through shared memory in chunks of whole
-// trees by the TMA engine (cp.async.bulk, double buffered).  A producer warp issues the copies and the
-// consumer warps hand buffers back through mbarriers (full / empty per buffer), so no CTA-wide barrier
-// sits in the loop: a warp may run up to a chunk ahead of the slowest one, which is what keeps the
-// shared-memory pipe busy when only one CTA fits an SM.  Each thread walks kIlp trees at a time for a fixed number of levels.  The kernel is bound
+// trees by the TMA engine (cp.async.bulk into a ring of four buffers).  A warp waits on the buffer's
+// mbarrier for the chunk to land and counts itself out when it is done with it; the last warp out
+// starts the copy of the chunk four positions ahead -- no CTA-wide barrier in the loop, no producer
+// thread polling (a first version with a dedicated producer warp spent 16 % of the issue slots in its
+// wait loop), and a warp may run up to three chunks ahead of the slowest one.  Each thread walks kIlp trees at a time for a fixed number of levels.  The kernel is bound
 // by shared-memory wavefronts (two loads per level: rank byte, node word), so everything else is
 // squeezed out of the level: the node word is carry coded (word + rank overflows into the child index
 // exactly when the row goes right; siblings are adjacent), child indices are absolute within the
@@ -49,9 +50,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -109,51 +107,46 @@ struct __align__(16) ChunkBuf {
     uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, first leaf), chunk relative
 };
 
-constexpr int kProducerThreads = 32;  // one extra warp: lane 0 drives the TMA engine
+constexpr int kStages = 4;  // chunk buffers in flight per CTA
 
 template <bool kWide, int T, int kIlp>
-__global__ void __launch_bounds__(T + kProducerThreads, kWide ? 1 : 2)
+__global__ void __launch_bounds__(T, kWide ? 1 : 2)
 k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const dr_forest_ranked& F = p.f;
-    ChunkBuf* buf = reinterpret_cast<ChunkBuf*>(smem_raw);                       // two chunk buffers
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(ChunkBuf));  // chunk landed (per buffer)
-    uint64_t* empty = full + 2;                                                  // every consumer warp left it
-    unsigned char* s_feat = smem_raw + 2 * sizeof(ChunkBuf) + 32;
+    ChunkBuf* buf = reinterpret_cast<ChunkBuf*>(smem_raw);                                // kStages chunk buffers
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * sizeof(ChunkBuf));  // chunk landed (per buffer)
+    uint32_t* done = reinterpret_cast<uint32_t*>(full + kStages);                         // warps that left the buffer
+    unsigned char* s_feat = smem_raw + kStages * sizeof(ChunkBuf) + kStages * 16;
     const int t = threadIdx.x;
     const int depth = F.max_depth;
-    if (t == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], T / 32);
-        mbar_init(&empty[1], T / 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();  // the only CTA-wide barrier: from here on warps synchronise through the mbarriers
+    // the CTA's chunk stream: every tile it owns walks chunks 0 .. n_chunks - 1; chunk k of the stream
+    // lives in buffer k % kStages
+    const int64_t first = (int64_t)blockIdx.x * T, step = (int64_t)gridDim.x * T;
+    const uint32_t n_tiles = first < p.n_cells ? (uint32_t)((p.n_cells - first + step - 1) / step) : 0u;
+    const uint32_t n_stream = n_tiles * (uint32_t)F.n_chunks;
 
-    if (t >= T) {  // ---- producer warp: chunk k of the CTA's stream goes to buffer k & 1 ----
-        if (t != T) return;
-        uint32_t k = 0;
-        for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
-            for (int c = 0; c < F.n_chunks; ++c, ++k) {
-                const int b = k & 1;
-                if (k >= 2) {  // wait until the previous tenant of this buffer (chunk k - 2) was released
-                    const uint32_t parity = ((k >> 1) - 1) & 1;
-                    while (!mbar_try_wait(&empty[b], parity)) __nanosleep(256);  // do not steal issue slots
-                }
-                const int n0 = F.chunk_node_off[c], n1 = F.chunk_node_off[c + 1];
-                const int l0 = F.chunk_leaf_off[c], l1 = F.chunk_leaf_off[c + 1];
-                const int h0 = F.chunk_hdr_off[c], h1 = F.chunk_hdr_off[c + 1];
-                const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u,
-                               hb = (uint32_t)(h1 - h0) * 8u;
-                mbar_expect_tx(&full[b], nb + lb + hb);
-                bulk_g2s(buf[b].node, F.node_word + n0, nb, &full[b]);
-                bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &full[b]);
-                bulk_g2s(buf[b].hdr, F.tree_hdr + 2 * (size_t)h0, hb, &full[b]);
-            }
+    auto issue = [&](uint32_t k) {  // one thread: start the TMA copies of stream chunk k
+        const int c = (int)(k % (uint32_t)F.n_chunks), b = (int)(k % kStages);
+        const int n0 = F.chunk_node_off[c], n1 = F.chunk_node_off[c + 1];
+        const int l0 = F.chunk_leaf_off[c], l1 = F.chunk_leaf_off[c + 1];
+        const int h0 = F.chunk_hdr_off[c], h1 = F.chunk_hdr_off[c + 1];
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u, hb = (uint32_t)(h1 - h0) * 8u;
+        mbar_expect_tx(&full[b], nb + lb + hb);
+        bulk_g2s(buf[b].node, F.node_word + n0, nb, &full[b]);
+        bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &full[b]);
+        bulk_g2s(buf[b].hdr, F.tree_hdr + 2 * (size_t)h0, hb, &full[b]);
+    };
+
+    if (t == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            done[s] = 0;
         }
-        return;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t k = 0; k < (uint32_t)kStages && k < n_stream; ++k) issue(k);
     }
+    __syncthreads();  // the only CTA-wide barrier: from here on warps meet through the mbarriers / counters
 
     // ---- consumer warps: one cell per thread; the feature tile is private to the thread ----
     unsigned char* my_feat = kWide ? s_feat + 4 * t : s_feat + (size_t)t * p.feat_stride;
@@ -206,7 +199,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         double best = 0.0, margin0 = 0.0, acc = F.baseline[0];
         int best_s = 0, cur_s = 0;
         for (int c = 0; c < F.n_chunks; ++c, ++k) {
-            const int b = k & 1;
+            const int b = (int)(k % kStages);
             const int s = F.chunk_seq[c];
             if (s != cur_s) {  // previous sequence is complete
                 if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
@@ -215,7 +208,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 cur_s = s;
                 acc = F.baseline[s];
             }
-            while (!mbar_try_wait(&full[b], (k >> 1) & 1)) __nanosleep(32);
+            while (!mbar_try_wait(&full[b], (k / kStages) & 1)) {}
             const uint32_t nodes = smem_u32(buf[b].node);
             const double* __restrict__ leaves = buf[b].leaf;
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
@@ -259,8 +252,20 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
 #pragma unroll
             for (int j = 0; j < kIlp; ++j)  // the chunk's last group
                 if (j < n_pend) acc += pend[j];
+            // this warp is done with buffer b; the last warp to leave refills it with stream chunk
+            // k + kStages (no producer thread, nobody polls)
             __syncwarp();
-            if ((t & 31) == 0) mbar_arrive(&empty[b]);  // this warp is done with buffer b
+            if ((t & 31) == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done[b], 1u) == (uint32_t)(T / 32 - 1)) {
+                    done[b] = 0;
+                    __threadfence_block();
+                    if (k + kStages < n_stream) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(k + kStages);
+                    }
+                }
+            }
         }
         if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
         if (cur_s == 0) { best = acc; margin0 = acc; }
@@ -301,11 +306,11 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     p.out_margin = out_margin;
     // a leaf's self-loop reads (and ignores) the rank slot named by its leaf number: the byte tile is
     // padded by 256 bytes for that, the wide tile is only used when every leaf number is a valid slot
-    const size_t fixed = 2 * sizeof(ChunkBuf) + 32;
+    const size_t fixed = kStages * sizeof(ChunkBuf) + kStages * 16;
     constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
     const int n_slots = 2 * f.n_feat > 0 ? 2 * f.n_feat : 1;
     DR_REQUIRE(ctx, f.max_tree_leaves >= 1 && f.max_tree_leaves <= 256, "bad max_tree_leaves");
-    DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 4, "bad layout");
+    DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 3, "bad layout");
     const size_t smem_512 = fixed + (size_t)n_slots * 512 * 4, smem_256 = fixed + (size_t)n_slots * 256 * 4;
     const bool leaves_ok = f.max_tree_leaves <= n_slots;
     const bool wide_ok = leaves_ok && smem_256 <= kMaxSmem;
@@ -314,7 +319,7 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     auto launch = [&](auto kernel, int threads, size_t smem, int per_sm) -> int {
         DR_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = dr_grid_for(ctx, n_cells, threads, per_sm);
-        kernel<<<grid, threads + kProducerThreads, smem, (cudaStream_t)stream>>>(p);
+        kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
         return DR_OK;
     };
     if (wide_ok && f.layout != 1) {
@@ -322,7 +327,6 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
         int rc;
         if (smem_512 <= kMaxSmem) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
         else if (f.layout == 2)     rc = launch(k_forest_predict_ranked<true, 256, 8>, 256, smem_256, 1);
-        else if (f.layout == 4)     rc = launch(k_forest_predict_ranked<true, 256, 32>, 256, smem_256, 1);
         else                        rc = launch(k_forest_predict_ranked<true, 256, 16>, 256, smem_256, 1);
         if (rc != DR_OK) return rc;
     } else {

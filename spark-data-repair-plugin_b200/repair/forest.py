@@ -230,7 +230,7 @@ def rank_code(spec, dict_sizes):
 
 
 # DR_RANKED_CHUNK_* in include/b200repair.h
-RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 4096, 2176, 256, 32
+RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 2048, 1088, 128, 16
 
 
 def ranked_image(rk, order, seq_tree_off):
@@ -375,9 +375,9 @@ class DeviceModel:
             r = dr_forest_ranked()
             r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, len(img["word"]), len(img["leaf"])
             r.n_feat, r.max_depth, r.n_chunks = n_feat, int(rk["max_depth"]), len(img["chunk_seq"])
-            # DR_RANKED_LAYOUT=bytes|wide8|wide16|wide32 pins the shared-memory feature tile (profiling aid)
+            # DR_RANKED_LAYOUT=bytes|wide8|wide16 pins the shared-memory feature tile (profiling aid)
             r.max_tree_leaves = int(rk["max_tree_leaves"])
-            r.layout = {"": 0, "bytes": 1, "wide8": 2, "wide16": 3, "wide32": 4}[os.environ.get("DR_RANKED_LAYOUT", "")]
+            r.layout = {"": 0, "bytes": 1, "wide8": 2, "wide16": 3}[os.environ.get("DR_RANKED_LAYOUT", "")]
             for field, key in (("chunk_tree_off", "r_chunk_tree_off"), ("chunk_seq", "r_chunk_seq"),
                                ("chunk_node_off", "r_chunk_node_off"), ("chunk_leaf_off", "r_chunk_leaf_off"),
                                ("chunk_hdr_off", "r_chunk_hdr_off"), ("tree_hdr", "r_tree_hdr"),

@@ -450,8 +450,8 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
     want_m, want = forest_margins(forest, X), forest_predict(forest, X)
     assert dm.ranked.max_tree_leaves <= 2 * n_feat          # so that the wide feature tile is exercised too
     assert (n_feat > 37) == bool(extra) and n_feat <= 75
-    for variant in ("auto", "bytes", "wide8", "wide16", "wide32", "generic"):
-        dm.ranked.layout = {"auto": 0, "bytes": 1, "wide8": 2, "wide16": 3, "wide32": 4, "generic": 0}[variant]
+    for variant in ("auto", "bytes", "wide8", "wide16", "generic"):
+        dm.ranked.layout = {"auto": 0, "bytes": 1, "wide8": 2, "wide16": 3, "generic": 0}[variant]
         tile = dev(tile_np)
         margins = torch.empty((len(cells), dm.n_seq), dtype=torch.float64, device="cuda")
         dm.predict(ctx, tile, k, None, 0, dev(cells), len(cells), 0, margins, force_generic=variant == "generic")
