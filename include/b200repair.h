@@ -290,9 +290,9 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  *   leaf_value[chunk_leaf_off[c] ..), its tree headers tree_hdr[2 * chunk_hdr_off[c] ..): two words
  *   per tree = (root node word, first leaf value of the tree relative to the chunk).  chunk_node_off
  *   is a multiple of 4, chunk_leaf_off and chunk_hdr_off multiples of 2 (16-byte TMA granules). */
-#define DR_RANKED_CHUNK_NODES 2048
-#define DR_RANKED_CHUNK_LEAVES 1088
-#define DR_RANKED_CHUNK_TREES 128
+#define DR_RANKED_CHUNK_NODES 4096
+#define DR_RANKED_CHUNK_LEAVES 2176
+#define DR_RANKED_CHUNK_TREES 256
 typedef struct dr_forest_ranked {
     int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth, n_chunks;
     int32_t max_tree_leaves; /* most leaves of any tree (1..256) */

@@ -3,11 +3,11 @@
 // Compared with the generic float64 kernel: a node is one 32-bit word instead of 12 bytes and a
 // cell's features are two bytes each instead of eight, so a CTA of 256 cells needs ~17 KB of features
 // and 16 warps stay resident per SM.  The forest is streamed through shared memory in chunks of whole
-// trees by the TMA engine (cp.async.bulk into a ring of four buffers).  A warp waits on the buffer's
-// mbarrier for the chunk to land and counts itself out when it is done with it; the last warp out
-// starts the copy of the chunk four positions ahead -- no CTA-wide barrier in the loop, no producer
-// thread polling (a first version with a dedicated producer warp spent 16 % of the issue slots in its
-// wait loop), and a warp may run up to three chunks ahead of the slowest one.  Each thread walks kIlp trees at a time for a fixed number of levels.  The kernel is bound
+// trees by the TMA engine (cp.async.bulk, double buffered).  A warp waits on the buffer's mbarrier for
+// the chunk to land and counts itself out when it is done with it; the last warp out starts the copy
+// of the chunk two positions ahead -- no CTA-wide barrier in the loop and no producer thread polling
+// (a version with a dedicated producer warp spent 16 % of the issue slots in its wait loop; a ring of
+// four half-size chunks was slower: the per-chunk bookkeeping doubles).  Each thread walks kIlp trees at a time for a fixed number of levels.  The kernel is bound
 // by shared-memory wavefronts (two loads per level: rank byte, node word), so everything else is
 // squeezed out of the level: the node word is carry coded (word + rank overflows into the child index
 // exactly when the row goes right; siblings are adjacent), child indices are absolute within the
@@ -107,7 +107,7 @@ struct __align__(16) ChunkBuf {
     uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, first leaf), chunk relative
 };
 
-constexpr int kStages = 4;  // chunk buffers in flight per CTA
+constexpr int kStages = 2;  // chunk buffers in flight per CTA
 
 template <bool kWide, int T, int kIlp>
 __global__ void __launch_bounds__(T, kWide ? 1 : 2)
@@ -198,10 +198,19 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         }
         double best = 0.0, margin0 = 0.0, acc = F.baseline[0];
         int best_s = 0, cur_s = 0;
+        // The leaf values of a group are only added (in tree order: bit-identical float64 sums) while
+        // the NEXT group -- possibly of the next chunk -- walks its first level, so that the serial DADD
+        // chain hides behind shared-memory latency instead of idling the warp.
+        double pend[kIlp];
+        int n_pend = 0;
         for (int c = 0; c < F.n_chunks; ++c, ++k) {
             const int b = (int)(k % kStages);
             const int s = F.chunk_seq[c];
             if (s != cur_s) {  // previous sequence is complete
+#pragma unroll
+                for (int j = 0; j < kIlp; ++j)
+                    if (j < n_pend) acc += pend[j];
+                n_pend = 0;
                 if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
                 if (cur_s == 0) { best = acc; margin0 = acc; }
                 else if (acc > best) { best = acc; best_s = cur_s; }
@@ -213,11 +222,6 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             const double* __restrict__ leaves = buf[b].leaf;
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
-            // The leaf values of a group are only added (in tree order: bit-identical float64 sums)
-            // while the NEXT group walks its first level, so that the serial DADD chain hides behind
-            // shared-memory latency instead of idling the warp.
-            double pend[kIlp];
-            int n_pend = 0;
             for (int q = 0; q < n_trees; q += kIlp) {
                 uint32_t w[kIlp], lb[kIlp];
 #pragma unroll
@@ -249,9 +253,6 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (w[j] >> 24)];
                 n_pend = n_trees - q < kIlp ? n_trees - q : kIlp;
             }
-#pragma unroll
-            for (int j = 0; j < kIlp; ++j)  // the chunk's last group
-                if (j < n_pend) acc += pend[j];
             // this warp is done with buffer b; the last warp to leave refills it with stream chunk
             // k + kStages (no producer thread, nobody polls)
             __syncwarp();
@@ -267,6 +268,9 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j)  // the last group of the last sequence
+            if (j < n_pend) acc += pend[j];
         if (live && p.out_margin) p.out_margin[i * F.n_seq + cur_s] = acc;
         if (cur_s == 0) { best = acc; margin0 = acc; }
         else if (acc > best) { best = acc; best_s = cur_s; }

@@ -230,7 +230,7 @@ def rank_code(spec, dict_sizes):
 
 
 # DR_RANKED_CHUNK_* in include/b200repair.h
-RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 2048, 1088, 128, 16
+RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 4096, 2176, 256, 16
 
 
 def ranked_image(rk, order, seq_tree_off):
