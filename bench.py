@@ -229,6 +229,8 @@ def b200_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as td
+        # NCCL's own log lines (e.g. "NCCL version ...") belong on stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=device)
         dist = Dist()
     n, k = args.rows, args.cols
