@@ -507,3 +507,97 @@ def test_misc_repair_applies_updates_like_the_reference():
         delphi.misc.options({"repair_updates": "inputView", "table_name": "inputView", "row_id": "tid"}).repair()
     with pytest.raises(ValueError, match="Required options not found: repair_updates, table_name, row_id"):
         delphi.misc.option("table_name", "inputView").repair()
+
+
+def test_regex_structure_repair_matches_the_oracle_on_random_patterns():
+    """Product scanner (repair/regex_structure.py) vs the oracle's restatement of RegexBase.g4 +
+    RegexStructureRepair.scala: same tokens, same verdict (lexer error / outside the grammar / ok),
+    same repaired strings -- on the reference's patterns and on random ones."""
+    import random
+    import re
+    from oracle.regex_repair import RegexStructureRepair as Oracle
+    from oracle.regex_repair import lex
+    from repair.regex_structure import LexError, StructureRepair, tokenize
+    rnd = random.Random(1)
+    pats = ["^[0-9]{1,3} patients$", "^[0-9]{1,3}%", "^[0-9]{2}-[0-9]{2}-[0-9]{2}-[0-9]{2}$", "[a-z]{2,}[0-9]{,3}xy",
+            "^ab[0-9]{2}.*cd$", "[a-c0-9A-Z]{3}--[x]{1}%", "ab|cd[0-9]{1}", "[0-9]+ab", "^[0-9]{1,", "a{2}bc",
+            "x[0-9]{2}", "[a-b-c]{2}zz", "[0-9]{2}?ab", "", "^$", "[z-a]{2}ab"]
+    alphabet = "ab0-9[]{},^$ %-xyz.*+?|"
+    pats += ["".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 10))) for _ in range(1500)]
+    vals = ["32 patxxnts", "1xx patients", "23.39.23.11", "ab12zzcd", "aa123xy", "9AZ--x%", "ab", "cd5", "55ab", "xx", ""]
+    n_ok = 0
+    for p in pats:
+        try:
+            want_tokens = [t[1] for t in lex(p)]
+        except ValueError:
+            want_tokens = None
+        try:
+            got_tokens = [t[1] for t in tokenize(p)]
+        except LexError:
+            got_tokens = None
+        assert got_tokens == want_tokens, p
+
+        def verdict(make):
+            try:
+                return make(p), "ok"
+            except NotImplementedError:
+                return None, "outside the grammar"
+            except re.error:
+                return None, "does not compile"
+            except ValueError:
+                return None, "lexer error"
+        o, ov = verdict(Oracle)
+        g, gv = verdict(StructureRepair)
+        assert ov == gv, (p, ov, gv)
+        if o is not None:
+            n_ok += 1
+            assert [o(v) for v in vals] == [g(v) for v in vals], p
+    assert n_ok > 50
+
+
+def test_nearest_value_lut_and_functional_deps_host_logic(tmp_path):
+    """Host halves of the rule-based repairs against the oracle (no GPU involved)."""
+    from oracle import repair as OR
+    from oracle.table import from_rows
+    from repair import RepairModel
+    from repair import rules as RU
+    from repair.costs import Levenshtein
+    from repair.errors import ConstraintErrorDetector, NullErrorDetector
+    from repair.table import EncodedTable
+    import pandas as pd
+    df = pd.DataFrame({"tid": [1, 3, 4, 5, 6], "v0": ["100%", "32%", "1xx%", "100x", "12x"],
+                       "v1": [100, 101, 1, 2, 300], "v2": ["a", "b", "a", "b", "a"]})
+    enc = EncodedTable.from_pandas(df, "tid")
+    # v0: error cells 1xx% / 100x / 12x, domain {100%, 32%}
+    col = enc.by_name["v0"]
+    cur = [col.code_of(v) for v in ("1xx%", "100x", "12x")]
+    dom = [col.code_of(v) for v in ("100%", "32%")]
+    lut = RU.nearest_value_lut(col, cur, dom, Levenshtein(), 2.0)
+    assert [col.dictionary[lut[c + 1]] for c in cur] == ["100%", "100%", "32%"] and (lut >= 0).sum() == 3
+    # v1 (integers): 101 -> 100, 2 -> 1, 300 -> 100; a zero in the domain has a NULL cost (costs.py:33-34)
+    col = enc.by_name["v1"]
+    cur = [col.code_of(v) for v in (101, 2, 300)]
+    lut = RU.nearest_value_lut(col, cur, [col.code_of(100), col.code_of(1)], Levenshtein(), 2.0)
+    assert [int(col.dictionary[lut[c + 1]]) for c in cur] == [100, 1, 100]
+    # ties and far values repair nothing
+    col = enc.by_name["v2"]
+    assert (RU.nearest_value_lut(col, [0], [0, 1], Levenshtein(), 0.5) >= 0).sum() == 1      # 'a' itself, cost 0
+    assert (RU.nearest_value_lut(enc.by_name["v0"], [enc.by_name["v0"].code_of("12x")], dom, Levenshtein(), 1.0)
+            >= 0).sum() == 0
+    # functional dependencies: same map as the oracle (DepGraphSuite.scala:230-266)
+    import os
+    from conftest import GOLDEN
+    hosp = pd.read_csv(os.path.join(GOLDEN, "hospital.csv"), dtype=str).astype({"tid": int})
+    henc = EncodedTable.from_pandas(hosp, "tid")
+    rm = RepairModel()
+    rm.setRepairByRules(True)
+    path = os.path.join(GOLDEN, "hospital_constraints.txt")
+    rm.setErrorDetectors([NullErrorDetector(), ConstraintErrorDetector(path, "City->ZipCode")])
+    targets = ["HospitalOwner", "Condition", "CountyName", "HospitalName", "EmergencyService", "ZipCode", "MeasureCode"]
+    assert RU.functional_deps(rm, henc, targets) == OR.functional_deps(henc.names, path, "City->ZipCode", targets)
+    rm.option("model.rule.repair_by_functional_deps.disabled", "1")
+    assert RU.functional_deps(rm, henc, targets) is None
+    order = RU.resolve_prediction_order([("a", ("fd", "b")), ("b", ("fd", "c")), ("c", ("forest",)), ("d", ("fd", "z"))],
+                                        ["a", "b", "c", "d"])
+    assert [y for y, _ in order] == ["c", "b", "d", "a"]
+    del from_rows, tmp_path
