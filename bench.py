@@ -460,7 +460,10 @@ def b200_arm(args):
     if host is not None:
         e_ms, _, _, _ = timed(True, max(1, min(args.steps, 3)), 1)
         line["e2e"] = {"value": total_rows / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
-                       "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(stats["d2h"])}
+                       "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(stats["d2h"]),
+                       "note": "every step copies its byte codes from pinned host memory (copy stream, double "
+                               "buffered: the copy of step i+1 overlaps the compute of step i) and reads its "
+                               "result frame back; whole-span device time / steps"}
 
     # ---- CPU baseline (rank 0, single GPU run only) -----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
