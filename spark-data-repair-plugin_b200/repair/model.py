@@ -53,6 +53,8 @@ def _as_encoded(obj, row_id, name="input"):
         return obj
     if _is_spark_df(obj):
         obj = obj.toPandas()
+    if type(obj).__module__.startswith("pyarrow") and hasattr(obj, "schema"):
+        return EncodedTable.from_arrow(obj, row_id, name)
     return EncodedTable.from_pandas(obj, row_id, name)
 
 
@@ -116,6 +118,16 @@ class RepairModel():
         else:
             self.db_name = ""
             self.input = input
+        return self
+
+    def setArrowInput(self, table: Any) -> "RepairModel":
+        """A ``pyarrow.Table`` as input (``spark_df.toArrow()``, ``pyarrow.parquet.read_table(path,
+        read_dictionary=[...])``): dictionary-encoded by Arrow, no Python object per cell
+        (EncodedTable.from_arrow).  ``setInput`` keeps the reference's str / DataFrame contract."""
+        if not (type(table).__module__.startswith("pyarrow") and hasattr(table, "schema")):
+            raise TypeError("`table` should be provided as pyarrow.Table, got {}".format(type(table).__name__))
+        self.db_name = ""
+        self.input = table
         return self
 
     def setEncodedInput(self, table: EncodedTable) -> "RepairModel":

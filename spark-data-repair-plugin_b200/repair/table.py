@@ -161,6 +161,84 @@ class EncodedTable:
         return cls(row_id, df[row_id].to_numpy(), kinds[row_id], cols, name)
 
     @classmethod
+    def from_arrow(cls, tbl, row_id, name="input"):
+        """Same gate and encoding as from_pandas for a ``pyarrow.Table`` (what ``spark_df.toArrow()`` or
+        ``pyarrow.parquet.read_table(path, read_dictionary=[...])`` return), without a Python object
+        per cell: strings are dictionary-encoded by Arrow's C++ kernels -- columns that already arrive
+        dictionary-encoded (Parquet dictionary pages) are NOT decoded first -- and only the
+        dictionaries (one entry per distinct value) are sorted and turned into Python strings."""
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        if row_id not in tbl.column_names:
+            raise AnalysisException("Column '{}' does not exist in table '{}'".format(row_id, name))
+        kinds, bad = {}, []
+        for f in tbl.schema:
+            t = f.type.value_type if pa.types.is_dictionary(f.type) else f.type
+            if pa.types.is_boolean(t):
+                bad.append("boolean")
+            elif pa.types.is_integer(t):
+                kinds[f.name] = "int"
+            elif pa.types.is_floating(t):
+                kinds[f.name] = "float"
+            elif pa.types.is_string(t) or pa.types.is_large_string(t):
+                kinds[f.name] = "str"
+            elif pa.types.is_timestamp(t):
+                bad.append("timestamp")
+            elif pa.types.is_date(t):
+                bad.append("date")
+            else:
+                bad.append(str(t))
+        if bad:
+            raise AnalysisException("Supported types are {}, but unsupported ones found: {}".format(
+                _SUPPORTED_MSG, ",".join(bad)))
+        if not tbl.num_columns >= 3:
+            raise AnalysisException("A least three columns (`{}` columns + two more ones) in table '{}'".format(
+                row_id, name))
+        n_distinct = int(pc.count_distinct(tbl[row_id], mode="all").as_py())
+        if n_distinct != tbl.num_rows:
+            raise AnalysisException(
+                "Uniqueness does not hold in column '{}' of table '{}' (# of distinct '{}': {}, # of rows: {})".format(
+                    row_id, name, row_id, n_distinct, tbl.num_rows))
+
+        def plain(col):
+            col = col.unify_dictionaries() if pa.types.is_dictionary(col.type) else col
+            return col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
+
+        cols = []
+        for f in tbl.schema:
+            if f.name == row_id:
+                continue
+            arr = plain(tbl[f.name])
+            if kinds[f.name] != "str":
+                if pa.types.is_dictionary(arr.type):
+                    arr = arr.dictionary_decode()
+                vals = pc.cast(arr, pa.float64()).to_numpy(zero_copy_only=False)
+                cols.append(_encode_numeric(f.name, kinds[f.name], np.asarray(vals, dtype=np.float64)))
+                continue
+            if not pa.types.is_dictionary(arr.type):
+                arr = pc.dictionary_encode(arr)
+            idx = arr.indices
+            valid = np.asarray(idx.is_valid())
+            raw = np.asarray(idx.fill_null(0).to_numpy(zero_copy_only=False), dtype=np.int64)
+            entries = np.array(arr.dictionary.to_pylist(), dtype=object)
+            # a Parquet dictionary page may list values the rows never use: keep what occurs, sorted
+            used = np.zeros(len(entries), dtype=bool)
+            used[raw[valid]] = True
+            used &= np.array([e is not None for e in entries], dtype=bool) if len(entries) else used
+            keep = np.nonzero(used)[0]
+            order = keep[np.argsort(np.array([str(entries[i]) for i in keep], dtype=object), kind="stable")] \
+                if len(keep) else keep
+            rank = np.full(len(entries), -1, dtype=np.int32)
+            rank[order] = np.arange(len(order), dtype=np.int32)
+            codes = np.where(valid, rank[raw], -1).astype(np.int32) if len(entries) else \
+                np.full(len(raw), -1, dtype=np.int32)
+            cols.append(Column(f.name, "str", np.array([str(entries[i]) for i in order], dtype=object), codes, None))
+        ids = plain(tbl[row_id])
+        if pa.types.is_dictionary(ids.type):
+            ids = ids.dictionary_decode()
+        return cls(row_id, np.asarray(ids.to_numpy(zero_copy_only=False)), kinds[row_id], cols, name)
+
+    @classmethod
     def from_codes(cls, row_id, names, codes, dict_sizes, name="input", row_ids=None, dictionaries=None):
         """Pre-encoded discrete table (already label-encoded upstream, e.g. Arrow dictionary pages
         or the synthetic generator): ``codes[k]`` int32, -1 = NULL; value c of column k prints as
@@ -284,4 +362,30 @@ class ByteStager:
         self.consumed[j].record(main)
         self.pending[j] = False
         self.n += 1
+
+
+def cells_to_arrow(table, cells):
+    """Egress without a Python string per cell: the (row id, attribute, current_value, repaired) frame of
+    encoded repair output ``[(attr, row positions, current codes, repaired codes)]`` as a pyarrow.Table
+    whose string columns are dictionary arrays over the column dictionaries (one chunk per attribute)."""
+    import pyarrow as pa
+    names = [a for a, _, _, _ in cells]
+    ids, attr_idx, cur, rep = [], [], [], []
+    for i, (a, rows, c, r) in enumerate(cells):
+        col = table.by_name[a]
+        if col.kind != "str":
+            raise NotImplementedError("cells_to_arrow takes discrete attributes (dictionary codes)")
+        strs = pa.array(col.strings(), type=pa.string())
+        ids.append(pa.array(table.row_ids[np.asarray(rows, dtype=np.int64)]))
+        attr_idx.append(np.full(len(rows), i, dtype=np.int32))
+        for codes, out in ((c, cur), (r, rep)):
+            codes = np.asarray(codes, dtype=np.int32)
+            out.append(pa.DictionaryArray.from_arrays(pa.array(codes, mask=codes < 0), strs))
+    if not cells:
+        empty = pa.array([], type=pa.string())
+        return pa.table({table.row_id: pa.array(table.row_ids[:0]), "attribute": empty, "current_value": empty,
+                         "repaired": empty})
+    attribute = pa.DictionaryArray.from_arrays(pa.array(np.concatenate(attr_idx)), pa.array(names, type=pa.string()))
+    return pa.table({table.row_id: pa.chunked_array(ids), "attribute": attribute,
+                     "current_value": pa.chunked_array(cur), "repaired": pa.chunked_array(rep)})
 

@@ -329,3 +329,14 @@ def test_repair_by_regex_structure_parity():
     assert len(fixed) >= 40 and all(g[3] == g[2].replace("ixxts", "ients") for g in fixed)
     assert any(g[2] is not None and g[2].startswith("x") for g in got)               # left to the statistical model
     assert info["rm"].last_run["detect"].n_cells["sample"] < len([g for g in got if g[1] == "sample"])
+
+
+def test_arrow_input_gives_the_same_repairs_as_pandas_input():
+    import pyarrow as pa
+    from repair import NullErrorDetector, RepairModel
+    df = adult()
+    want = RepairModel().setInput(df).setRowId("tid").setErrorDetectors([NullErrorDetector()]) \
+        .option("model.lgb.n_estimators", "30").run()
+    got = RepairModel().setArrowInput(pa.Table.from_pandas(df, preserve_index=False)).setRowId("tid") \
+        .setErrorDetectors([NullErrorDetector()]).option("model.lgb.n_estimators", "30").run()
+    assert PU.frame_tuples(got, "tid") == PU.frame_tuples(want, "tid") and len(got) == 7

@@ -601,3 +601,60 @@ def test_nearest_value_lut_and_functional_deps_host_logic(tmp_path):
                                         ["a", "b", "c", "d"])
     assert [y for y, _ in order] == ["c", "b", "d", "a"]
     del from_rows, tmp_path
+
+
+def test_arrow_ingest_matches_pandas_ingest_and_arrow_egress(tmp_path):
+    """EncodedTable.from_arrow (plain, chunked and Parquet-dictionary-page input) == from_pandas on the
+    reference's fixtures; cells_to_arrow decodes like Column.decode."""
+    import pandas as pd
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from conftest import GOLDEN
+    from repair import RepairModel
+    from repair.table import EncodedTable, cells_to_arrow
+    from repair.utils import AnalysisException
+
+    def same(a, b):
+        assert a.names == b.names and np.array_equal(a.row_ids, b.row_ids) and a.row_id_kind == b.row_id_kind
+        for ca, cb in zip(a.columns, b.columns):
+            assert ca.kind == cb.kind and list(ca.dictionary) == list(cb.dictionary), ca.name
+            assert np.array_equal(ca.codes, cb.codes), ca.name
+            assert (ca.values is None) == (cb.values is None)
+            if ca.values is not None:
+                assert np.array_equal(ca.values, cb.values, equal_nan=True)
+
+    for name in ("adult.csv", "hospital.csv", "boston.csv"):
+        df = pd.read_csv(os.path.join(GOLDEN, name), dtype=str if name == "hospital.csv" else None)
+        if name == "hospital.csv":
+            df = df.astype({"tid": int})
+        want = EncodedTable.from_pandas(df, "tid")
+        t = pa.Table.from_pandas(df, preserve_index=False)
+        same(EncodedTable.from_arrow(t, "tid"), want)
+        path = str(tmp_path / (name + ".parquet"))
+        pq.write_table(t, path, row_group_size=max(len(df) // 3, 1))
+        strs = [f.name for f in t.schema if pa.types.is_string(f.type) or pa.types.is_large_string(f.type)]
+        t2 = pq.read_table(path, read_dictionary=strs)                       # dictionary pages, several chunks
+        assert not strs or any(pa.types.is_dictionary(f.type) for f in t2.schema)
+        same(EncodedTable.from_arrow(t2, "tid"), want)
+    # the type gate and the row-id check speak like checkInputTable (RepairApi.scala:34-67)
+    bad = pa.table({"tid": [1, 2], "x": [True, False], "y": ["a", "b"]})
+    with pytest.raises(AnalysisException, match="unsupported ones found: boolean"):
+        EncodedTable.from_arrow(bad, "tid")
+    with pytest.raises(AnalysisException, match="Uniqueness does not hold in column 'tid'"):
+        EncodedTable.from_arrow(pa.table({"tid": [1, 1], "x": ["a", "b"], "y": ["a", "b"]}), "tid")
+    assert RepairModel().setArrowInput(t).input is t
+    with pytest.raises(TypeError, match="should be provided as str/DataFrame"):
+        RepairModel().setInput(t)
+    # egress: dictionary arrays over the column dictionaries
+    enc = EncodedTable.from_pandas(pd.read_csv(os.path.join(GOLDEN, "adult.csv")), "tid")
+    cells = [("Sex", np.array([3, 7, 12]), np.array([-1, -1, 0], dtype=np.int32), np.array([1, 0, -1], dtype=np.int32)),
+             ("Age", np.array([5]), np.array([-1], dtype=np.int32), np.array([2], dtype=np.int32))]
+    frame = cells_to_arrow(enc, cells)
+    assert pa.types.is_dictionary(frame.schema.field("repaired").type)
+    got = frame.to_pylist()
+    sex, age = enc.by_name["Sex"].strings(), enc.by_name["Age"].strings()
+    assert got == [{"tid": enc.row_ids[3], "attribute": "Sex", "current_value": None, "repaired": sex[1]},
+                   {"tid": enc.row_ids[7], "attribute": "Sex", "current_value": None, "repaired": sex[0]},
+                   {"tid": enc.row_ids[12], "attribute": "Sex", "current_value": sex[0], "repaired": None},
+                   {"tid": enc.row_ids[5], "attribute": "Age", "current_value": None, "repaired": age[2]}]
+    assert cells_to_arrow(enc, []).num_rows == 0
