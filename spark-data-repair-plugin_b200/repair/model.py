@@ -280,6 +280,12 @@ class RepairModel():
             raise ValueError("Cannot enable the maximal likelihood repair mode when continous attributes found")
         if self.targets and len(set(self.targets) & (set(table.names) | {table.row_id})) == 0:
             raise ValueError("Target attributes not found in {}: {}".format(input_name, to_list_str(self.targets)))
+        if self.training_data_rebalancing_enabled:
+            # train.py:242-290 over/under-samples with imbalanced-learn's SMOTEN, which this build does not
+            # carry; silently training on unbalanced data would not be what was asked for
+            raise NotImplementedError("training data rebalancing needs imbalanced-learn (SMOTEN), which is not "
+                                      "available; `class_weight=balanced` (model.lgb.class_weight) is applied "
+                                      "by default instead")
         err_opts = ErrorModelOptions.resolve(self.opts)
         validate_options(self.opts)
         for key in _MODEL_OPT:
