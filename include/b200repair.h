@@ -109,6 +109,13 @@ int dr_dc_fd_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* s
 int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
                   int64_t n_rows, int64_t key_space, const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap,
                   void* stream);
+/* Two-tuple DC  EQ(a_1)..EQ(a_m) & LT(t1.x, t2.x): a row is matched iff another row of its NULL-safe key
+ * group has a larger x (`<` is never true for NULL).  hi = the max table dr_dc_fd_build makes for b = x;
+ * flags rows with x >= 0 and x + 1 < hi[key].  GT(t1.x, t2.x) is the same test on the reversed codes
+ * x' = dom - 1 - x (NULL kept), which the caller materialises. */
+int dr_dc_lt_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                  const int32_t* x_col, int64_t n_rows, int64_t key_space, const int32_t* hi, uint32_t* row_bitmap,
+                  void* stream);
 
 /* ---- bitmap plumbing (a6: union + distinct of detector outputs, errors.py:405-421) ------------
  * dr_bitmap_or:      dst |= src                                  (n_rows bits)

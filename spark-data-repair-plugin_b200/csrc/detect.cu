@@ -132,6 +132,21 @@ __global__ void __launch_bounds__(kThreads) k_dc_fd_flag(const __grid_constant__
     });
 }
 
+// EQ(a..) & LT(t1.x, t2.x): a row is matched iff some row of its key group has a larger x, i.e. iff
+// x + 1 < max(x + 1) of the group (NULL never compares true: it is neither flagged nor the maximum)
+__global__ void __launch_bounds__(kThreads) k_dc_lt_flag(const __grid_constant__ KeyParams k,
+                                                         const int32_t* __restrict__ x, int64_t n_rows,
+                                                         int64_t key_space, const int32_t* __restrict__ hi,
+                                                         uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        const int v = x[r];
+        if (v < 0) return false;
+        const int64_t key = row_key(k, r);
+        if (key < 0 || key >= key_space) return false;
+        return v + 1 < __ldg(hi + key);
+    });
+}
+
 __global__ void __launch_bounds__(kThreads) k_discretize(const double* __restrict__ vals, int64_t n_rows,
                                                          double vmin, double denom, int thres,
                                                          int32_t* __restrict__ out) {
@@ -291,6 +306,21 @@ int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* st
     if (n_rows <= 0) return DR_OK;
     k_dc_fd_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
         k, n_rows, key_space, lo, hi, row_bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_dc_lt_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                  const int32_t* x_col, int64_t n_rows, int64_t key_space, const int32_t* hi, uint32_t* row_bitmap,
+                  void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, x_col && hi && row_bitmap, "null pointer");
+    KeyParams k;
+    int rc = fill_keys(ctx, &k, key_cols, strides, n_keys);
+    if (rc) return rc;
+    if (n_rows <= 0) return DR_OK;
+    k_dc_lt_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        k, x_col, n_rows, key_space, hi, row_bitmap);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

@@ -64,6 +64,8 @@ _SIGNATURES = {
                                c_void_p, c_void_p]),
     "dr_dc_fd_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_void_p,
                               c_void_p, c_void_p]),
+    "dr_dc_lt_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_void_p, c_int64, c_int64, c_void_p,
+                              c_void_p, c_void_p]),
     "dr_bitmap_or": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dr_bitmap_andnot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dr_bitmap_count": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
@@ -229,6 +231,11 @@ class Context:
         cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
         self._check(self.lib.dr_dc_fd_flag(self._h, cp, _i64_array(strides), len(key_cols), n_rows, key_space,
                                            _dp(lo), _dp(hi), _dp(row_bitmap), self._stream()))
+
+    def dc_lt_flag(self, key_cols, strides, x_col, n_rows, key_space, hi, row_bitmap):
+        cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
+        self._check(self.lib.dr_dc_lt_flag(self._h, cp, _i64_array(strides), len(key_cols), _dp(x_col), n_rows,
+                                           key_space, _dp(hi), _dp(row_bitmap), self._stream()))
 
     # ---- bitmaps ---------------------------------------------------------------------------------
     def bitmap_or(self, dst, src, n_rows):

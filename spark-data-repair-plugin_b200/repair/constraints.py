@@ -7,8 +7,10 @@ Each parsed constraint is classified into the shape the CUDA detectors evaluate:
   CONST     every predicate compares a t1 attribute with a constant      -> dr_dc_const
   FD        EQ(a,a)+ & exactly one IQ(b,b), same attribute on both sides  -> dr_dc_fd_build/flag
   EQ_ONLY   only EQ(a,a) predicates: every row matches itself             -> all rows
-  OTHER     anything else (LT/GT between two tuples, several IQs, cross-attribute predicates):
-            not evaluated on the GPU in this version; raises NotImplementedError at detect time.
+  INEQ      EQ(a,a)* & exactly one LT(b,b) or GT(b,b): "another row of the key group has a larger /
+            smaller b"                                                     -> dr_dc_fd_build + dr_dc_lt_flag
+  OTHER     anything else (several inequalities, several IQs, cross-attribute predicates): not
+            evaluated on the GPU in this version; raises NotImplementedError at detect time.
 """
 import logging
 import re
@@ -137,6 +139,9 @@ def classify(preds):
                 return "FD", (list(dict.fromkeys(eqs)), iqs[0])
             if len(iqs) == 1 and not eqs:
                 return "FD", ([], iqs[0])
+        ineq = [p for p in preds if p.sign in ("LT", "GT")]
+        if len(ineq) == 1 and len(eqs) + 1 == len(preds):
+            return "INEQ", (list(dict.fromkeys(eqs)), ineq[0].sign, ineq[0].left)
     return "OTHER", list(preds)
 
 

@@ -267,6 +267,29 @@ class Engine:
                     self.dist.min_(lo)
                     self.dist.max_(hi)
                 self.ctx.dc_fd_flag(key_cols, strides, self.n_rows, space, lo, hi, rowmask)
+            elif shape == "INEQ":
+                keys, sign, b = payload
+                strides, space = [], 1
+                for k in keys:
+                    strides.append(space)
+                    space *= self.table.by_name[k].dict_size + 1
+                if space > MAX_FD_KEY_SPACE:
+                    raise NotImplementedError(
+                        "denial constraint key space {} exceeds {} (hash-table path not built yet)".format(
+                            space, MAX_FD_KEY_SPACE))
+                x = self.dt.col(b)
+                if sign == "GT":   # "some row has a smaller b" = "some row has a larger reversed code"
+                    dom = self.table.by_name[b].dict_size
+                    x = self.torch.where(x >= 0, dom - 1 - x, x)
+                lo = self.torch.full((space,), 2 ** 31 - 1, dtype=self.torch.int32, device=self.device)
+                hi = self.torch.full((space,), -2 ** 31, dtype=self.torch.int32, device=self.device)
+                key_cols = [self.dt.col(k) for k in keys] or [x]
+                if not keys:
+                    strides = [0]
+                self.ctx.dc_fd_build(key_cols, strides, x, self.n_rows, space, lo, hi)
+                if self.dist is not None:
+                    self.dist.max_(hi)
+                self.ctx.dc_lt_flag(key_cols, strides, x, self.n_rows, space, hi, rowmask)
             elif shape == "EQ_ONLY":
                 rowmask.fill_(-1)
             else:

@@ -340,3 +340,20 @@ def test_arrow_input_gives_the_same_repairs_as_pandas_input():
     got = RepairModel().setArrowInput(pa.Table.from_pandas(df, preserve_index=False)).setRowId("tid") \
         .setErrorDetectors([NullErrorDetector()]).option("model.lgb.n_estimators", "30").run()
     assert PU.frame_tuples(got, "tid") == PU.frame_tuples(want, "tid") and len(got) == 7
+
+
+def test_inequality_denial_constraints_parity():
+    """EQ(keys) & LT / GT(b): "another row of the key group has a larger / smaller b" (the oracle
+    evaluates these by brute force over all row pairs)."""
+    rng = np.random.default_rng(11)
+    n = 600
+    df = pd.DataFrame({"tid": np.arange(n), "a": rng.integers(0, 12, n).astype(str), "g": rng.integers(0, 3, n).astype(str),
+                       "b": rng.integers(0, 30, n), "s": rng.choice(list("pqrstu"), n), "z": rng.integers(0, 5, n).astype(str)})
+    df["a"] = df["a"].where(rng.random(n) > 0.05, None)
+    df["s"] = df["s"].where(rng.random(n) > 0.05, None)
+    df["b"] = df["b"].astype(float).where(rng.random(n) > 0.05, np.nan)
+    for cons in ("t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.b)", "t1&t2&EQ(t1.a,t2.a)&EQ(t1.g,t2.g)&GT(t1.s,t2.s)",
+                 "t1&t2&GT(t1.b,t2.b)&EQ(t1.g,t2.g)"):
+        specs = [{"type": "constraint", "constraints": cons}]
+        got, want, _ = PU.run_both_frame(df, "tid", specs, mode="detect")
+        assert got == want and len(got) > 100, cons

@@ -200,7 +200,10 @@ def test_constraint_parser_matches_oracle():
     assert PC.classify(preds[0])[0] == "FD" and PC.classify(preds[1]) == ("FD", (["A"], "B"))
     assert PC.classify(PC.parse_denial_constraint('t1&EQ(t1.Sex,"Female")&EQ(t1.Relationship,"Husband")'))[0] == "CONST"
     assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&EQ(t1.b,t2.b)"))[0] == "EQ_ONLY"
-    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.b)"))[0] == "OTHER"
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.b)")) == ("INEQ", (["a"], "LT", "b"))
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&GT(t1.b,t2.b)&EQ(t1.g,t2.g)")) == ("INEQ", (["g"], "GT", "b"))
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&LT(t1.a,t2.a)&GT(t1.b,t2.b)"))[0] == "OTHER"
+    assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.c)"))[0] == "OTHER"
     assert PC.classify(PC.parse_denial_constraint("t1&t2&EQ(t1.a,t2.b)&IQ(t1.c,t2.c)"))[0] == "OTHER"
 
 
