@@ -109,6 +109,17 @@ int dr_dc_fd_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* s
 int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
                   int64_t n_rows, int64_t key_space, const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap,
                   void* stream);
+/* The same two reductions for key spaces too large for direct tables: an open-addressing hash table of
+ * `capacity` (power of two, >= 2 * n_rows) slots keyed by the 64-bit mixed-radix key.  The caller
+ * initialises table_keys = all ones (empty), lo = INT32_MAX, hi = INT32_MIN.  dr_dc_hash_flag: mode 0
+ * flags lo != hi (EQ.. & IQ(b)), mode 1 flags x >= 0 && x + 1 < hi (EQ.. & LT(x), table built with b = x).
+ * Single GPU only: slot positions differ between tables, so they cannot be combined by an all-reduce. */
+int dr_dc_hash_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                     const int32_t* b_col, int64_t n_rows, int64_t capacity, uint64_t* table_keys, int32_t* lo,
+                     int32_t* hi, void* stream);
+int dr_dc_hash_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                    const int32_t* x_col, int mode, int64_t n_rows, int64_t capacity, const uint64_t* table_keys,
+                    const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap, void* stream);
 /* Two-tuple DC  EQ(a_1)..EQ(a_m) & LT(t1.x, t2.x): a row is matched iff another row of its NULL-safe key
  * group has a larger x (`<` is never true for NULL).  hi = the max table dr_dc_fd_build makes for b = x;
  * flags rows with x >= 0 and x + 1 < hi[key].  GT(t1.x, t2.x) is the same test on the reversed codes

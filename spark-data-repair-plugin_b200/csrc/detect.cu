@@ -147,6 +147,58 @@ __global__ void __launch_bounds__(kThreads) k_dc_lt_flag(const __grid_constant__
     });
 }
 
+// ---- key spaces too large for direct tables: open-addressing hash table keyed by the 64-bit key ----
+// slot = (key, lo, hi); the key is claimed with a 64-bit CAS, lo / hi are the same idempotent min / max.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(kThreads) k_dc_hash_build(const __grid_constant__ KeyParams k,
+                                                            const int32_t* __restrict__ b_col, int64_t n_rows,
+                                                            unsigned long long* __restrict__ keys,
+                                                            int32_t* __restrict__ lo, int32_t* __restrict__ hi,
+                                                            uint64_t mask) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const unsigned long long key = (unsigned long long)row_key(k, r);
+        const int v = __ldcs(b_col + r) + 1;
+        uint64_t h = mix64(key) & mask;
+        while (true) {
+            unsigned long long cur = keys[h];
+            if (cur == ~0ull) cur = atomicCAS(keys + h, ~0ull, key);  // claim an empty slot
+            if (cur == ~0ull || cur == key) {
+                if (v < __ldcg(lo + h)) atomicMin(lo + h, v);
+                if (v > __ldcg(hi + h)) atomicMax(hi + h, v);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+// mode 0: lo != hi (EQ.. & IQ(b));  mode 1: x + 1 < hi (EQ.. & LT(x))
+__global__ void __launch_bounds__(kThreads) k_dc_hash_flag(const __grid_constant__ KeyParams k,
+                                                           const int32_t* __restrict__ x, int mode, int64_t n_rows,
+                                                           const unsigned long long* __restrict__ keys,
+                                                           const int32_t* __restrict__ lo,
+                                                           const int32_t* __restrict__ hi, uint64_t mask,
+                                                           uint32_t* __restrict__ bm) {
+    rows_to_bitmap(n_rows, bm, [&](int64_t r) {
+        const int v = mode == 1 ? x[r] : 0;
+        if (mode == 1 && v < 0) return false;
+        const unsigned long long key = (unsigned long long)row_key(k, r);
+        uint64_t h = mix64(key) & mask;
+        while (true) {
+            const unsigned long long cur = __ldg(keys + h);
+            if (cur == key) return mode == 1 ? v + 1 < __ldg(hi + h) : __ldg(lo + h) != __ldg(hi + h);
+            if (cur == ~0ull) return false;  // (cannot happen for a row that was inserted)
+            h = (h + 1) & mask;
+        }
+    });
+}
+
 __global__ void __launch_bounds__(kThreads) k_discretize(const double* __restrict__ vals, int64_t n_rows,
                                                          double vmin, double denom, int thres,
                                                          int32_t* __restrict__ out) {
@@ -306,6 +358,40 @@ int dr_dc_fd_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* st
     if (n_rows <= 0) return DR_OK;
     k_dc_fd_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
         k, n_rows, key_space, lo, hi, row_bitmap);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_dc_hash_build(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                     const int32_t* b_col, int64_t n_rows, int64_t capacity, uint64_t* table_keys, int32_t* lo,
+                     int32_t* hi, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, b_col && table_keys && lo && hi, "null pointer");
+    DR_REQUIRE(ctx, capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two");
+    DR_REQUIRE(ctx, capacity >= 2 * n_rows, "capacity must be at least twice the number of rows");
+    KeyParams k;
+    int rc = fill_keys(ctx, &k, key_cols, strides, n_keys);
+    if (rc) return rc;
+    if (n_rows <= 0) return DR_OK;
+    k_dc_hash_build<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        k, b_col, n_rows, (unsigned long long*)table_keys, lo, hi, (uint64_t)capacity - 1);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_dc_hash_flag(dr_ctx* ctx, const int32_t* const* key_cols, const int64_t* strides, int n_keys,
+                    const int32_t* x_col, int mode, int64_t n_rows, int64_t capacity, const uint64_t* table_keys,
+                    const int32_t* lo, const int32_t* hi, uint32_t* row_bitmap, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, table_keys && lo && hi && row_bitmap, "null pointer");
+    DR_REQUIRE(ctx, mode == 0 || (mode == 1 && x_col), "mode 1 (LT) needs the compared column");
+    DR_REQUIRE(ctx, capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two");
+    KeyParams k;
+    int rc = fill_keys(ctx, &k, key_cols, strides, n_keys);
+    if (rc) return rc;
+    if (n_rows <= 0) return DR_OK;
+    k_dc_hash_flag<<<dr_grid_for(ctx, n_rows, kThreads, kCtasPerSm), kThreads, 0, (cudaStream_t)stream>>>(
+        k, x_col, mode, n_rows, (const unsigned long long*)table_keys, lo, hi, (uint64_t)capacity - 1, row_bitmap);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

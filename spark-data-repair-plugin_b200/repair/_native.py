@@ -64,6 +64,10 @@ _SIGNATURES = {
                                c_void_p, c_void_p]),
     "dr_dc_fd_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_void_p,
                               c_void_p, c_void_p]),
+    "dr_dc_hash_build": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_void_p, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "dr_dc_hash_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "dr_dc_lt_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_void_p, c_int64, c_int64, c_void_p,
                               c_void_p, c_void_p]),
     "dr_bitmap_or": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
@@ -231,6 +235,17 @@ class Context:
         cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
         self._check(self.lib.dr_dc_fd_flag(self._h, cp, _i64_array(strides), len(key_cols), n_rows, key_space,
                                            _dp(lo), _dp(hi), _dp(row_bitmap), self._stream()))
+
+    def dc_hash_build(self, key_cols, strides, b_col, n_rows, capacity, table_keys, lo, hi):
+        cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
+        self._check(self.lib.dr_dc_hash_build(self._h, cp, _i64_array(strides), len(key_cols), _dp(b_col), n_rows,
+                                              capacity, _dp(table_keys), _dp(lo), _dp(hi), self._stream()))
+
+    def dc_hash_flag(self, key_cols, strides, x_col, mode, n_rows, capacity, table_keys, lo, hi, row_bitmap):
+        cp, _k = _ptr_array([c.data_ptr() for c in key_cols])
+        self._check(self.lib.dr_dc_hash_flag(self._h, cp, _i64_array(strides), len(key_cols), _dp(x_col), mode, n_rows,
+                                             capacity, _dp(table_keys), _dp(lo), _dp(hi), _dp(row_bitmap),
+                                             self._stream()))
 
     def dc_lt_flag(self, key_cols, strides, x_col, n_rows, key_space, hi, row_bitmap):
         cp, _k = _ptr_array([c.data_ptr() for c in key_cols])

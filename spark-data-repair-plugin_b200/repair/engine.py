@@ -249,47 +249,14 @@ class Engine:
                 self.ctx.dc_const(cols, ops, args, self.n_rows, rowmask)
             elif shape == "FD":
                 keys, b = payload
-                strides, space = [], 1
-                for k in keys:
-                    strides.append(space)
-                    space *= self.table.by_name[k].dict_size + 1
-                if space > MAX_FD_KEY_SPACE:
-                    raise NotImplementedError(
-                        "denial constraint key space {} exceeds {} (hash-table path not built yet)".format(
-                            space, MAX_FD_KEY_SPACE))
-                lo = self.torch.full((space,), 2 ** 31 - 1, dtype=self.torch.int32, device=self.device)
-                hi = self.torch.full((space,), -2 ** 31, dtype=self.torch.int32, device=self.device)
-                key_cols = [self.dt.col(k) for k in keys] or [self.dt.col(b)]
-                if not keys:
-                    strides = [0]
-                self.ctx.dc_fd_build(key_cols, strides, self.dt.col(b), self.n_rows, space, lo, hi)
-                if self.dist is not None:
-                    self.dist.min_(lo)
-                    self.dist.max_(hi)
-                self.ctx.dc_fd_flag(key_cols, strides, self.n_rows, space, lo, hi, rowmask)
+                self._flag_by_key_group(keys, self.dt.col(b), 0, rowmask)
             elif shape == "INEQ":
                 keys, sign, b = payload
-                strides, space = [], 1
-                for k in keys:
-                    strides.append(space)
-                    space *= self.table.by_name[k].dict_size + 1
-                if space > MAX_FD_KEY_SPACE:
-                    raise NotImplementedError(
-                        "denial constraint key space {} exceeds {} (hash-table path not built yet)".format(
-                            space, MAX_FD_KEY_SPACE))
                 x = self.dt.col(b)
                 if sign == "GT":   # "some row has a smaller b" = "some row has a larger reversed code"
                     dom = self.table.by_name[b].dict_size
                     x = self.torch.where(x >= 0, dom - 1 - x, x)
-                lo = self.torch.full((space,), 2 ** 31 - 1, dtype=self.torch.int32, device=self.device)
-                hi = self.torch.full((space,), -2 ** 31, dtype=self.torch.int32, device=self.device)
-                key_cols = [self.dt.col(k) for k in keys] or [x]
-                if not keys:
-                    strides = [0]
-                self.ctx.dc_fd_build(key_cols, strides, x, self.n_rows, space, lo, hi)
-                if self.dist is not None:
-                    self.dist.max_(hi)
-                self.ctx.dc_lt_flag(key_cols, strides, x, self.n_rows, space, hi, rowmask)
+                self._flag_by_key_group(keys, x, 1, rowmask)
             elif shape == "EQ_ONLY":
                 rowmask.fill_(-1)
             else:
@@ -297,6 +264,43 @@ class Engine:
                     "denial constraint shape not supported on the GPU path yet: {}".format(
                         " & ".join("{}({},{})".format(p.sign, p.left, p.right) for p in preds)))
             self._or_rows_into(rowmask, attrs, bitmaps)
+
+    def _flag_by_key_group(self, keys, x, mode, rowmask):
+        """Rows whose NULL-safe key group (attributes `keys`) holds two distinct x (mode 0: EQ.. & IQ(x))
+        or a larger x than their own (mode 1: EQ.. & LT(x)).  Per-key min / max of x + 1: in direct tables
+        over the mixed-radix key space when it is small enough, else in a hash table keyed by the key."""
+        torch = self.torch
+        strides, space = [], 1
+        for k in keys:
+            strides.append(space)
+            space *= self.table.by_name[k].dict_size + 1
+        key_cols = [self.dt.col(k) for k in keys] or [x]
+        if not keys:
+            strides = [0]
+        if space <= MAX_FD_KEY_SPACE:
+            lo = torch.full((space,), 2 ** 31 - 1, dtype=torch.int32, device=self.device)
+            hi = torch.full((space,), -2 ** 31, dtype=torch.int32, device=self.device)
+            self.ctx.dc_fd_build(key_cols, strides, x, self.n_rows, space, lo, hi)
+            if self.dist is not None:
+                self.dist.min_(lo)
+                self.dist.max_(hi)
+            if mode == 0:
+                self.ctx.dc_fd_flag(key_cols, strides, self.n_rows, space, lo, hi, rowmask)
+            else:
+                self.ctx.dc_lt_flag(key_cols, strides, x, self.n_rows, space, hi, rowmask)
+            return
+        if space >= 2 ** 62:
+            raise NotImplementedError("denial constraint key space {} does not fit a 64-bit key".format(space))
+        if self.dist is not None:
+            raise NotImplementedError("denial constraint key space {} needs the hash-table path, which is "
+                                      "single-GPU (tables of different ranks cannot be all-reduced)".format(space))
+        cap = 1 << max(1, (2 * max(self.n_rows, 1) - 1).bit_length())
+        tkeys = torch.full((cap,), -1, dtype=torch.int64, device=self.device)
+        lo = torch.full((cap,), 2 ** 31 - 1, dtype=torch.int32, device=self.device)
+        hi = torch.full((cap,), -2 ** 31, dtype=torch.int32, device=self.device)
+        self.ctx.dc_hash_build(key_cols, strides, x, self.n_rows, cap, tkeys, lo, hi)
+        self.ctx.dc_hash_flag(key_cols, strides, x if mode == 1 else None, mode, self.n_rows, cap, tkeys, lo, hi,
+                              rowmask)
 
     def detect_outliers(self, targets, bitmaps, approx_enabled=False):
         for a in self.table.continuous_attrs:
