@@ -359,9 +359,11 @@ def test_inequality_denial_constraints_parity():
         assert got == want and len(got) > 100, cons
 
 
-def test_fd_constraint_with_a_huge_key_space_uses_the_hash_table():
-    """Three key attributes with ~600 values each: 2.2e8 possible keys > the direct tables' 2^27."""
+def test_fd_constraint_with_a_huge_key_space_uses_the_hash_table(monkeypatch):
+    """Key spaces beyond the direct min / max tables go through the hash table (the limit is lowered here
+    so that a three-attribute key of a small table crosses it)."""
     from repair import engine as E
+    from repair._native import Context
     rng = np.random.default_rng(12)
     n, groups = 4000, 500
     trip = rng.integers(0, 600, size=(groups, 3))
@@ -369,14 +371,16 @@ def test_fd_constraint_with_a_huge_key_space_uses_the_hash_table():
     df = pd.DataFrame({"tid": np.arange(n), "k1": ["a%03d" % v for v in trip[pick, 0]],
                        "k2": ["b%03d" % v for v in trip[pick, 1]], "k3": ["c%03d" % v for v in trip[pick, 2]],
                        "y": (pick % 7).astype(str), "w": rng.integers(0, 40, n)})
-    noise = rng.random(n) < 0.03
-    df.loc[noise, "y"] = "x"
+    df.loc[rng.random(n) < 0.03, "y"] = "x"
     df.loc[rng.random(n) < 0.02, "k2"] = None
     df.loc[rng.random(n) < 0.02, "y"] = None
-    for c in ("k1", "k2", "k3"):
-        assert df[c].nunique() > 300
-    assert (df["k1"].nunique() + 1) * (df["k2"].nunique() + 1) * (df["k3"].nunique() + 1) > E.MAX_FD_KEY_SPACE
+    monkeypatch.setattr(E, "MAX_FD_KEY_SPACE", 1 << 12)
+    calls = []
+    real = Context.dc_hash_build
+    monkeypatch.setattr(Context, "dc_hash_build", lambda self, *a: (calls.append(1), real(self, *a))[1])
     for cons in ("t1&t2&EQ(t1.k1,t2.k1)&EQ(t1.k2,t2.k2)&EQ(t1.k3,t2.k3)&IQ(t1.y,t2.y)",
-                 "t1&t2&EQ(t1.k1,t2.k1)&EQ(t1.k2,t2.k2)&EQ(t1.k3,t2.k3)&LT(t1.w,t2.w)"):
+                 "t1&t2&EQ(t1.k1,t2.k1)&EQ(t1.k2,t2.k2)&EQ(t1.k3,t2.k3)&LT(t1.w,t2.w)",
+                 "t1&t2&EQ(t1.k1,t2.k1)&EQ(t1.k3,t2.k3)&GT(t1.w,t2.w)"):
         got, want, _ = PU.run_both_frame(df, "tid", [{"type": "constraint", "constraints": cons}], mode="detect")
         assert got == want and len(got) > 50, cons
+    assert len(calls) == 3
