@@ -308,7 +308,7 @@ class DeviceTable:
             staging = torch.empty((self.n_pad,), dtype=torch.float64).pin_memory()
             for c in table.columns:
                 if c.continuous:
-                    staging[:self.n_rows].copy_(torch.from_numpy(np.ascontiguousarray(c.values)))
+                    staging[:self.n_rows].copy_(torch.from_numpy(np.array(c.values, dtype=np.float64)))  # (own, writable copy)
                     staging[self.n_rows:].fill_(float("nan"))
                     values[self.cont_index[c.name]].copy_(staging, non_blocking=True)
                     torch.cuda.current_stream().synchronize()
