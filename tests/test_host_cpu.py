@@ -661,3 +661,26 @@ def test_arrow_ingest_matches_pandas_ingest_and_arrow_egress(tmp_path):
                    {"tid": enc.row_ids[12], "attribute": "Sex", "current_value": sex[0], "repaired": None},
                    {"tid": enc.row_ids[5], "attribute": "Age", "current_value": None, "repaired": age[2]}]
     assert cells_to_arrow(enc, []).num_rows == 0
+
+
+def test_invalid_running_modes_are_refused_before_any_gpu_work():
+    # tests/test_model.py:231-266 (all raised on the host, before an engine exists)
+    import pandas as pd
+    from repair import RepairModel
+    from repair.costs import Levenshtein
+    mixed = pd.DataFrame({"tid": range(6), "v1": [1, 2, 3, 2, None, 2], "v2": ["a", "b", "a", None, "a", "b"],
+                          "v3": [1.0, 1.5, None, 1.4, 1.1, 1.2]})
+    m = RepairModel().setInput(mixed).setRowId("tid").setRepairDelta(1).setUpdateCostFunction(Levenshtein())
+    with pytest.raises(ValueError, match="Cannot enable the maximal likelihood repair mode when continous attributes found"):
+        m.run(maximal_likelihood_repair=True)
+    adult = pd.read_csv(os.path.join(GOLDEN, "adult.csv"))
+    m = RepairModel().setInput(adult).setRowId("tid").setRepairByRules(True).setUpdateCostFunction(Levenshtein()) \
+        .setRepairDelta(3).option("model.rule.repair_by_nearest_values.disabled", "")
+    msg = "Cannot repair data by nearest values when enabling `maximal_likelihood_repair`, " \
+          "`compute_repair_candidate_prob`, `compute_repair_prob`, or `compute_repair_score`"
+    for mode in ("maximal_likelihood_repair", "compute_repair_candidate_prob", "compute_repair_prob",
+                 "compute_repair_score"):
+        with pytest.raises(ValueError, match=msg):
+            m.run(**{mode: True})
+    with pytest.raises(NotImplementedError, match="rebalancing needs imbalanced-learn"):
+        RepairModel().setInput(adult).setRowId("tid").setTrainingDataRebalancingEnabled(True).run()
