@@ -591,3 +591,23 @@ def test_repair_by_regular_expression_kat():
     assert done == [(0, "xx", "32 patxxnts", "32 patients")] and rest == cells[1:]
     rest, done = R.repair_by_regexs(cells, [("xx", "^[0-9]{1,")])
     assert done == [] and rest == cells
+
+
+def test_no_repairable_cell_exists():
+    # tests/test_model.py:841-864: y has a single value, so no error cell sits in a discretisable column
+    t = from_rows(["tid", "x", "y"], [(1, "1", None), (2, "2", None), (3, "1", "test-1"), (4, "1", "test-1"),
+                                      (5, "1", "test-1"), (6, "1", None)])
+    with pytest.raises(ValueError, match="At least one valid discretizable feature is needed to repair error cells"):
+        R.run(t, "tid", [{"type": "null"}])
+    assert sorted(R.run(t, "tid", [{"type": "null"}], detect_errors_only=True)) == \
+        [("1", "y", None), ("2", "y", None), ("6", "y", None)]
+
+
+def test_error_cells_having_no_existent_attribute():
+    # tests/test_model.py:493-508: a given error cell of an unknown attribute is ignored
+    t = adult()
+    given = [(1, "NoExistent"), (5, "Income"), (16, "Income")]
+    cells = R.run(t, "tid", [{"type": "null"}], given_error_cells=given, detect_errors_only=True)
+    assert sorted(cells) == [("16", "Income", None), ("5", "Income", None)]
+    out = R.run(t, "tid", [{"type": "null"}], given_error_cells=given, model_provider=lambda ctx: {"const": "MoreThan50K"})
+    assert sorted(out) == [("16", "Income", None, "MoreThan50K"), ("5", "Income", None, "MoreThan50K")]
