@@ -72,7 +72,7 @@ def random_forest_provider(n_iter):
     cache = {}
 
     def provider(ctx):
-        from repair.train import random_forest
+        from tools.randforest import random_forest
         n_feat = ctx["X"].shape[1]
         if ctx["is_discrete"]:
             classes = sorted(set(int(v) for v in np.asarray(ctx["y_values"]).tolist()))
@@ -288,6 +288,8 @@ def b200_arm(args):
     torch.cuda.synchronize()
     t_train = time.time() - t_train
     n_trees = sum(m[1].n_trees for _, m in models if m[0] == "forest")
+    from repair.forest import forest_shape_stats
+    shape = {y: forest_shape_stats(m[2]["spec"]["forest"]) for y, m in models if m[0] == "forest"}
 
     stats = {}
     res_cells = {}
@@ -417,6 +419,14 @@ def b200_arm(args):
                      res_cells.get(y, 0) for y, m in models if m[0] == "forest")
         tree_cells = sum(m[1].n_trees * res_cells.get(y, 0) for y, m in models if m[0] == "forest")
         line["forest_tree_levels_per_sec"] = levels / (f_ms / 1e3)
+        # how much of the fixed-depth walk the trained trees need (weights: trees x cells of each model)
+        wsum = sum(shape[y]["n_trees"] * res_cells.get(y, 0) for y in shape) or 1
+        wavg = (lambda key: sum(shape[y][key] * shape[y]["n_trees"] * res_cells.get(y, 0) for y in shape) / wsum)
+        line["forest_stats"] = {
+            "levels_walked_per_tree": levels / max(tree_cells, 1), "mean_tree_depth": wavg("mean_tree_depth"),
+            "mean_leaf_depth": wavg("mean_leaf_depth"), "mean_leaves": wavg("mean_leaves"),
+            "single_leaf_tree_frac": wavg("single_leaf_tree_frac"),
+            "max_depth_by_model": {y: shape[y]["max_depth"] for y in shape}}
         sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         sm_count = torch.cuda.get_device_properties(device).multi_processor_count
         wf = (2.0 * levels + 3.0 * tree_cells) / 32.0

@@ -127,13 +127,14 @@ def group_by_sequence(forest):
 def bfs_relabel(toff, left, right, is_leaf):
     """Breadth-first renumbering of every tree at once: root = 0 and the right child of a node is its
     left child + 1 (what the carry-coded node word needs).  -> (new tree-relative index per node, -1
-    for nodes the root does not reach; nodes kept per tree; deepest leaf of any tree)."""
+    for nodes the root does not reach; nodes kept per tree; depth of every tree = its deepest leaf)."""
     toff = np.asarray(toff, dtype=np.int64)
     n_trees = len(toff) - 1
     new = np.full(len(left), -1, dtype=np.int64)
     kept = np.ones(n_trees, dtype=np.int64)
+    tree_depth = np.zeros(n_trees, dtype=np.int64)
     if n_trees == 0:
-        return new, kept, 0
+        return new, kept, tree_depth
     frontier, ftree = toff[:-1].copy(), np.arange(n_trees, dtype=np.int64)
     new[frontier] = 0
     depth = 0
@@ -151,7 +152,44 @@ def bfs_relabel(toff, left, right, is_leaf):
         kept[tr[start]] += 2 * cnt
         frontier, ftree = np.stack([lch, rch], axis=1).ravel(), np.repeat(tr, 2)
         depth += 1
-    return new, kept, depth
+        tree_depth[tr[start]] = depth
+    return new, kept, tree_depth
+
+
+def forest_shape_stats(forest):
+    """Shape of a flat forest (host, for bench.py / DESIGN.md): how much of a fixed-depth walk is
+    needed.  -> dict(n_trees, max_depth, mean_tree_depth, single_leaf_tree_frac, mean_leaves,
+    mean_leaf_depth = unweighted mean depth of the leaves)."""
+    toff = np.asarray(forest["tree_offset"], dtype=np.int64)
+    feat = np.asarray(forest["feature"], dtype=np.int64)
+    left, right = np.asarray(forest["left"], dtype=np.int64), np.asarray(forest["right"], dtype=np.int64)
+    n_trees = len(toff) - 1
+    if n_trees == 0:
+        return {"n_trees": 0, "max_depth": 0, "mean_tree_depth": 0.0, "single_leaf_tree_frac": 0.0,
+                "mean_leaves": 0.0, "mean_leaf_depth": 0.0}
+    is_leaf = feat < 0
+    _, _, tree_depth = bfs_relabel(toff, left, right, is_leaf)
+    node_depth = np.full(len(feat), -1, dtype=np.int64)
+    frontier = toff[:-1].copy()
+    sizes = toff[1:] - toff[:-1]
+    tree_of = np.repeat(np.arange(n_trees), sizes)
+    node_depth[frontier] = 0
+    d = 0
+    while len(frontier):
+        inner = frontier[~is_leaf[frontier]]
+        if not len(inner):
+            break
+        base = toff[tree_of[inner]]
+        frontier = np.concatenate([base + left[inner], base + right[inner]])
+        d += 1
+        node_depth[frontier] = d
+    reach = is_leaf & (node_depth >= 0)
+    leaves_per_tree = np.bincount(tree_of[reach], minlength=n_trees)
+    return {"n_trees": int(n_trees), "max_depth": int(tree_depth.max()),
+            "mean_tree_depth": float(tree_depth.mean()),
+            "single_leaf_tree_frac": float((leaves_per_tree <= 1).mean()),
+            "mean_leaves": float(leaves_per_tree.mean()),
+            "mean_leaf_depth": float(node_depth[reach].mean())}
 
 
 def rank_code(spec, dict_sizes):
@@ -192,7 +230,8 @@ def rank_code(spec, dict_sizes):
     feat = np.asarray(f["feature"], dtype=np.int64)
     is_leaf = feat < 0
     left, right = np.asarray(f["left"], dtype=np.int64), np.asarray(f["right"], dtype=np.int64)
-    new, kept, depth = bfs_relabel(toff, left, right, is_leaf)
+    new, kept, tree_depth = bfs_relabel(toff, left, right, is_leaf)
+    depth = int(tree_depth.max()) if len(tree_depth) else 0
     new_toff = np.zeros(len(toff), dtype=np.int64)
     new_toff[1:] = np.cumsum(kept)
     old_sizes = toff[1:] - toff[:-1]
@@ -226,6 +265,7 @@ def rank_code(spec, dict_sizes):
     return {"word": word, "tree_offset": new_toff, "leaf_value": np.asarray(f["value"], dtype=np.float64)[src][n_leaf],
             "tree_leaf_off": tree_leaf_off, "rank_lut": np.concatenate(rank_lut) if rank_lut else np.zeros(1, np.uint8),
             "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth,
+            "tree_depth": tree_depth,
             "max_tree_leaves": int((tree_leaf_off[1:] - tree_leaf_off[:-1]).max()) if len(old_sizes) else 1}
 
 

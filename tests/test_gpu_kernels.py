@@ -323,7 +323,7 @@ def test_gather_rows_masked_and_tile_ops(ctx, n, k):
 
 
 def _rand_forest(rng, n_feat, n_classes, n_iter):
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     thr = [[-0.5, 0.5, 1.5, 2.5, 3.5] for _ in range(n_feat)]
     return random_forest(n_feat, n_classes, n_iter, thr, rng, leaf_scale=0.1)
 
@@ -421,7 +421,7 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
     256-cell wide kernels run."""
     from oracle.forest import forest_margins, forest_predict
     from repair.forest import DeviceModel, encode_matrix, encoder_width
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     rng = np.random.default_rng(n_classes + n)
     doms = [7, 4, 30, 3, 9, 64, 2, 12] + extra
     k = len(doms)

@@ -345,7 +345,7 @@ def test_oracle_forest_matches_sklearn(kind):
 
 def test_pack_nodes_roundtrip():
     from repair.forest import LEAF, pack_nodes
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     rng = np.random.default_rng(0)
     f = random_forest(10, 3, 5, [[0.5, 1.5]] * 10, rng)
     thr, meta = pack_nodes(f)
@@ -429,7 +429,7 @@ def _eval_ranked(rk, forest, codes_by_feat):
 def test_rank_coded_forest_makes_the_same_decisions():
     from oracle.forest import forest_margins
     from repair.forest import encode_matrix, encoder_width, rank_code
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     rng = np.random.default_rng(4)
     dict_sizes = {"a": 5, "b": 14, "c": 3}
     encoders = [{"attr": "a", "type": "sum", "categories": [2, -1, 0, 4]},
@@ -454,7 +454,7 @@ def test_ranked_image_padding_and_chunks():
     from oracle.forest import forest_margins
     from repair.forest import (RANKED_CHUNK_LEAVES, RANKED_CHUNK_NODES, RANKED_CHUNK_TREES, RANKED_GROUP,
                                encode_matrix, encoder_width, group_by_sequence, rank_code, ranked_image)
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     rng = np.random.default_rng(8)
     dict_sizes = {"a": 6, "b": 20}
     encoders = [{"attr": "a", "type": "sum", "categories": [0, 1, 2, 3, 4, 5]},

@@ -29,7 +29,7 @@ def test_scan_hist_and_cooc():
 @pytest.mark.parametrize("n_classes", [1, 2, 5])
 def test_forest_margins(n_classes):
     from oracle.forest import forest_margins
-    from repair.train import random_forest
+    from tools.randforest import random_forest
     rng = np.random.default_rng(n_classes)
     f = random_forest(9, n_classes, 30, [[-0.5, 0.5, 1.5, 2.5]] * 9, rng, leaf_scale=0.3)
     X = rng.integers(-2, 4, size=(2000, 9)).astype(np.float64)
