@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-calls", action="store_true", help="print the per-call timing table to stderr")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="skip the after-the-fact self-check of the last timed step (histograms, cell counts, "
+                         "a seeded sample of repaired cells re-evaluated by the oracle's C forest)")
+    ap.add_argument("--verify-cells", type=int, default=50000)
     ap.add_argument("--trace", action="store_true",
                     help="one extra step with device-synchronised split points of the repair phase on stderr")
     return ap.parse_args()
@@ -212,6 +216,113 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# --verify: after the timed region, re-derive what the last step produced by independent means
+# ---------------------------------------------------------------------------------------------
+def verify_step(engine, table, res, out, models, k, n_sample, dist, seed=12345):
+    """Independent re-computation of the last pass (untimed):
+      * every column histogram vs torch.bincount of the resident codes (all-reduced when sharded);
+      * per-attribute error-cell counts (before the weak-label pruning) vs NULL counts + a torch
+        restatement of the FD constraints (per-key min/max through scatter_reduce);
+      * a seeded sample of the emitted repairs: the cell's feature vector as the chain saw it (later
+        targets' error cells still NULL, earlier ones already filled) is encoded on the host and
+        evaluated by the ORACLE's C forest (oracle/c, float64 thresholds, generic layout) -- label must
+        equal the code the CUDA chain wrote.
+    -> dict for the JSON line."""
+    import torch
+    from oracle import ckernels
+    from repair import synth
+    from repair.forest import encode_matrix
+    dev = engine.device
+    names = table.names
+    n = engine.n_rows
+    info = {"hist_columns_checked": 0, "hist_mismatches": 0, "cell_count_attrs_checked": 0,
+            "cell_count_mismatches": 0, "cells_checked": 0, "mismatches": 0}
+    # ---- histograms ----
+    for a in names:
+        col = engine.dt.col(a)[:n]
+        d = table.by_name[a].dict_size
+        h = torch.bincount((col + 1).to(torch.int64), minlength=d + 1)
+        if dist is not None:
+            dist.sum_(h)
+        got = engine._hist_cache.get(a)
+        info["hist_columns_checked"] += 1
+        if got is None or not np.array_equal(np.asarray(got), h.cpu().numpy()):
+            info["hist_mismatches"] += 1
+    # ---- error-cell counts of the detect phase (local shard; the FD tables are global) ----
+    flagged = {}
+    fds = synth.fd_constraints(k)
+    for stmt in [x for x in fds.split(";") if x]:
+        xname, yname = stmt.split("->")
+        x, y = engine.dt.col(xname)[:n], engine.dt.col(yname)[:n]
+        dx = table.by_name[xname].dict_size
+        key = (x + 1).to(torch.int64)
+        lo = torch.full((dx + 1,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+        hi = torch.full((dx + 1,), -2 ** 31, dtype=torch.int32, device=dev)
+        lo.scatter_reduce_(0, key, y + 1, reduce="amin")
+        hi.scatter_reduce_(0, key, y + 1, reduce="amax")
+        if dist is not None:
+            dist.min_(lo)
+            dist.max_(hi)
+        viol = (lo != hi)[key]
+        for a in (xname, yname):
+            flagged[a] = viol if a not in flagged else (flagged[a] | viol)
+    for a in names:
+        want = (engine.dt.col(a)[:n] < 0)
+        if a in flagged:
+            want = want | flagged[a]
+        want = int(want.sum().item())
+        info["cell_count_attrs_checked"] += 1
+        if int(res.n_cells_detected.get(a, 0)) != want:
+            info["cell_count_mismatches"] += 1
+    # ---- sampled repairs through the oracle's forest ----
+    lr = getattr(engine, "last_repair", None)
+    if lr is None or not out or not ckernels.available():
+        info["note"] = "no repaired cells to sample" if ckernels.available() else "oracle/c not built"
+        return info
+    chain = lr["chain"]
+    pos_in_chain = {y: i for i, y in enumerate(chain)}
+    tile_col = {c.name: i for i, c in enumerate(table.columns)}
+    dict_sizes = {c.name: c.dict_size for c in table.columns}
+    by_attr = {a: (rows, cur, rep) for a, rows, cur, rep in out}
+    forest_of = {y: m for y, m in models if m[0] == "forest"}
+    sizes = np.asarray([len(by_attr[a][0]) if a in forest_of and a in by_attr else 0 for a in names], dtype=np.int64)
+    total = int(sizes.sum())
+    if total == 0:
+        return info
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(total, size=min(n_sample, total), replace=False))
+    bounds = np.r_[0, np.cumsum(sizes)]
+    drows = lr["drows"]
+    K = len(names)
+    for ai, a in enumerate(names):
+        sel = pick[(pick >= bounds[ai]) & (pick < bounds[ai + 1])] - bounds[ai]
+        if len(sel) == 0:
+            continue
+        rows, _, rep = by_attr[a]
+        rows_s, rep_s = np.asarray(rows)[sel], np.asarray(rep)[sel]
+        d_rows = torch.from_numpy(np.ascontiguousarray(rows_s, dtype=np.int32)).to(dev)
+        dpos = torch.searchsorted(drows[:lr["D"]], d_rows).to(torch.int64)
+        assert bool((drows[dpos] == d_rows).all())
+        codes = lr["tile"][dpos].cpu().numpy().astype(np.int64)                    # [m, K] final tile rows
+        was_null = ((lr["nulls"][:, dpos >> 5] >> (dpos & 31).to(torch.int32)) & 1).cpu().numpy().astype(bool)  # [K, m]
+        assert np.array_equal(codes[:, tile_col[a]], rep_s.astype(np.int64))       # the frame reports the tile
+        for c in names:   # state of the row when model `a` ran
+            j = tile_col[c]
+            if c == a or (c in pos_in_chain and pos_in_chain[c] > pos_in_chain[a]):
+                codes[was_null[j], j] = -1
+        spec = forest_of[a][2]["spec"]
+        X = encode_matrix(spec["encoders"], {e["attr"]: codes[:, tile_col[e["attr"]]] for e in spec["encoders"]}, {},
+                          dict_sizes)
+        m = ckernels.forest_margins(spec["forest"], X)
+        lab = (m[:, 0] > 0).astype(np.int64) if m.shape[1] == 1 else np.argmax(m, axis=1)
+        want = np.asarray(spec["class_codes"], dtype=np.int64)[lab]
+        info["cells_checked"] += int(len(sel))
+        info["mismatches"] += int((want != rep_s.astype(np.int64)).sum())
+    return info
+
+
 def b200_arm(args):
     import torch
     from repair import RepairModel, synth
@@ -316,6 +427,7 @@ def b200_arm(args):
         stats["cells"] = rm.last_run["n_error_cells"]
         stats["dirty"] = rm.last_run["n_dirty_rows"]
         stats["out_rows"] = sum(len(x[1]) for x in out)
+        stats["last"] = (r, out)
         stats["d2h"] = sum(x[1].nbytes + x[2].nbytes + x[3].nbytes for x in out)
         return ev
 
@@ -367,6 +479,24 @@ def b200_arm(args):
         "gpu_launches": launches, "clocks": clocks,
         "model_training_s": t_train, "forests": args.forests,
     }
+
+    # ---- self-check of the last timed step (untimed) -------------------------------------------
+    if not args.no_verify:
+        t_v = time.time()
+        r_last, out_last = stats["last"]
+        # copies: the result arrays are views of a pinned staging buffer the next pass reuses
+        out_last = [(a, np.array(x), np.array(c), np.array(rp)) for a, x, c, rp in out_last]
+        v = verify_step(engine, table, r_last, out_last, models, k, args.verify_cells, dist)
+        cnt = torch.tensor([v["hist_mismatches"], v["cell_count_mismatches"], v["cells_checked"], v["mismatches"]],
+                           dtype=torch.int64, device=device)
+        if dist is not None:
+            dist.sum_(cnt)
+            v["hist_mismatches"], v["cell_count_mismatches"] = int(cnt[0]), int(cnt[1])
+            v["cells_checked"], v["mismatches"] = int(cnt[2]), int(cnt[3])
+        v["seconds"] = round(time.time() - t_v, 2)
+        v["how"] = "torch.bincount histograms; NULL + torch scatter_reduce FD cell counts; sampled repairs " \
+                   "re-evaluated by oracle/c forest_margins on host-encoded feature vectors"
+        line["verify"] = v
 
     # ---- per-kernel timing (CUDA events on the launching stream) and rooflines ------------------
     engine.ctx.profile = []

@@ -283,22 +283,25 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
                       const int32_t* cells, int64_t n_cells, int target_col, double* out_margin, void* stream);
 /* Rank-coded variant for all-discrete models (the common case: every feature is a label-encoded
  * attribute).  An encoded feature then takes only a handful of distinct values, so the host replaces
- * every value by its RANK among the feature's sorted distinct values (255 = NaN) and every threshold
- * by the number of values <= threshold: `x <= thr` becomes `rank < thr_rank` -- same decisions, but a
- * node is ONE 32-bit word and a cell's feature vector is one byte per feature, which is what lets
- * 16+ warps per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins
- * remain bit-identical to dr_forest_predict / the oracle.
- *   node word: bits 24-31 = 2 * feature + (NaN goes left), bits 8-23 = index of the LEFT child in
- *              the chunk's node array (the right child is the next word: trees are stored breadth
- *              first with siblings adjacent), bits 0-7 = 256 - (thr_rank + 1).  Adding the row's
- *              rank byte to the word carries into the child field exactly when rank >= thr_rank + 1,
- *              i.e. when the row goes right: a level is load rank, add, load word[bits 8-23].
- *              A LEAF has bits 0-7 = 0 (never carries), its own index in bits 8-23 (the walk stays
- *              put, so every tree is walked max_depth levels without a branch) and its leaf number
- *              within the tree in bits 24-31 (at most 256 leaves per tree, at most 127 features).
- *   rank_lut:  uint8, rank + 1 (1..254) of feature f of a row = rank_lut[rank_lut_off[f] +
- *              tile[row][feat_col[f]] + 1], 255 = NaN; NaN is stored as 255 in the "goes right" copy
- *              of the feature byte and as 0 in the "goes left" copy.
+ * every value by its RANK among the feature's sorted distinct values and every threshold by the
+ * number of values <= threshold: `x <= thr` becomes `rank < thr_rank` -- same decisions, but a node is
+ * ONE 32-bit word and a cell's feature vector is one byte per rank slot, which is what lets 16 warps
+ * per SM stay resident.  Leaf values stay float64 and are summed in tree order, so margins remain
+ * bit-identical to dr_forest_predict / the oracle.
+ *   rank slot: one (encoded feature, NaN direction) combination that some node tests.  Slot s of a
+ *              row = rank_lut[rank_lut_off[s] + tile[row][slot_col[s]] + 1] when the code lies inside
+ *              the slot's LUT, else slot_nan[s]; LUT entries are rank + 1 (1..254) with NaN already
+ *              folded to 0 (the slot's nodes send NaN left) or 255 (right).  At most 255 slots.
+ *   node word: bits 24-31 = rank slot, bits 8-23 = index of the LEFT child in the chunk's node array
+ *              (the right child is the next word: siblings are adjacent), bits 0-7 = 256 -
+ *              (thr_rank + 1).  Adding the row's rank byte to the word carries into the child field
+ *              exactly when rank >= thr_rank + 1, i.e. when the row goes right: a level is load rank,
+ *              add, load word[bits 8-23].  A LEAF is (own index << 8): slot 0, never carries, the
+ *              walk stays put -- every tree is walked max_depth levels without a branch.
+ *   leaf values: the LAST level only computes the index c of the node the walk ends on (no load of
+ *              that node's word); its value is leaf_value[chunk_leaf_off[chunk] + bias + c], where
+ *              bias (signed) is the second header word of the tree.  The host orders the nodes of a
+ *              tree so that all leaves sit in its tail and stores values for that tail only.
  *   max_depth: deepest leaf of any tree.
  *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered).
  *   The host supplies the chunk table: chunk c = trees [chunk_tree_off[c], chunk_tree_off[c+1]) of
@@ -306,16 +309,15 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  *   most DR_RANKED_CHUNK_TREES trees, DR_RANKED_CHUNK_NODES node words and DR_RANKED_CHUNK_LEAVES leaf
  *   values; its words are node_word[chunk_node_off[c] .. chunk_node_off[c+1]), its leaf values
  *   leaf_value[chunk_leaf_off[c] ..), its tree headers tree_hdr[2 * chunk_hdr_off[c] ..): two words
- *   per tree = (root node word, first leaf value of the tree relative to the chunk).  chunk_node_off
- *   is a multiple of 4, chunk_leaf_off and chunk_hdr_off multiples of 2 (16-byte TMA granules). */
+ *   per tree = (root node word, value bias).  chunk_node_off is a multiple of 4, chunk_leaf_off and
+ *   chunk_hdr_off multiples of 2 (16-byte TMA granules). */
 #define DR_RANKED_CHUNK_NODES 4096
-#define DR_RANKED_CHUNK_LEAVES 2176
+#define DR_RANKED_CHUNK_LEAVES 2560
 #define DR_RANKED_CHUNK_TREES 256
 typedef struct dr_forest_ranked {
-    int32_t n_seq, n_trees, n_nodes, n_leaves, n_feat, max_depth, n_chunks;
-    int32_t max_tree_leaves; /* most leaves of any tree (1..256) */
-    int32_t layout;          /* shared-memory feature tile: 0 = choose, 1 = bytes, 2 / 3 = one word per rank
-                                byte with 8 / 16 trees in flight per thread (DR_ERR_UNSUPPORTED if it does not fit) */
+    int32_t n_seq, n_trees, n_nodes, n_leaves, n_slots, max_depth, n_chunks;
+    int32_t layout;          /* shared-memory rank tile: 0 = choose, 1 = bytes, 2 / 3 = one word per rank
+                                with 8 / 16 trees in flight per thread (DR_ERR_UNSUPPORTED if it does not fit) */
     const int32_t* chunk_tree_off;
     const int32_t* chunk_seq;
     const int32_t* chunk_node_off;
@@ -325,9 +327,10 @@ typedef struct dr_forest_ranked {
     const uint32_t* node_word;
     const double* leaf_value;
     const double* baseline;
-    const int32_t* feat_col;
-    const int32_t* rank_lut_off;
+    const int32_t* slot_col;      /* int32[n_slots]: tile column the slot reads */
+    const int32_t* rank_lut_off;  /* int32[n_slots + 1] */
     const uint8_t* rank_lut;
+    const uint8_t* slot_nan;      /* uint8[n_slots]: rank byte of a code outside the slot's LUT */
     const int32_t* class_code;
     int32_t n_classes;
 } dr_forest_ranked;

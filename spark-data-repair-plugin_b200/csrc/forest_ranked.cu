@@ -11,22 +11,24 @@
 // by shared-memory wavefronts (two loads per level: rank byte, node word), so everything else is
 // squeezed out of the level: the node word is carry coded (word + rank overflows into the child index
 // exactly when the row goes right; siblings are adjacent), child indices are absolute within the
-// chunk, leaves point at themselves and NaN is folded into two copies of every rank byte -- a level
-// is LDS.U8, IADD, PRMT, LDS with no compare, select or branch.  Leaf values are float64 and are
-// added to the sequence's accumulator in tree order: margins are bit-identical to the generic kernel
-// and to the oracle.
+// chunk, leaves point at themselves and NaN is folded into the rank slots (one slot per (feature, NaN
+// direction) that some node tests) -- a level is LDS, IADD, PRMT, LDS with no compare, select or
+// branch.  The LAST level stops at the index of the node the walk ends on: leaf values are stored per
+// node of each tree's tail (the host orders a tree's nodes so that all leaves sit there), so the leaf's
+// own word is never loaded.  Leaf values are float64 and are added to the sequence's accumulator in
+// tree order: margins are bit-identical to the generic kernel and to the oracle.
 #include "common.cuh"
 
 namespace {
 
 // The kernel runs at ~92 % of the shared-memory pipe (ncu: 0.92 wavefronts / cycle / SM), so what
 // counts is wavefronts per level.  Two feature-tile layouts:
-//  * wide   (1 CTA / SM): one 32-bit word per rank byte, [feature byte][thread].  Lane L of a warp
-//           always reads bank L, whatever feature its node tests: the rank load is ONE wavefront (the
-//           byte layout measures 1.96 once the lanes of a warp have spread over different nodes).
-//           512 cells / CTA when 2 * n_feat * 2 KB fits beside the chunk buffers (<= 37 features),
-//           else 256 cells / CTA (<= 75 features), then with more trees in flight per thread.
-//  * bytes  (256 cells / CTA, 2 CTAs / SM): [thread][feature byte], odd word stride.
+//  * wide   (1 CTA / SM): one 32-bit word per rank, [slot][thread].  Lane L of a warp always reads
+//           bank L, whatever slot its node tests: the rank load is ONE wavefront (the byte layout
+//           measures 1.96 once the lanes of a warp have spread over different nodes).
+//           512 cells / CTA when n_slots * 2 KB fits beside the chunk buffers (<= 72 slots),
+//           else 256 cells / CTA (<= 148 slots), then with more trees in flight per thread.
+//  * bytes  (256 cells / CTA, 2 CTAs / SM when it fits): [thread][slot], odd word stride.
 constexpr int kByteThreads = 256;
 constexpr int kChunkNodes = DR_RANKED_CHUNK_NODES;
 constexpr int kChunkLeaves = DR_RANKED_CHUNK_LEAVES;
@@ -99,12 +101,26 @@ __device__ __forceinline__ uint32_t step_node(uint32_t nodes, uint32_t w, uint32
     return lds_u32(__byte_perm(w2, 0, 0x4421) * 4u + nodes);     // bits 8..23: left child (+1 = right child)
 }
 
+// Last level: only the index of the node the walk ends on (chunk relative).
+template <bool kWide, int T>
+__device__ __forceinline__ uint32_t last_node(uint32_t w, uint32_t feat, uint32_t lane_off) {
+    uint32_t r;
+    if (kWide) {
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(w >> 24), "n"(T * 4), "r"(feat + lane_off));
+        r = lds_u32(addr);
+    } else {
+        r = lds_u8((w >> 24) + feat);
+    }
+    return __byte_perm(w + r, 0, 0x4421);
+}
+
 constexpr int kChunkTrees = DR_RANKED_CHUNK_TREES;
 
 struct __align__(16) ChunkBuf {
     double leaf[kChunkLeaves];
     uint32_t node[kChunkNodes];
-    uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, first leaf), chunk relative
+    uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, value bias), chunk relative
 };
 
 constexpr int kStages = 2;  // chunk buffers in flight per CTA
@@ -159,39 +175,34 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         const bool live = i < p.n_cells;
         const int64_t row = live ? p.cells[i] : 0;
         {
-            // feature tile of this thread's cell: rank bytes of its encoded features (eight features at a
-            // time, loads first: the tile row and the rank look-ups are dependent global loads)
+            // rank tile of this thread's cell (eight slots at a time, loads first: the tile row and the
+            // rank look-ups are dependent global loads)
             const int32_t* trow = p.tile + row * p.n_cols;
             constexpr int kFill = 8;
-            for (int f0 = 0; f0 < F.n_feat; f0 += kFill) {
+            for (int s0 = 0; s0 < F.n_slots; s0 += kFill) {
                 int code[kFill], lo[kFill], hi[kFill];
+                uint8_t nanv[kFill];
 #pragma unroll
                 for (int j = 0; j < kFill; ++j) {
-                    const int f = f0 + j < F.n_feat ? f0 + j : F.n_feat - 1;
-                    lo[j] = F.rank_lut_off[f];
-                    hi[j] = F.rank_lut_off[f + 1];
-                    code[j] = live ? trow[F.feat_col[f]] : -1;
+                    const int sl = s0 + j < F.n_slots ? s0 + j : F.n_slots - 1;
+                    lo[j] = F.rank_lut_off[sl];
+                    hi[j] = F.rank_lut_off[sl + 1];
+                    nanv[j] = F.slot_nan[sl];
+                    code[j] = live ? trow[F.slot_col[sl]] : -1;
                 }
                 uint8_t r[kFill];
 #pragma unroll
                 for (int j = 0; j < kFill; ++j) {
                     const int kk = lo[j] + code[j] + 1;
-                    r[j] = (live && kk >= lo[j] && kk < hi[j]) ? __ldg(F.rank_lut + kk) : (uint8_t)255;  // 255 = NaN
+                    // a code outside the slot's LUT (e.g. the pmf modes' "unknown category") is NaN
+                    r[j] = (kk >= lo[j] && kk < hi[j]) ? __ldg(F.rank_lut + kk) : nanv[j];
                 }
 #pragma unroll
                 for (int j = 0; j < kFill; ++j) {
-                    const int f = f0 + j;
-                    if (f < F.n_feat) {
-                        // ranks are stored +1 (1..254); NaN is 255 in the copy read by nodes that send
-                        // NaN right and 0 in the copy read by nodes that send it left
-                        const uint8_t rl = r[j] == 255 ? 0 : r[j];
-                        if (kWide) {
-                            reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 0) * T] = r[j];
-                            reinterpret_cast<uint32_t*>(my_feat)[(2 * f + 1) * T] = rl;
-                        } else {
-                            my_feat[2 * f + 0] = r[j];
-                            my_feat[2 * f + 1] = rl;
-                        }
+                    const int sl = s0 + j;
+                    if (sl < F.n_slots) {
+                        if (kWide) reinterpret_cast<uint32_t*>(my_feat)[sl * T] = r[j];
+                        else       my_feat[sl] = r[j];
                     }
                 }
             }
@@ -223,18 +234,21 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
             for (int q = 0; q < n_trees; q += kIlp) {
-                uint32_t w[kIlp], lb[kIlp];
+                uint32_t w[kIlp];
+                int lb[kIlp];
 #pragma unroll
                 for (int j = 0; j < kIlp; j += 2) {  // two tree headers per 128-bit broadcast load
                     const uint4 h = hdr4[(q + j) >> 1];
-                    w[j] = h.x; lb[j] = h.y; w[j + 1] = h.z; lb[j + 1] = h.w;
+                    w[j] = h.x; lb[j] = (int)h.y; w[j + 1] = h.z; lb[j + 1] = (int)h.w;
                 }
                 if (q + kIlp > n_trees) {  // last group of a sequence: surplus slots re-walk tree 0
 #pragma unroll
                     for (int j = 1; j < kIlp; ++j)
                         if (q + j >= n_trees) { w[j] = w[0]; lb[j] = lb[0]; }
                 }
-                if (depth > 0) {
+                // levels 1 .. depth-1: rank load + node load; the serial float64 adds of the PREVIOUS group
+                // are issued between the loads of this group's first level
+                if (depth > 1) {
 #pragma unroll
                     for (int j = 0; j < kIlp; ++j) {
                         w[j] = step_node<kWide, T>(nodes, w[j], feat, lane_off);
@@ -245,12 +259,18 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                     for (int j = 0; j < kIlp; ++j)
                         if (j < n_pend) acc += pend[j];
                 }
-                for (int d = 1; d < depth; ++d) {
+                for (int d = 2; d < depth; ++d) {
 #pragma unroll
                     for (int j = 0; j < kIlp; ++j) w[j] = step_node<kWide, T>(nodes, w[j], feat, lane_off);
                 }
+                // last level: the index of the final node is enough, its value is stored per node
+                if (depth > 0) {
 #pragma unroll
-                for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (w[j] >> 24)];
+                    for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (int)last_node<kWide, T>(w[j], feat, lane_off)];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (int)__byte_perm(w[j], 0, 0x4421)];
+                }
                 n_pend = n_trees - q < kIlp ? n_trees - q : kIlp;
             }
             // this warp is done with buffer b; the last warp to leave refills it with stream chunk
@@ -290,10 +310,10 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (n_cells <= 0) return DR_OK;
     DR_REQUIRE(ctx, forest && cells && tile, "null pointer");
     const dr_forest_ranked& f = *forest;
-    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_feat >= 0 && f.n_feat <= 127, "the ranked kernel takes at most 127 features");
-    DR_REQUIRE(ctx, f.baseline && f.feat_col && f.rank_lut_off && f.class_code && f.chunk_tree_off && f.chunk_seq &&
-                        f.chunk_node_off && f.chunk_leaf_off && f.chunk_hdr_off && f.tree_hdr && f.node_word &&
-                        f.leaf_value, "null forest array");
+    DR_REQUIRE(ctx, f.n_seq >= 1 && f.n_slots >= 0 && f.n_slots <= 255, "the ranked kernel takes at most 255 rank slots");
+    DR_REQUIRE(ctx, f.baseline && f.slot_col && f.rank_lut_off && f.rank_lut && f.slot_nan && f.class_code &&
+                        f.chunk_tree_off && f.chunk_seq && f.chunk_node_off && f.chunk_leaf_off && f.chunk_hdr_off &&
+                        f.tree_hdr && f.node_word && f.leaf_value, "null forest array");
     DR_REQUIRE(ctx, f.n_chunks >= 1, "the ranked forest needs at least one chunk (one tree per sequence)");
     DR_REQUIRE(ctx, ((uintptr_t)f.node_word & 15) == 0 && ((uintptr_t)f.leaf_value & 15) == 0 &&
                         ((uintptr_t)f.tree_hdr & 15) == 0, "node / leaf / header arrays must be 16-byte aligned");
@@ -308,18 +328,15 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     p.n_cells = n_cells;
     p.target_col = target_col;
     p.out_margin = out_margin;
-    // a leaf's self-loop reads (and ignores) the rank slot named by its leaf number: the byte tile is
-    // padded by 256 bytes for that, the wide tile is only used when every leaf number is a valid slot
+    // a leaf's self-loop reads (and ignores) rank slot 0: the tile always holds at least one slot
     const size_t fixed = kStages * sizeof(ChunkBuf) + kStages * 16;
     constexpr size_t kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
-    const int n_slots = 2 * f.n_feat > 0 ? 2 * f.n_feat : 1;
-    DR_REQUIRE(ctx, f.max_tree_leaves >= 1 && f.max_tree_leaves <= 256, "bad max_tree_leaves");
+    const int n_slots = f.n_slots > 0 ? f.n_slots : 1;
     DR_REQUIRE(ctx, f.layout >= 0 && f.layout <= 3, "bad layout");
     const size_t smem_512 = fixed + (size_t)n_slots * 512 * 4, smem_256 = fixed + (size_t)n_slots * 256 * 4;
-    const bool leaves_ok = f.max_tree_leaves <= n_slots;
-    const bool wide_ok = leaves_ok && smem_256 <= kMaxSmem;
+    const bool wide_ok = smem_256 <= kMaxSmem;
     if (f.layout >= 2 && !wide_ok)
-        return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide feature tile does not fit a forest with %d features", f.n_feat);
+        return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide rank tile does not fit a forest with %d slots", f.n_slots);
     auto launch = [&](auto kernel, int threads, size_t smem, int per_sm) -> int {
         DR_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = dr_grid_for(ctx, n_cells, threads, per_sm);
@@ -329,18 +346,17 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
     if (wide_ok && f.layout != 1) {
         p.feat_stride = 0;
         int rc;
-        if (smem_512 <= kMaxSmem) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
+        if (smem_512 <= kMaxSmem && f.layout == 0) rc = launch(k_forest_predict_ranked<true, 512, 8>, 512, smem_512, 1);
         else if (f.layout == 2)     rc = launch(k_forest_predict_ranked<true, 256, 8>, 256, smem_256, 1);
         else                        rc = launch(k_forest_predict_ranked<true, 256, 16>, 256, smem_256, 1);
         if (rc != DR_OK) return rc;
     } else {
-        int words = (2 * f.n_feat + 3) / 4;
-        if (words < 1) words = 1;
+        int words = (n_slots + 3) / 4;
         if ((words & 1) == 0) ++words;  // odd word stride: consecutive threads land on different banks
         p.feat_stride = words * 4;
-        const size_t smem = fixed + (size_t)kByteThreads * p.feat_stride + 256;
-        if (smem > 200 * 1024)
-            return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d features exceeds shared memory", f.n_feat);
+        const size_t smem = fixed + (size_t)kByteThreads * p.feat_stride;
+        if (smem > kMaxSmem)
+            return dr_fail(ctx, DR_ERR_UNSUPPORTED, "ranked forest with %d slots exceeds shared memory", f.n_slots);
         const int rc = launch(k_forest_predict_ranked<false, kByteThreads, 8>, kByteThreads, smem,
                               smem <= 110 * 1024 ? 2 : 1);
         if (rc != DR_OK) return rc;

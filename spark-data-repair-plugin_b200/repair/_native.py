@@ -31,12 +31,12 @@ class dr_forest(ctypes.Structure):
 class dr_forest_ranked(ctypes.Structure):
     _fields_ = [
         ("n_seq", c_int32), ("n_trees", c_int32), ("n_nodes", c_int32), ("n_leaves", c_int32),
-        ("n_feat", c_int32), ("max_depth", c_int32), ("n_chunks", c_int32), ("max_tree_leaves", c_int32),
-        ("layout", c_int32),
+        ("n_slots", c_int32), ("max_depth", c_int32), ("n_chunks", c_int32), ("layout", c_int32),
         ("chunk_tree_off", c_void_p), ("chunk_seq", c_void_p), ("chunk_node_off", c_void_p),
         ("chunk_leaf_off", c_void_p), ("chunk_hdr_off", c_void_p), ("tree_hdr", c_void_p),
-        ("node_word", c_void_p), ("leaf_value", c_void_p), ("baseline", c_void_p), ("feat_col", c_void_p),
-        ("rank_lut_off", c_void_p), ("rank_lut", c_void_p), ("class_code", c_void_p), ("n_classes", c_int32),
+        ("node_word", c_void_p), ("leaf_value", c_void_p), ("baseline", c_void_p), ("slot_col", c_void_p),
+        ("rank_lut_off", c_void_p), ("rank_lut", c_void_p), ("slot_nan", c_void_p), ("class_code", c_void_p),
+        ("n_classes", c_int32),
     ]
 
 

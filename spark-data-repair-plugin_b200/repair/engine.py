@@ -52,6 +52,7 @@ class DetectResult:
         self.domain_stats = {}
         self.disc_attrs = []
         self.n_cells = {}
+        self.n_cells_detected = {}
         self.weak_removed = 0
 
 
@@ -488,6 +489,7 @@ class Engine:
         self.scan_hist([a for a in res.disc_attrs if a not in self._hist_cache], fused)
         res.bitmaps = bitmaps
         res.n_cells = dict(zip(bitmaps.keys(), self.ctx.bitmap_count_many(list(bitmaps.values()), self.n_rows)))
+        res.n_cells_detected = dict(res.n_cells)     # before the weak-label pruning of the domain analysis
         total = sum(res.n_cells.values())
         if self.dist is not None:
             t = self.torch.tensor([total], dtype=self.torch.int64, device=self.device)

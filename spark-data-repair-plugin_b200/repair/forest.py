@@ -192,16 +192,52 @@ def forest_shape_stats(forest):
             "mean_leaf_depth": float(node_depth[reach].mean())}
 
 
+def pair_order(kept, is_leaf_new_order):
+    """Final tree-relative node order for the rank-coded image: the root, then the sibling pairs
+    (breadth-first numbering of bfs_relabel: pair p of a tree = nodes 2p+1, 2p+2) stably sorted by class --
+    two internal nodes, one of each, two leaves -- so that every leaf of a tree sits in the tail
+    [first_leaf, n_nodes) and the leaf-value array indexed by `node - first_leaf` wastes at most one
+    slot per mixed pair.  kept: nodes per tree; is_leaf_new_order: leaf flag per node in breadth-first
+    order (all trees concatenated).  -> (final index per node in that order, first_leaf per tree)."""
+    n_trees = len(kept)
+    starts = np.zeros(n_trees + 1, dtype=np.int64)
+    starts[1:] = np.cumsum(kept)
+    n_pairs = (kept - 1) // 2
+    pstart = np.zeros(n_trees + 1, dtype=np.int64)
+    pstart[1:] = np.cumsum(n_pairs)
+    ptree = np.repeat(np.arange(n_trees), n_pairs)
+    pidx = np.arange(int(pstart[-1])) - pstart[ptree]                 # pair number inside its tree
+    lpos = starts[ptree] + 1 + 2 * pidx                               # left node of the pair (new order)
+    pclass = is_leaf_new_order[lpos].astype(np.int64) + is_leaf_new_order[lpos + 1].astype(np.int64)
+    order = np.lexsort((pidx, pclass, ptree))                          # stable inside (tree, class)
+    rank_in_tree = np.empty(len(order), dtype=np.int64)
+    rank_in_tree[order] = np.arange(len(order)) - pstart[ptree[order]]
+    fin = np.zeros(int(starts[-1]), dtype=np.int64)                    # roots stay at 0
+    fin[lpos] = 1 + 2 * rank_in_tree
+    fin[lpos + 1] = 2 + 2 * rank_in_tree
+    tree_of = np.repeat(np.arange(n_trees), kept)
+    big = np.iinfo(np.int64).max
+    first_leaf = np.full(n_trees, big, dtype=np.int64)
+    np.minimum.at(first_leaf, tree_of[is_leaf_new_order], fin[is_leaf_new_order])
+    return fin, first_leaf
+
+
 def rank_code(spec, dict_sizes):
     """Rank-coded image of an all-discrete model for dr_forest_predict_ranked, or None when the
-    model does not qualify (continuous feature, > 253 distinct values per feature, > 127 features, a
-    tree with more than 256 leaves).  Decisions are unchanged: `x <= thr` <=> `rank(x) < #values <= thr`.
+    model does not qualify (continuous feature, > 253 distinct values per feature, > 255 rank slots).
+    Decisions are unchanged: `x <= thr` <=> `rank(x) < #values <= thr`.
 
-    Trees are renumbered breadth first with siblings adjacent (bfs_relabel); `word` holds the node
-    words with TREE-relative child indices (ranked_image rebases them to the chunk):
-      internal  (2*feature + nan_left) << 24 | left child << 8 | (256 - (thr_rank + 1))
-      leaf      leaf number in the tree  << 24 | own index  << 8 | 0
-    so that `word + rank` carries into the child field exactly when the row goes right."""
+    A rank SLOT is one (encoded feature, NaN direction) combination that some node of the forest
+    actually tests: its LUT maps a dictionary code (+1) to rank + 1 (1..254), with NaN already folded
+    to 0 (nodes that send NaN left) or 255 (right).  Features no node tests get no slot.
+    Nodes of a tree are ordered by pair_order(); `word` holds the node words with TREE-relative child
+    indices (ranked_image rebases them to the chunk):
+      internal  slot << 24 | left child << 8 | (256 - (thr_rank + 1))     right child = left child + 1
+      leaf      own index << 8                                            (slot 0, never carries)
+    so that `word + rank` carries into the child field exactly when the row goes right, and a leaf
+    stays where it is.  `leaf_value` holds, per tree, the values of nodes first_leaf .. n_nodes-1
+    (0 for the few internal nodes in that range): the value of the node a walk ends on is
+    leaf_value[tree_leaf_off[t] + node - first_leaf[t]], no look-up of the leaf's own word needed."""
     f = spec["forest"]
     encoders = spec["encoders"]
     if any(e["type"] == "cont" for e in encoders) or spec.get("class_codes") is None:
@@ -213,23 +249,13 @@ def rank_code(spec, dict_sizes):
             luts.append(lut[:, j])
             feat_attr.append(e["attr"])
     n_feat = len(luts)
-    if n_feat != int(f["n_features"]) or n_feat > 127:
+    if n_feat != int(f["n_features"]):
         return None
-    rank_lut, rank_off, values = [], [0], []
-    for col in luts:
-        vals = np.unique(col[~np.isnan(col)])
-        if len(vals) > 253:
-            return None
-        r = np.full(len(col), 255, dtype=np.uint8)
-        ok = ~np.isnan(col)
-        r[ok] = (np.searchsorted(vals, col[ok]) + 1).astype(np.uint8)  # ranks are stored +1 (1..254)
-        rank_lut.append(r)
-        rank_off.append(rank_off[-1] + len(r))
-        values.append(vals)
     toff = np.asarray(f["tree_offset"], dtype=np.int64)
     feat = np.asarray(f["feature"], dtype=np.int64)
     is_leaf = feat < 0
     left, right = np.asarray(f["left"], dtype=np.int64), np.asarray(f["right"], dtype=np.int64)
+    ml_all = np.asarray(f["missing_left"], dtype=np.int64) & 1
     new, kept, tree_depth = bfs_relabel(toff, left, right, is_leaf)
     depth = int(tree_depth.max()) if len(tree_depth) else 0
     new_toff = np.zeros(len(toff), dtype=np.int64)
@@ -237,40 +263,68 @@ def rank_code(spec, dict_sizes):
     old_sizes = toff[1:] - toff[:-1]
     tree_of = np.repeat(np.arange(len(old_sizes)), old_sizes)
     live = new >= 0
-    pos = new_toff[tree_of[live]] + new[live]                      # new global slot of every kept node
-    src = np.empty(int(new_toff[-1]), dtype=np.int64)
-    src[pos] = np.flatnonzero(live)                                # old node stored in each new slot
+    pos = new_toff[tree_of[live]] + new[live]                      # BFS slot of every kept node
+    src_bfs = np.empty(int(new_toff[-1]), dtype=np.int64)
+    src_bfs[pos] = np.flatnonzero(live)                            # old node stored in each BFS slot
+    fin_bfs, first_leaf = pair_order(kept, is_leaf[src_bfs])
+    n_tree_bfs = tree_of[src_bfs]
+    src = np.empty_like(src_bfs)
+    src[new_toff[n_tree_bfs] + fin_bfs] = src_bfs                  # old node stored in each FINAL slot
+    fin_of_old = np.full(len(feat), -1, dtype=np.int64)
+    fin_of_old[src_bfs] = fin_bfs
+    # rank slots: the (feature, NaN direction) combinations the reachable internal nodes test
+    used = live & ~is_leaf
+    combo = np.unique(feat[used] * 2 + ml_all[used])
+    if len(combo) > 255:
+        return None
+    slot_of = np.full(2 * max(n_feat, 1), 0, dtype=np.int64)
+    slot_of[combo] = np.arange(len(combo))
+    rank_lut, rank_off, slot_attr, slot_nan, values = [], [0], [], [], {}
+    for cb in combo.tolist():
+        j, nan_left = cb >> 1, cb & 1
+        col = luts[j]
+        if j not in values:
+            values[j] = np.unique(col[~np.isnan(col)])
+        vals = values[j]
+        if len(vals) > 253:
+            return None
+        nan_byte = 0 if nan_left else 255
+        r = np.full(len(col), nan_byte, dtype=np.uint8)
+        ok = ~np.isnan(col)
+        r[ok] = (np.searchsorted(vals, col[ok]) + 1).astype(np.uint8)  # ranks are stored +1 (1..254)
+        rank_lut.append(r)
+        rank_off.append(rank_off[-1] + len(r))
+        slot_attr.append(feat_attr[j])
+        slot_nan.append(nan_byte)
     thr = np.asarray(f["threshold"], dtype=np.float64)
     thr_rank = np.zeros(len(feat), dtype=np.int64)
-    for j in range(n_feat):  # number of distinct values <= threshold, per feature
-        m = feat == j
-        if m.any():
-            thr_rank[m] = np.searchsorted(values[j], thr[m], side="right")
+    for j in values:  # number of distinct values <= threshold, per feature
+        m = used & (feat == j)
+        thr_rank[m] = np.searchsorted(values[j], thr[m], side="right")
     n_leaf = is_leaf[src]
     n_tree = tree_of[src]
-    leaf_cum = np.cumsum(n_leaf) - n_leaf                          # leaves before each slot
-    tree_leaf_off = np.zeros(len(toff), dtype=np.int64)
-    tree_leaf_off[:-1] = leaf_cum[new_toff[:-1]] if len(old_sizes) else 0
-    tree_leaf_off[-1] = int(n_leaf.sum())
-    leaf_no = leaf_cum - tree_leaf_off[n_tree] if len(src) else leaf_cum
-    if len(leaf_no) and leaf_no[n_leaf].size and leaf_no[n_leaf].max() > 255:
-        return None
     own = np.arange(len(src), dtype=np.int64) - new_toff[n_tree]
-    ml = np.asarray(f["missing_left"], dtype=np.int64)[src] & 1
-    child = new[np.where(n_leaf, src, toff[n_tree] + left[src])]   # left child, tree relative
+    child = fin_of_old[np.where(n_leaf, src, toff[n_tree] + left[src])]   # left child, tree relative
     cthr = 256 - (thr_rank[src] + 1)                               # thr in 1..254 -> 2..255
-    internal = ((feat[src] * 2 + ml) << 24) | (child << 8) | cthr
-    leaf = (leaf_no << 24) | (own << 8)
+    slot = slot_of[np.where(n_leaf, 0, feat[src] * 2 + ml_all[src])]
+    internal = (slot << 24) | (child << 8) | cthr
+    leaf = own << 8
     word = np.where(n_leaf, leaf, internal).astype(np.uint32)
-    return {"word": word, "tree_offset": new_toff, "leaf_value": np.asarray(f["value"], dtype=np.float64)[src][n_leaf],
-            "tree_leaf_off": tree_leaf_off, "rank_lut": np.concatenate(rank_lut) if rank_lut else np.zeros(1, np.uint8),
-            "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "feat_attr": feat_attr, "max_depth": depth,
-            "tree_depth": tree_depth,
-            "max_tree_leaves": int((tree_leaf_off[1:] - tree_leaf_off[:-1]).max()) if len(old_sizes) else 1}
+    n_vals = kept - first_leaf                                     # value slots per tree
+    tree_leaf_off = np.zeros(len(toff), dtype=np.int64)
+    tree_leaf_off[1:] = np.cumsum(n_vals)
+    leaf_value = np.zeros(int(tree_leaf_off[-1]), dtype=np.float64)
+    vpos = tree_leaf_off[n_tree] + own - first_leaf[n_tree]
+    leaf_value[vpos[n_leaf]] = np.asarray(f["value"], dtype=np.float64)[src][n_leaf]
+    return {"word": word, "tree_offset": new_toff, "leaf_value": leaf_value, "tree_leaf_off": tree_leaf_off,
+            "first_leaf": first_leaf, "rank_lut": np.concatenate(rank_lut) if rank_lut else np.zeros(1, np.uint8),
+            "rank_lut_off": np.asarray(rank_off, dtype=np.int32), "slot_attr": slot_attr,
+            "slot_nan": np.asarray(slot_nan if slot_nan else [0], dtype=np.uint8), "n_slots": len(combo),
+            "max_depth": depth, "tree_depth": tree_depth}
 
 
 # DR_RANKED_CHUNK_* in include/b200repair.h
-RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 4096, 2176, 256, 16
+RANKED_CHUNK_NODES, RANKED_CHUNK_LEAVES, RANKED_CHUNK_TREES, RANKED_GROUP = 4096, 2560, 256, 16
 
 
 def ranked_image(rk, order, seq_tree_off):
@@ -278,7 +332,8 @@ def ranked_image(rk, order, seq_tree_off):
     of whole trees that fit the kernel's shared-memory buffers (never straddling a sequence; a
     multiple of RANKED_GROUP trees except at the end of a sequence).  Every chunk starts on a 16-byte
     boundary of the node / leaf / header arrays (TMA granules); child indices are rebased to the
-    chunk; tree_hdr holds, per tree, (root word, first leaf) relative to the chunk."""
+    chunk; tree_hdr holds, per tree, (root word, value bias) relative to the chunk: the value of the
+    chunk-relative node c a walk ends on is leaf[chunk_leaf_off + bias + c] (bias is a signed int32)."""
     toff = np.asarray(rk["tree_offset"], dtype=np.int64)
     lo = np.asarray(rk["tree_leaf_off"], dtype=np.int64)
     order = np.asarray(order, dtype=np.int64)
@@ -323,7 +378,8 @@ def ranked_image(rk, order, seq_tree_off):
     slot = chunk_hdr_off[chunk_of_tree] + (np.arange(len(order)) - cto[:-1][chunk_of_tree])
     roots = chunk_node_off[chunk_of_tree] + node_in_chunk
     hdr[slot, 0] = word[roots] if len(order) else 0
-    hdr[slot, 1] = leaf_in_chunk
+    bias = leaf_in_chunk - (node_in_chunk + np.asarray(rk["first_leaf"], dtype=np.int64)[order])
+    hdr[slot, 1] = bias.astype(np.int32).view(np.uint32) if len(order) else 0
     return {"word": word, "leaf": leaf, "tree_hdr": hdr.reshape(-1),
             "chunk_tree_off": cto.astype(np.int32), "chunk_seq": np.asarray(chunk_seq, dtype=np.int32),
             "chunk_node_off": chunk_node_off.astype(np.int32), "chunk_leaf_off": chunk_leaf_off.astype(np.int32),
@@ -396,9 +452,14 @@ class DeviceModel:
         self.n_nodes = s.n_nodes
         self.ranked = None
         rk = rank_code(spec, dict_sizes) if self.kind == 0 else None
+        img = None
         if rk is not None and len(order) and np.all(np.diff(off) > 0):
+            try:
+                img = ranked_image(rk, order, off)
+            except ValueError:  # a tree larger than a chunk buffer: the generic kernel takes the model
+                img = None
+        if img is not None:
             from ._native import dr_forest_ranked
-            img = ranked_image(rk, order, off)
             self._keep.update({
                 "r_node_word": dev(img["word"].view(np.int32), np.int32),
                 "r_leaf_value": dev(img["leaf"], np.float64),
@@ -410,20 +471,21 @@ class DeviceModel:
                 "r_tree_hdr": dev(img["tree_hdr"].view(np.int32), np.int32),
                 "r_rank_lut": dev(rk["rank_lut"], np.uint8),
                 "r_rank_lut_off": dev(rk["rank_lut_off"], np.int32),
-                "r_feat_col": dev([feature_tile_cols[a] for a in rk["feat_attr"]] or [0], np.int32),
+                "r_slot_col": dev([feature_tile_cols[a] for a in rk["slot_attr"]] or [0], np.int32),
+                "r_slot_nan": dev(rk["slot_nan"], np.uint8),
             })
             r = dr_forest_ranked()
             r.n_seq, r.n_trees, r.n_nodes, r.n_leaves = s.n_seq, s.n_trees, len(img["word"]), len(img["leaf"])
-            r.n_feat, r.max_depth, r.n_chunks = n_feat, int(rk["max_depth"]), len(img["chunk_seq"])
-            # DR_RANKED_LAYOUT=bytes|wide8|wide16 pins the shared-memory feature tile (profiling aid)
-            r.max_tree_leaves = int(rk["max_tree_leaves"])
+            r.n_slots, r.max_depth, r.n_chunks = int(rk["n_slots"]), int(rk["max_depth"]), len(img["chunk_seq"])
+            # DR_RANKED_LAYOUT=bytes|wide8|wide16 pins the shared-memory rank tile (profiling aid)
             r.layout = {"": 0, "bytes": 1, "wide8": 2, "wide16": 3}[os.environ.get("DR_RANKED_LAYOUT", "")]
             for field, key in (("chunk_tree_off", "r_chunk_tree_off"), ("chunk_seq", "r_chunk_seq"),
                                ("chunk_node_off", "r_chunk_node_off"), ("chunk_leaf_off", "r_chunk_leaf_off"),
                                ("chunk_hdr_off", "r_chunk_hdr_off"), ("tree_hdr", "r_tree_hdr"),
                                ("node_word", "r_node_word"), ("leaf_value", "r_leaf_value"),
-                               ("baseline", "baseline"), ("feat_col", "r_feat_col"),
+                               ("baseline", "baseline"), ("slot_col", "r_slot_col"),
                                ("rank_lut_off", "r_rank_lut_off"), ("rank_lut", "r_rank_lut"),
+                               ("slot_nan", "r_slot_nan"),
                                ("class_code", "class_code")):
                 setattr(r, field, self._keep[key].data_ptr())
             r.n_classes = s.n_classes

@@ -641,8 +641,13 @@ def repair_cells_encoded(rm, engine, table, res, models):
     D = int(drows.numel())
     rm.last_run["n_dirty_rows"] = D
     engine.mark("repair:dirty tile")
-    run_chain(engine, table, [(y, m) for y, m in models if y in targets], tile, ctile, D)
+    chain = [(y, m) for y, m in models if y in targets]
+    run_chain(engine, table, chain, tile, ctile, D)
     engine.mark("repair:chain")
+    # kept until the next pass for after-the-fact checks (bench.py --verify): the filled tile, its rows,
+    # the NULL state of every tile column BEFORE the chain and the order the models ran in
+    engine.last_repair = {"tile": tile, "drows": drows, "D": D, "nulls": engine.tile_nulls,
+                          "chain": [y for y, _ in chain]}
     dpos = torch.empty(E, dtype=torch.int32, device=engine.device)
     engine.ctx.lookup_sorted(drows, D, rows_all, E, dpos)
     for a, o, n in seg:

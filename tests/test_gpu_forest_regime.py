@@ -84,9 +84,8 @@ def test_ranked_forest_many_tiles_per_cta(ctx, n_classes, n_iter, extra):
     # oracle label rule (oracle/forest.py forest_predict): binary margin > 0, multiclass argmax, ties -> lowest
     lab = (want_m[:, 0] > 0).astype(np.int32) if want_m.shape[1] == 1 else np.argmax(want_m, axis=1).astype(np.int32)
     assert np.array_equal(forest_predict(forest, X[:2048]).astype(np.int32), lab[:2048])
-    variants = ["auto", "bytes"]
-    if dm.ranked.max_tree_leaves <= 2 * n_feat:
-        variants += ["wide8", "wide16"]
+    variants = ["auto", "bytes", "wide8", "wide16"]
+    assert (dm.ranked.n_slots > 72) == bool(extra)               # past the 512-cell tile: the 256-cell kernels
     k = len(doms)
     for variant in variants:
         dm.ranked.layout = {"auto": 0, "bytes": 1, "wide8": 2, "wide16": 3}[variant]

@@ -448,8 +448,7 @@ def test_forest_predict_ranked_matches_oracle_and_generic(ctx, n_classes, n_iter
     cells = np.sort(rng.choice(n, size=n * 2 // 3, replace=False)).astype(np.int32)
     X = encode_matrix(encoders, {nm: tile_np[cells, tile_cols[nm]] for nm in names[1:]}, {}, dict_sizes)
     want_m, want = forest_margins(forest, X), forest_predict(forest, X)
-    assert dm.ranked.max_tree_leaves <= 2 * n_feat          # so that the wide feature tile is exercised too
-    assert (n_feat > 37) == bool(extra) and n_feat <= 75
+    assert (dm.ranked.n_slots > 72) == bool(extra) and dm.ranked.n_slots <= 148   # 512- / 256-cell wide tiles
     for variant in ("auto", "bytes", "wide8", "wide16", "generic"):
         dm.ranked.layout = {"auto": 0, "bytes": 1, "wide8": 2, "wide16": 3, "generic": 0}[variant]
         tile = dev(tile_np)

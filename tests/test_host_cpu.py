@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "missing export: " + sym
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 1
+    assert lib.dr_abi_version() == 2
     raw = ctypes.CDLL(_native.LIB_PATH)
     for sym in declared:
         getattr(raw, sym)
@@ -397,33 +397,13 @@ def test_synthetic_generator_is_shardable_and_deterministic():
     assert any(len(set(dep[(det == v)].tolist())) > 1 for v in range(spec.dom[5] - 3, spec.dom[5]))
 
 
-def _walk_ranked(words, base, w, ranks_of_row, depth):
-    """One tree of the carry-coded layout for one row: -> leaf number within the tree."""
-    for _ in range(depth):
-        fsel = w >> 24
-        r = 0
-        if w & 0xFF:                                     # internal node (a leaf never reads its rank)
-            r = int(ranks_of_row[fsel >> 1])
-            r = (0 if (fsel & 1) else 255) if r == 255 else r
-        w2 = w + r                                       # carries into bit 8 iff rank >= threshold
-        w = int(words[base + ((w2 >> 8) & 0xFFFF)])
-    assert (w & 0xFF) == 0                               # a leaf: never carries ...
-    return w >> 24, (w >> 8) & 0xFFFF                    # ... and points at itself
-
-
-def _eval_ranked(rk, forest, codes_by_feat):
-    """Reference evaluation of the rank-coded layout (what k_forest_predict_ranked does)."""
-    n = len(codes_by_feat[0])
-    toff = np.asarray(rk["tree_offset"])
-    raw = np.tile(np.asarray(forest["baseline"], dtype=np.float64), (n, 1))
-    ranks = np.stack([rk["rank_lut"][rk["rank_lut_off"][j] + codes_by_feat[j] + 1]
-                      for j in range(len(codes_by_feat))], axis=1)
-    for t in range(len(toff) - 1):
-        for i in range(n):
-            leaf_no, own = _walk_ranked(rk["word"], toff[t], int(rk["word"][toff[t]]), ranks[i], rk["max_depth"])
-            assert int(rk["word"][toff[t] + own]) >> 24 == leaf_no
-            raw[i, forest["tree_seq"][t]] += rk["leaf_value"][rk["tree_leaf_off"][t] + leaf_no]
-    return raw
+def _image_margins(spec, dict_sizes, codes):
+    from ranked_emul import eval_image
+    from repair.forest import group_by_sequence, rank_code, ranked_image
+    rk = rank_code(spec, dict_sizes)
+    off, order = group_by_sequence(spec["forest"])
+    img = ranked_image(rk, order, off)
+    return rk, img, off, order, eval_image(rk, img, spec["forest"]["baseline"], codes)
 
 
 def test_rank_coded_forest_makes_the_same_decisions():
@@ -439,21 +419,53 @@ def test_rank_coded_forest_makes_the_same_decisions():
     thr = [[-1.5, -0.5, 0.5, 1.5]] * 3 + [[-3.0, -1.0, 0.5, 3.5, 7.5, 12.5, 20.0]] + [[-0.5, 0.5]] * 2
     forest = random_forest(n_feat, 3, 6, thr, rng, leaf_scale=0.2)
     spec = {"forest": forest, "encoders": encoders, "class_codes": [0, 1, 2]}
-    rk = rank_code(spec, dict_sizes)
-    assert rk is not None and rk["max_depth"] <= 7
     n = 200
-    codes = {a: rng.integers(-1, d, size=n) for a, d in dict_sizes.items()}
-    X = encode_matrix(encoders, codes, {}, dict_sizes)
-    by_feat = [codes[a] for a in rk["feat_attr"]]
-    assert np.array_equal(_eval_ranked(rk, forest, by_feat), forest_margins(forest, X))
+    codes = {a: rng.integers(-1, d + 1, size=n) for a, d in dict_sizes.items()}   # d = "unknown category"
+    rk, img, _, _, got = _image_margins(spec, dict_sizes, codes)
+    assert rk is not None and rk["max_depth"] <= 7 and 1 <= rk["n_slots"] <= 2 * n_feat
+    inr = {a: np.where(codes[a] < dict_sizes[a], codes[a], 0) for a in codes}
+    X = encode_matrix(encoders, inr, {}, dict_sizes)
+    j = 0
+    for e in encoders:  # a code outside the dictionary encodes to NaN in every column of its encoder
+        w = encoder_width(e)
+        X[codes[e["attr"]] >= dict_sizes[e["attr"]], j:j + w] = np.nan
+        j += w
+    assert np.array_equal(got, forest_margins(forest, X))
     spec["encoders"] = encoders + [{"attr": "x", "type": "cont"}]
     assert rank_code(spec, dict_sizes) is None  # continuous feature -> generic kernel
+
+
+def test_rank_slots_only_for_tested_feature_directions():
+    """One slot per (feature, NaN direction) that a node tests; a forest whose nodes all send NaN the
+    same way needs one slot per tested feature."""
+    from oracle.forest import forest_margins
+    from repair.forest import encode_matrix, rank_code
+    from tools.randforest import random_forest
+    rng = np.random.default_rng(11)
+    dict_sizes = {"a": 9, "b": 30}
+    encoders = [{"attr": "a", "type": "sum", "categories": list(range(9))},
+                {"attr": "b", "type": "ordinal", "categories": list(range(28))}]   # codes 28, 29 unseen -> NaN
+    thr = [[-0.5, 0.5]] * 8 + [[j + 0.5 for j in range(1, 28)]]
+    forest = random_forest(9, 4, 10, thr, rng)
+    forest["missing_left"][:] = 0
+    forest["feature"] = np.where(forest["feature"] == 3, 4, forest["feature"]).astype(np.int32)  # feature 3 unused
+    spec = {"forest": forest, "encoders": encoders, "class_codes": [0, 1, 2, 3]}
+    rk = rank_code(spec, dict_sizes)
+    used = set(int(f) for f in forest["feature"] if f >= 0)
+    assert 3 not in used and rk["n_slots"] == len(used)
+    codes = {a: rng.integers(-1, d, size=300) for a, d in dict_sizes.items()}
+    got = _image_margins(spec, dict_sizes, codes)[4]
+    assert np.array_equal(got, forest_margins(forest, encode_matrix(encoders, codes, {}, dict_sizes)))
+    forest["missing_left"][::3] = 1                              # both directions now -> more slots
+    assert rank_code(spec, dict_sizes)["n_slots"] > len(used)
+    got = _image_margins(spec, dict_sizes, codes)[4]
+    assert np.array_equal(got, forest_margins(forest, encode_matrix(encoders, codes, {}, dict_sizes)))
 
 
 def test_ranked_image_padding_and_chunks():
     from oracle.forest import forest_margins
     from repair.forest import (RANKED_CHUNK_LEAVES, RANKED_CHUNK_NODES, RANKED_CHUNK_TREES, RANKED_GROUP,
-                               encode_matrix, encoder_width, group_by_sequence, rank_code, ranked_image)
+                               encode_matrix, encoder_width)
     from tools.randforest import random_forest
     rng = np.random.default_rng(8)
     dict_sizes = {"a": 6, "b": 20}
@@ -461,9 +473,10 @@ def test_ranked_image_padding_and_chunks():
                 {"attr": "b", "type": "ordinal", "categories": list(range(20))}]
     n_feat = sum(encoder_width(e) for e in encoders)
     forest = random_forest(n_feat, 7, 120, [[-0.5, 0.5]] * 5 + [[j + 0.5 for j in range(1, 20)]], rng)
-    rk = rank_code({"forest": forest, "encoders": encoders, "class_codes": list(range(7))}, dict_sizes)
-    off, order = group_by_sequence(forest)
-    img = ranked_image(rk, order, off)
+    spec = {"forest": forest, "encoders": encoders, "class_codes": list(range(7))}
+    n = 40
+    codes = {a: rng.integers(-1, d, size=n) for a, d in dict_sizes.items()}
+    rk, img, off, order, got = _image_margins(spec, dict_sizes, codes)
     cto, cs = img["chunk_tree_off"], img["chunk_seq"]
     cn, cl, ch = img["chunk_node_off"], img["chunk_leaf_off"], img["chunk_hdr_off"]
     assert np.all(cn % 4 == 0) and np.all(cl % 2 == 0) and np.all(ch % 2 == 0)
@@ -474,21 +487,37 @@ def test_ranked_image_padding_and_chunks():
         assert cto[c + 1] - cto[c] <= RANKED_CHUNK_TREES
         assert (cto[c + 1] - cto[c]) % RANKED_GROUP == 0 or cto[c + 1] == off[cs[c] + 1]
     assert list(cs) == sorted(cs) and set(cs) == set(range(7))
-    # walking the chunked image (chunk-absolute child indices, root words in the headers) gives the
-    # oracle's margins
-    n = 40
-    codes = {a: rng.integers(-1, d, size=n) for a, d in dict_sizes.items()}
+    # every leaf of a tree sits in the tail its values are stored for; few slots are wasted on internal nodes
+    toff, first = rk["tree_offset"], rk["first_leaf"]
+    for t in range(len(first)):
+        w = rk["word"][toff[t]:toff[t + 1]]
+        leaves = np.nonzero((w & 0xFF) == 0)[0]
+        assert leaves.min() == first[t] and np.array_equal((w[leaves] >> 8) & 0xFFFF, leaves)
+    n_leaves = int(((rk["word"] & 0xFF) == 0).sum())
+    assert n_leaves <= len(rk["leaf_value"]) <= 1.35 * n_leaves
+    # walking the chunked image (chunk-absolute child indices, root words and value biases in the
+    # headers) gives the oracle's margins
+    assert np.array_equal(got, forest_margins(forest, encode_matrix(encoders, codes, {}, dict_sizes)))
+
+
+def test_ranked_image_of_stumps_and_single_leaf_trees():
+    """Depth 0 / 1 forests and mixed shapes: the walk's last level is the only level."""
+    from oracle.forest import forest_margins
+    from repair.forest import encode_matrix
+    from tools.randforest import random_forest
+    rng = np.random.default_rng(3)
+    dict_sizes = {"a": 4, "b": 17}
+    encoders = [{"attr": "a", "type": "sum", "categories": [0, 1, 2, 3]},
+                {"attr": "b", "type": "ordinal", "categories": list(range(17))}]
+    thr = [[-0.5, 0.5]] * 3 + [[j + 0.5 for j in range(1, 17)]]
+    codes = {a: rng.integers(-1, d, size=64) for a, d in dict_sizes.items()}
     X = encode_matrix(encoders, codes, {}, dict_sizes)
-    ranks = np.stack([rk["rank_lut"][rk["rank_lut_off"][j] + codes[a] + 1] for j, a in enumerate(rk["feat_attr"])], 1)
-    raw = np.tile(np.asarray(forest["baseline"], dtype=np.float64), (n, 1))
-    hdr = img["tree_hdr"].reshape(-1, 2)
-    for c in range(len(cs)):
-        for j in range(cto[c + 1] - cto[c]):
-            root, first_leaf = int(hdr[ch[c] + j, 0]), int(hdr[ch[c] + j, 1])
-            for i in range(n):
-                leaf_no, _ = _walk_ranked(img["word"], cn[c], root, ranks[i], rk["max_depth"])
-                raw[i, cs[c]] += img["leaf"][cl[c] + first_leaf + leaf_no]
-    assert np.array_equal(raw, forest_margins(forest, X))
+    for max_depth, max_leaves in ((0, 1), (1, 2), (2, 3), (7, 31)):
+        forest = random_forest(4, 3, 9, thr, rng, max_depth=max_depth, max_leaves=max_leaves)
+        spec = {"forest": forest, "encoders": encoders, "class_codes": [0, 1, 2]}
+        rk, img, _, _, got = _image_margins(spec, dict_sizes, codes)
+        assert rk["max_depth"] <= max_depth
+        assert np.array_equal(got, forest_margins(forest, X)), max_depth
 
 
 def test_misc_repair_applies_updates_like_the_reference():
