@@ -30,6 +30,8 @@ extern "C" {
 #endif
 
 #define DR_MAX_COLS 64 /* computeFreqStats' own limit, RepairApi.scala:241-244 */
+#define DR_MAX_PREDS 8     /* predicates of one denial constraint evaluated by dr_dc_exists */
+#define DR_MAX_SEGMENTS 32 /* segments of one packed exchange buffer (dr_combine_counts) */
 #define DR_OK 0
 #define DR_ERR_INVALID 1
 #define DR_ERR_CUDA 2
@@ -158,6 +160,37 @@ int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int6
 int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,
                          void* stream);
 
+/* ---- a3 (general): any two-tuple denial constraint -----------------------------------------------
+ * Replaces the generic `EXISTS (SELECT .. WHERE p1 AND p2 ..)` self semi-join of
+ * ErrorDetectorApi.scala:211-229 for predicate lists that are not of the FD / single-inequality
+ * shapes above.  A row's answer only depends on its projection onto the attributes the constraint
+ * references:
+ *   dr_key_presence  bit (sum_i (code_i + 1) * strides[i]) of `bits` is set for every row (OR-accumulated;
+ *                    key_space bits).  The set bits are the DISTINCT projections of the table.
+ *   dr_dc_exists     for distinct projection i (n of them, sorted so that the members of an equality
+ *                    group are contiguous): out[i] = 1 iff some j in [group_begin[i], group_end[i])
+ *                    satisfies every predicate q: sign[q](left[q][i], right[q][j]); operands are RANKS in
+ *                    a per-predicate common order (-1 = NULL): EQ is `<=>`, IQ is NOT(<=>), LT / GT are
+ *                    false on NULL (DenialConstraints.scala:66-79).
+ *   dr_key_flag      row bit |= viol_bits[key(row)].
+ * ---- 8(e): the exchange step of the row-sharded path --------------------------------------------
+ * dr_combine_counts: `gathered` = world copies (rank-major) of an n-element int64 buffer, the result
+ * of ONE all-gather; segment s = [seg_off[s], seg_off[s+1]) is reduced with seg_op[s] into out[0..n).
+ * Replaces the driver-side aggregation Spark does after every scan. */
+#define DR_RED_SUM 0
+#define DR_RED_MIN 1
+#define DR_RED_MAX 2
+#define DR_RED_OR 3
+int dr_key_presence(dr_ctx* ctx, const int32_t* const* cols, const int64_t* strides, int n_keys, int64_t n_rows,
+                    int64_t key_space, uint32_t* bits, void* stream);
+int dr_key_flag(dr_ctx* ctx, const int32_t* const* cols, const int64_t* strides, int n_keys, int64_t n_rows,
+                int64_t key_space, const uint32_t* viol_bits, uint32_t* row_bitmap, void* stream);
+int dr_dc_exists(dr_ctx* ctx, const int32_t* const* left, const int32_t* const* right, const int32_t* sign,
+                 int n_preds, int64_t n, const int32_t* group_begin, const int32_t* group_end, uint8_t* out,
+                 void* stream);
+int dr_combine_counts(dr_ctx* ctx, const int64_t* gathered, int world, int64_t n, const int64_t* seg_off,
+                      const int32_t* seg_op, int n_seg, int64_t* out, void* stream);
+
 /* ---- a7: discretisation of continuous attributes ----------------------------------------------
  * Replaces the projection of RepairApi.convertToDiscretizedTable (RepairApi.scala:126-169):
  *   out = (int)((v - vmin) / denom * thres)   (truncation toward zero), NaN -> -1; denom == 0 -> -1 */
@@ -181,6 +214,15 @@ int dr_pair_presence(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom
                      int64_t n_blocks, uint32_t* bits, void* stream);
 int dr_cooc(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
             const int32_t* py, int n_pairs, const int64_t* tab_off, int64_t n_rows, int64_t* out, void* stream);
+/* dr_cooc_skip: dr_cooc that leaves ONE entry per x value uncounted: rows with cy + 1 == skip[skip_off[p] + cx + 1]
+ * are not counted (skip: device int32, -1 = count everything; skip_off: host int64[n_pairs + 1], pair p has
+ * dom[px[p]] + 1 entries).  The caller restores table[x][skip[x]] = hist_x[x] - sum_y table[x][y] from the
+ * column histogram of the same rows.  With the skipped entry = the most frequent partner of every x the
+ * shared-memory atomics -- what bounds dr_cooc -- all but vanish on correlated pairs (the pairs the
+ * statistics select), at identical results. */
+int dr_cooc_skip(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+                 const int32_t* py, int n_pairs, const int64_t* tab_off, int64_t n_rows, const int32_t* skip,
+                 const int64_t* skip_off, int64_t* out, void* stream);
 
 /* ---- a9: cell-domain analysis (weak labelling) -------------------------------------------------
  * Replaces RepairApi.computeDomainInErrorCells (RepairApi.scala:479-675) + the weak-label test

@@ -18,6 +18,8 @@ struct PairParams {
     const int32_t* px;  // device, indices into `used` order
     const int32_t* py;
     const int32_t* off;  // device int32[n_pairs + 1], word/entry offsets relative to the launch
+    const int32_t* skip;      // counts only: device, entry (cx) of pair q at skip[skip_off[q] + cx], or nullptr
+    const int32_t* skip_off;  // device int32[n_pairs], offsets into `skip`
     int n_pairs;
     int64_t n_rows;
     int64_t block_rows;
@@ -74,7 +76,10 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ Pair
                 const int idx = cx * (p.dom[p.used[y]] + 1) + cy;
                 const int base = __ldg(p.off + q);
                 if (kCount) {
-                    atomicAdd(&tab[base + idx], 1u);
+                    // the most frequent partner of cx is not counted: the host restores it from the column
+                    // histogram (dr_cooc_skip) -- on correlated pairs that removes nearly every atomic
+                    if (p.skip == nullptr || __ldg(p.skip + __ldg(p.skip_off + q) + cx) != cy)
+                        atomicAdd(&tab[base + idx], 1u);
                 } else {
                     const uint32_t bit = 1u << (idx & 31);
                     uint32_t* w = &tab[base + (idx >> 5)];
@@ -99,7 +104,8 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ Pair
 template <bool kCount>
 int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
               const int32_t* py, int n_pairs, const int64_t* off, int64_t n_rows, int64_t block_rows,
-              int64_t n_blocks, void* out, cudaStream_t st) {
+              int64_t n_blocks, void* out, cudaStream_t st, const int32_t* skip = nullptr,
+              const int64_t* skip_off = nullptr) {
     DR_REQUIRE(ctx, cols && dom && px && py && off && out, "null pointer");
     DR_REQUIRE(ctx, n_cols >= 1 && n_cols <= DR_MAX_COLS, "n_cols must be in [1, 64]");
     DR_REQUIRE(ctx, n_rows < (int64_t)INT32_MAX, "n_rows must be < 2^31 per shard");
@@ -112,13 +118,13 @@ int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n
         DR_REQUIRE(ctx, dom[px[q]] < 65535 && dom[py[q]] < 65535, "domain too large for 16-bit staging");
     }
     // device copies of the per-launch pair lists live in the context scratch buffer
-    int rc = dr_ensure_scratch(ctx, sizeof(int32_t) * (size_t)(3 * n_pairs + 3) + 256);
+    int rc = dr_ensure_scratch(ctx, sizeof(int32_t) * (size_t)(4 * n_pairs + 4) + 256);
     if (rc) return rc;
     static thread_local int32_t* h = nullptr;
     static thread_local size_t h_cap = 0;
-    if (h_cap < (size_t)(3 * n_pairs + 3)) {
+    if (h_cap < (size_t)(4 * n_pairs + 4)) {
         free(h);
-        h_cap = (size_t)(3 * n_pairs + 3);
+        h_cap = (size_t)(4 * n_pairs + 4);
         h = (int32_t*)malloc(sizeof(int32_t) * h_cap);
         if (!h) { h_cap = 0; return dr_fail(ctx, DR_ERR_INVALID, "out of host memory"); }
     }
@@ -149,16 +155,19 @@ int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n
             h[q] = slot_of[px[q0 + q]];
             h[np + q] = slot_of[py[q0 + q]];
             h[2 * np + q] = (int32_t)(off[q0 + q] - off[q0]);
+            h[3 * np + 1 + q] = skip_off ? (int32_t)skip_off[q0 + q] : 0;
         }
         h[3 * np] = (int32_t)(off[q1] - off[q0]);
         int32_t* d = (int32_t*)ctx->scratch;
         // the scratch copy must be consumed before the next range overwrites it
         DR_CUDA(ctx, cudaStreamSynchronize(st));
-        DR_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(int32_t) * (size_t)(3 * np + 1), cudaMemcpyHostToDevice, st));
+        DR_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(int32_t) * (size_t)(4 * np + 1), cudaMemcpyHostToDevice, st));
         for (int i = 0; i < n_cols; ++i) { p.cols[i] = cols[i]; p.dom[i] = dom[i]; }
         p.px = d;
         p.py = d + np;
         p.off = d + 2 * np;
+        p.skip = skip;
+        p.skip_off = d + 3 * np + 1;
         p.n_pairs = np;
         p.n_rows = n_rows;
         p.block_rows = block_rows;
@@ -196,6 +205,22 @@ int dr_cooc(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_c
     const int64_t n_blocks = (n_rows + block_rows - 1) / block_rows;
     return run_pairs<true>(ctx, cols, dom, n_cols, px, py, n_pairs, tab_off, n_rows, block_rows, n_blocks, out,
                            (cudaStream_t)stream);
+}
+
+
+int dr_cooc_skip(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n_cols, const int32_t* px,
+                 const int32_t* py, int n_pairs, const int64_t* tab_off, int64_t n_rows, const int32_t* skip,
+                 const int64_t* skip_off, int64_t* out, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    DR_REQUIRE(ctx, (skip == nullptr) == (skip_off == nullptr), "skip and skip_off go together");
+    if (skip_off)
+        for (int q = 0; q < n_pairs; ++q)
+            DR_REQUIRE(ctx, skip_off[q + 1] - skip_off[q] >= dom[px[q]] + 1 && skip_off[q] < INT32_MAX,
+                       "skip table offsets too small");
+    const int64_t block_rows = 1 << 16;
+    const int64_t n_blocks = (n_rows + block_rows - 1) / block_rows;
+    return run_pairs<true>(ctx, cols, dom, n_cols, px, py, n_pairs, tab_off, n_rows, block_rows, n_blocks, out,
+                           (cudaStream_t)stream, skip, skip_off);
 }
 
 }  // extern "C"

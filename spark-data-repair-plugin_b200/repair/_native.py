@@ -102,6 +102,14 @@ _SIGNATURES = {
     "dr_lookup_sorted": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_forest_predict": (c_int, [c_void_p, POINTER(dr_forest), c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
                                   c_int, c_void_p, c_void_p]),
+    "dr_cooc_skip": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, POINTER(c_int32), POINTER(c_int32), c_int,
+                             POINTER(c_int64), c_int64, c_void_p, POINTER(c_int64), c_void_p, c_void_p]),
+    "dr_key_presence": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "dr_key_flag": (c_int, [c_void_p, _PP, POINTER(c_int64), c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dr_dc_exists": (c_int, [c_void_p, _PP, _PP, POINTER(c_int32), c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
+    "dr_combine_counts": (c_int, [c_void_p, c_void_p, c_int, c_int64, POINTER(c_int64), POINTER(c_int32), c_int,
+                                  c_void_p, c_void_p]),
     "dr_forest_predict_ranked": (c_int, [c_void_p, POINTER(dr_forest_ranked), c_void_p, c_int, c_void_p, c_int64,
                                          c_int, c_void_p, c_void_p]),
     "dr_gbdt_workspace_bytes": (c_int64, [c_int32, c_int32]),
@@ -317,6 +325,34 @@ class Context:
         cp, _k = _ptr_array([c.data_ptr() for c in cols])
         self._check(self.lib.dr_cooc(self._h, cp, _i32_array(dom), len(cols), _i32_array(px), _i32_array(py), len(px),
                                      _i64_array(tab_off), n_rows, _dp(out), self._stream()))
+
+    def cooc_skip(self, cols, dom, px, py, tab_off, n_rows, skip, skip_off, out):
+        """dr_cooc with one uncounted entry per x value (skip: device int32 or None)."""
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_cooc_skip(self._h, cp, _i32_array(dom), len(cols), _i32_array(px), _i32_array(py),
+                                          len(px), _i64_array(tab_off), n_rows, _dp(skip),
+                                          _i64_array(skip_off) if skip is not None else None, _dp(out),
+                                          self._stream()))
+
+    def key_presence(self, cols, strides, n_rows, space, bits):
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_key_presence(self._h, cp, _i64_array(strides), len(cols), n_rows, space, _dp(bits),
+                                             self._stream()))
+
+    def key_flag(self, cols, strides, n_rows, space, viol_bits, row_bitmap):
+        cp, _k = _ptr_array([c.data_ptr() for c in cols])
+        self._check(self.lib.dr_key_flag(self._h, cp, _i64_array(strides), len(cols), n_rows, space, _dp(viol_bits),
+                                         _dp(row_bitmap), self._stream()))
+
+    def dc_exists(self, left, right, signs, n, group_begin, group_end, out):
+        lp, _k1 = _ptr_array([c.data_ptr() for c in left])
+        rp, _k2 = _ptr_array([c.data_ptr() for c in right])
+        self._check(self.lib.dr_dc_exists(self._h, lp, rp, _i32_array(signs), len(signs), n, _dp(group_begin),
+                                          _dp(group_end), _dp(out), self._stream()))
+
+    def combine_counts(self, gathered, world, n, seg_off, seg_op, out):
+        self._check(self.lib.dr_combine_counts(self._h, _dp(gathered), world, n, _i64_array(seg_off),
+                                               _i32_array(seg_op), len(seg_op), _dp(out), self._stream()))
 
     def domain_score(self, rows, n_cells, target, dom_t, corr, dom_c, cooc, hist_t, tau, n_total, beta, out_top1,
                      out_prob, out_weak):

@@ -94,6 +94,7 @@ class RepairModel():
         self.device_index: int = 0
         self.model_provider = None   # callable(ctx) -> model spec; default: _fit (GPU GBDT / scikit-learn)
         self.trainer = "gpu"         # "gpu": dr_gbdt_train when eligible; "sklearn": always train.build_model
+        self.distributed = None      # torch.distributed process group (or True = default group): row-sharded run
         self.last_run: Dict[str, Any] = {}
 
     # ---- setters (same names / checks / messages as the reference) -------------------------------
@@ -140,6 +141,17 @@ class RepairModel():
         return self
 
     @argtype_check
+    def setDistributed(self, group: Any = True, device_index: Optional[int] = None) -> "RepairModel":
+        """Row-sharded run over the ranks of a ``torch.distributed`` process group (one process per GPU,
+        NCCL): every rank passes ITS rows to ``setInput`` and gets the repairs of its rows back.  The
+        shards exchange dictionaries once at ingest and count tensors (one collective per pass phase)
+        during detection; models are trained on the same global sample on every rank, so the union of
+        the per-rank results equals the one-GPU result (not part of the reference API)."""
+        self.distributed = group
+        if device_index is not None:
+            self.device_index = int(device_index)
+        return self
+
     def setRowId(self, row_id: str) -> "RepairModel":
         if not row_id:
             raise ValueError("`row_id` should have at least character")
@@ -291,8 +303,12 @@ class RepairModel():
         for key in _MODEL_OPT:
             self._opt(key)
 
-        from .engine import Engine
-        engine = Engine(table, self.device_index)
+        from .engine import Dist, Engine
+        dist = None
+        if self.distributed is not None and self.distributed is not False:
+            dist = Dist(None if self.distributed is True else self.distributed)
+            table = table.unify(dist)
+        engine = Engine(table, self.device_index, dist=dist)
         try:
             detectors = self.error_detectors or default_detectors(self.targets, table.names)
             _logger.info("[Error Detection Phase] Used error detectors: {}".format(to_list_str(detectors)))
@@ -301,7 +317,7 @@ class RepairModel():
             self.last_run = {"detect": res, "elapsed_detect": time.time() - t0}
             if detect_errors_only:
                 return self._cells_frame(engine, table, res)
-            if sum(res.n_cells.values()) == 0:
+            if sum((res.n_cells_global or res.n_cells).values()) == 0:
                 _logger.info("Any error cell not found, so the input data is already clean")
                 return self._input_frame(table) if repair_data else self._empty_frame(table, repaired=True)
             if len(res.target_columns) == 0:
@@ -413,12 +429,15 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps=None):
     input_columns = [c for c in table.names if c != y]
     if is_discrete:
         counts = np.asarray(engine.raw_value_counts(y), dtype=np.int64).copy()
-        if y in res.bitmaps and res.n_cells.get(y, 0):
-            rows = engine.bitmap_rows(res.bitmaps[y])
-            cur = engine.torch.empty(int(rows.numel()), dtype=engine.torch.int32, device=engine.device)
-            engine.ctx.gather(engine.dt.col(y), rows, int(rows.numel()), cur)
-            masked = np.bincount(cur.cpu().numpy().astype(np.int64) + 1, minlength=len(counts))
-            counts -= masked
+        if y in res.bitmaps and (res.n_cells_global or res.n_cells).get(y, 0):
+            masked = engine.torch.zeros(len(counts), dtype=engine.torch.int64, device=engine.device)
+            if res.n_cells.get(y, 0):
+                rows = engine.bitmap_rows(res.bitmaps[y])
+                cur = engine.torch.empty(int(rows.numel()), dtype=engine.torch.int32, device=engine.device)
+                engine.ctx.gather(engine.dt.col(y), rows, int(rows.numel()), cur)
+                masked += engine.torch.bincount((cur + 1).to(engine.torch.int64), minlength=len(counts))
+            engine.exchange([(masked, "sum")])
+            counts -= masked.cpu().numpy()
         present = np.nonzero(counts[1:] > 0)[0]
         num_class = len(present)
         if num_class <= 1:
@@ -431,10 +450,10 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps=None):
             _logger.info("Building model... type=rule(FD: X->y) y={} X={}".format(y, fx[0]))
             return R.build_fd_model(engine, table, res, fx[0], y)
     features = select_features(res.pairwise_stats, y, input_columns, rm._opt("model.max_training_column_num"))
-    rows, n_valid = engine.valid_training_rows(res, y, rm._opt("model.max_training_row_num"))
+    rows_local, rows, n_valid = engine.valid_training_rows(res, y, rm._opt("model.max_training_row_num"))
     if n_valid == 0:
         return ("const", None)
-    codes, vals = engine.sample_rows_masked(res, res.target_columns, rows)
+    codes, vals = engine.sample_rows_masked(res, res.target_columns, rows_local)
     cont_idx = engine.dt.cont_index
     encoders = []
     dict_sizes = {c.name: c.dict_size for c in table.columns}
@@ -717,7 +736,7 @@ def _repair_cells(rm, engine, table, res, continuous, repair_data, models, encod
     tile_col = {c.name: i for i, c in enumerate(table.columns)}
     cont_idx = engine.dt.cont_index
     cells = engine.cells_of(res, targets)           # (attr, rows, current codes), table order
-    if not cells:
+    if not cells and engine.dist is None:           # (a shard without cells still takes part in the training collectives)
         if by_rules and not repair_data:
             return _rule_repairs_frame(table, by_rules)
         if by_rules:
@@ -775,7 +794,7 @@ def _repair_cells(rm, engine, table, res, continuous, repair_data, models, encod
         return repaired_cells
     if repair_data:
         return _apply_repairs(rm, table, repaired_cells + _rule_cells_for_apply(table, by_rules))
-    frame = DataFrame({table.row_id: np.concatenate(ids), "attribute": attrs,
+    frame = DataFrame({table.row_id: np.concatenate(ids) if ids else table.row_ids[:0], "attribute": attrs,
                        "current_value": pd.array(curs, dtype=object), "repaired": pd.array(reps, dtype=object)})
     # repaired IS NULL OR NOT(current_value <=> repaired)   (model.py:1401)
     cur_a, rep_a = frame["current_value"].to_numpy(dtype=object), frame["repaired"].to_numpy(dtype=object)

@@ -260,6 +260,43 @@ class EncodedTable:
         ids = self.row_ids[np.asarray(positions, dtype=np.int64)]
         return ids
 
+    def unify(self, dist):
+        """Row-sharded input (every rank collected its own rows): makes the dictionaries GLOBAL -- the
+        sorted union of the shards' dictionaries, so that a code means the same value on every GPU and
+        the count tensors of the shards add up -- and records the shard's place in the global table.
+        Only dictionaries (one entry per distinct value) and row counts cross the wire."""
+        import torch.distributed as td
+        local = [(c.name, c.kind, list(c.dictionary) if c.kind == "str" else np.asarray(c.dictionary, dtype=np.float64))
+                 for c in self.columns]
+        gathered = [None] * dist.world
+        td.all_gather_object(gathered, (self.n_rows, local), group=dist.group)
+        names = [nm for nm, _, _ in local]
+        for n_r, cols in gathered:
+            if [nm for nm, _, _ in cols] != names:
+                raise AnalysisException("the shards of table '{}' do not have the same columns".format(self.name))
+        counts = [n_r for n_r, _ in gathered]
+        cols = []
+        for i, c in enumerate(self.columns):
+            kinds = {g[1][i][1] for g in gathered}
+            kind = c.kind if len(kinds) == 1 else ("float" if kinds <= {"int", "float"} else "str")
+            if kind == "str":
+                merged = np.array(sorted(set(str(v) for g in gathered for v in g[1][i][2])), dtype=object)
+                mine = np.array([str(v) for v in c.dictionary], dtype=object)
+                lut = np.searchsorted(merged.astype(str), mine.astype(str)).astype(np.int32) if len(mine) else \
+                    np.zeros(0, dtype=np.int32)
+                values = None
+            else:
+                merged = np.unique(np.concatenate([np.asarray(g[1][i][2], dtype=np.float64) for g in gathered]))
+                lut = np.searchsorted(merged, np.asarray(c.dictionary, dtype=np.float64)).astype(np.int32)
+                values = c.values
+            codes = np.where(c.codes >= 0, np.r_[lut, np.int32(-1)][c.codes], -1).astype(np.int32) if len(lut) else \
+                np.full(len(c.codes), -1, dtype=np.int32)
+            cols.append(Column(c.name, kind, merged, codes, values))
+        t = EncodedTable(self.row_id, self.row_ids, self.row_id_kind, cols, self.name)
+        t.row_offset = int(sum(counts[:dist.rank]))
+        t.n_rows_global = int(sum(counts))
+        return t
+
     def shard(self, rank, world):
         """Contiguous row shard [lo, hi) for rank `rank` of `world` (global dictionaries kept)."""
         n = self.n_rows

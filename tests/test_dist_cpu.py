@@ -58,7 +58,15 @@ def _worker(rank, world, port, out_dir):
     dist = Dist()
     hist, tabs = _local_counts(cols, doms, pairs)
     flat = torch.from_numpy(np.concatenate(hist + tabs).astype(np.int64))
-    dist.sum_(flat)                                      # THE exchange step
+    # FD key tables (MIN / MAX) and presence bits (OR) travel in the SAME exchange as the counts
+    lo, hi = _fd_tables(cols[5].astype(np.int64) + 1, cols[4], doms[5] + 1)
+    tlo, thi = torch.from_numpy(lo), torch.from_numpy(hi)
+    idx = (cols[0].astype(np.int64) + 1) * (doms[1] + 1) + cols[1] + 1
+    local_bits = np.zeros(((doms[0] + 1) * (doms[1] + 1) + 31) // 32, dtype=np.uint32)
+    np.bitwise_or.at(local_bits, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
+    tbits = torch.from_numpy(local_bits.view(np.int32).copy())
+    dist.exchange(None, [(flat, "sum"), (tlo, "min"), (thi, "max"), (tbits, "or")])   # THE exchange step
+    assert dist.n_exchanges == 1
     g = flat.numpy()
     ghist, off = {}, 0
     for nm, d in zip(names, doms):
@@ -77,15 +85,15 @@ def _worker(rank, world, port, out_dir):
                                  {p: t.reshape(doms[x] + 1, doms[y] + 1) for p, t, (x, y) in
                                   zip(named_pairs, ftabs, pairs)}, named_pairs, ndv)
     assert got == want                                   # integer sums are order independent -> bit identical
-    # FD key tables: MIN / MAX all-reduce
-    lo, hi = _fd_tables(cols[5].astype(np.int64) + 1, cols[4], doms[5] + 1)
-    tlo, thi = torch.from_numpy(lo), torch.from_numpy(hi)
-    dist.min_(tlo)
-    dist.max_(thi)
+    # FD key tables: MIN / MAX segments of the exchange
     flo, fhi = _fd_tables(full[5].astype(np.int64) + 1, full[4], doms[5] + 1)
     assert np.array_equal(tlo.numpy(), flo) and np.array_equal(thi.numpy(), fhi)
     viol = (flo != fhi)
     assert viol[-3:].all() and not viol[1:-3].any()      # exactly the three dirty determinant values
+    fidx = (full[0].astype(np.int64) + 1) * (doms[1] + 1) + full[1] + 1
+    fbits = np.zeros_like(local_bits)
+    np.bitwise_or.at(fbits, fidx >> 5, np.uint32(1) << (fidx & 31).astype(np.uint32))
+    assert np.array_equal(tbits.numpy().view(np.uint32), fbits)       # OR segment
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     td.destroy_process_group()
 

@@ -359,6 +359,49 @@ def test_inequality_denial_constraints_parity():
         assert got == want and len(got) > 100, cons
 
 
+GENERAL_DCS = [
+    # several IQs / several inequalities / cross-attribute predicates: every shape the reference's parser
+    # accepts (DenialConstraintsSuite.scala:27-52) is evaluated, none raises
+    "t1&t2&EQ(t1.a,t2.a)&IQ(t1.b,t2.b)&IQ(t1.s,t2.s)",
+    "t1&t2&LT(t1.b,t2.b)&GT(t1.w,t2.w)",
+    "t1&t2&LT(t1.b,t2.b)&GT(t1.w,t2.w)&EQ(t1.b,t2.b)",          # DenialConstraintsSuite.scala:41-44: unsatisfiable
+    "t1&t2&EQ(t1.a,t2.a)&LT(t1.b,t2.b)&GT(t1.w,t2.w)",
+    "t1&t2&EQ(t1.a,t2.z)&IQ(t1.s,t2.s)",                        # cross-attribute equality (strings)
+    "t1&t2&LT(t1.b,t2.w)&EQ(t1.g,t2.g)",                        # cross-attribute inequality (numbers)
+    "t1&t2&IQ(t1.a,t2.a)&IQ(t1.g,t2.g)",
+    "t1&t2&GT(t1.s,t2.s)&LT(t1.a,t2.a)&EQ(t1.g,t2.g)&IQ(t1.z,t2.z)",
+]
+
+
+@pytest.mark.parametrize("cons", GENERAL_DCS)
+def test_general_two_tuple_denial_constraints_parity(cons):
+    """ErrorDetectorApi.scala:211-229 evaluates ANY parsed predicate list as an EXISTS self semi-join; the
+    GPU path decides distinct projections (dr_key_presence / dr_dc_exists / dr_key_flag) and must agree
+    with the oracle's brute force over all row pairs."""
+    rng = np.random.default_rng(21)
+    n = 500
+    df = pd.DataFrame({"tid": np.arange(n), "a": rng.integers(0, 9, n).astype(str), "g": rng.integers(0, 3, n).astype(str),
+                       "b": rng.integers(0, 12, n), "w": rng.integers(3, 15, n),
+                       "s": rng.choice(list("pqrstu"), n), "z": rng.integers(0, 9, n).astype(str)})
+    df["a"] = df["a"].where(rng.random(n) > 0.05, None)
+    df["s"] = df["s"].where(rng.random(n) > 0.05, None)
+    df["b"] = df["b"].astype(float).where(rng.random(n) > 0.05, np.nan)
+    df["w"] = df["w"].astype(float).where(rng.random(n) > 0.03, np.nan)
+    specs = [{"type": "constraint", "constraints": cons}]
+    got, want, _ = PU.run_both_frame(df, "tid", specs, mode="detect")
+    assert got == want, cons
+    if "EQ(t1.b,t2.b)" not in cons:
+        assert len(got) > 20, cons
+
+
+def test_general_constraint_beyond_the_projection_bitmap(monkeypatch):
+    """Projection spaces larger than the presence bitmap fall back to sorted distinct keys."""
+    from repair import engine as E
+    monkeypatch.setattr(E, "MAX_PROJECTION_BITS", 64)
+    test_general_two_tuple_denial_constraints_parity(GENERAL_DCS[0])
+    test_general_two_tuple_denial_constraints_parity(GENERAL_DCS[5])
+
+
 def test_fd_constraint_with_a_huge_key_space_uses_the_hash_table(monkeypatch):
     """Key spaces beyond the direct min / max tables go through the hash table (the limit is lowered here
     so that a three-attribute key of a small table crosses it)."""
