@@ -101,7 +101,8 @@ def detector_specs(n_cols):
     return specs
 
 
-OPTS = {"error.pairwise_freq_ratio_threshold": "1.0"}
+# model.hp.max_evals=1: fixed parameters, no search -- SURVEY.md 8(d) "trained once per target ... with fixed params"
+OPTS = {"error.pairwise_freq_ratio_threshold": "1.0", "model.hp.max_evals": "1"}
 
 
 # ---------------------------------------------------------------------------------------------

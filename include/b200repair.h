@@ -398,6 +398,13 @@ int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* forest, int32_
 typedef struct dr_gbdt_params {
     int32_t n_rows, n_features, n_classes, n_iter, max_depth, num_leaves, min_data_in_leaf;
     double learning_rate, min_sum_hessian, qscale;
+    /* the remaining parameters of the reference's search space (train.py:148-156); defaults 0 / 1 / 1 / 0:
+     * reg_lambda is added to every hessian sum (gain and leaf value); feature f takes part in tree
+     * (iteration, sequence) iff hash(seed, iteration, sequence, f) < colsample_bytree (the feature with
+     * the smallest hash always does); every subsample_freq iterations row i is (re)drawn into the bag iff
+     * hash(seed, bag, i) < subsample -- oracle/gbdt.py states the hashes */
+    double reg_lambda, colsample_bytree, subsample;
+    int32_t subsample_freq, seed;
 } dr_gbdt_params;
 typedef struct dr_gbdt_node {
     int16_t feature; /* -1 = leaf */

@@ -18,7 +18,16 @@ num_leaves 31, min_child_samples 20, min_child_weight 1e-3, reg_lambda 0):
   (gain = GL^2/HL + GR^2/HR - G^2/H, both directions tried for the missing bin, constraints
   min_data_in_leaf / min_sum_hessian), proposals are applied in order of decreasing gain while the
   tree has fewer than ``num_leaves`` leaves;
-* leaf value = -G/H * learning_rate.
+* leaf value = -G/(H + lambda) * learning_rate.
+
+The seven parameters the reference tunes with hyperopt (``train.py:148-156``) are all honoured:
+``num_leaves``, ``min_child_samples`` (min_data_in_leaf), ``min_child_weight`` (min_sum_hessian),
+``reg_lambda`` (added to every hessian sum of the gain and of the leaf value), ``colsample_bytree``
+(feature f takes part in tree (iteration, sequence) iff a counter-based hash of (seed, iteration,
+sequence, f) falls below the fraction; the feature with the smallest hash always takes part) and
+``subsample`` / ``subsample_freq`` (every ``subsample_freq`` iterations a new bag: row i is in the bag
+iff a hash of (seed, bag number, i) falls below the fraction; rows outside the bag contribute neither
+gradients nor counts to the trees of those iterations, their scores are still updated).
 """
 import numpy as np
 
@@ -26,6 +35,35 @@ LN2_HI = 6.93147180369123816490e-01
 LN2_LO = 1.90821492927058770002e-10
 INV_LN2 = 1.44269504088896338700e+00
 _COEF = [1.0 / float(np.prod(np.arange(1, k + 1, dtype=np.float64))) if k else 1.0 for k in range(14)]
+
+
+_M64 = (1 << 64) - 1
+
+
+def mix64(z):
+    """splitmix64 finaliser on Python ints (the CUDA trainer evaluates the same function)."""
+    z &= _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def feature_used(seed, it, s, n_features, colsample):
+    """bool[F]: the features tree (it, s) may split on."""
+    if colsample >= 1.0:
+        return np.ones(n_features, dtype=bool)
+    thr = int(colsample * float(1 << 24))
+    h = [mix64(seed * 0x9E3779B97F4A7C15 + (it << 40) + (s << 20) + f + 1) >> 40 for f in range(n_features)]
+    used = np.array([x < thr for x in h], dtype=bool)
+    used[int(np.argmin(h))] = True
+    return used
+
+
+def rows_in_bag(seed, bag, n_rows, subsample):
+    """bool[n]: the rows of bag number `bag`."""
+    thr = int(subsample * float(1 << 24))
+    return np.array([(mix64((seed + 1) * 0x9E3779B97F4A7C15 + (bag << 32) + i) >> 40) < thr for i in range(n_rows)],
+                    dtype=bool)
 
 
 def quant_bits(n_rows):
@@ -60,7 +98,8 @@ def sigmoid_det(s):
 
 
 def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_rate=0.01, max_depth=7,
-          num_leaves=31, min_data_in_leaf=20, min_sum_hessian=1e-3):
+          num_leaves=31, min_data_in_leaf=20, min_sum_hessian=1e-3, reg_lambda=0.0, colsample_bytree=1.0,
+          subsample=1.0, subsample_freq=0, seed=42):
     """bins: uint8 [n, F], value bins 0..n_bins[f]-2, missing bin = n_bins[f]-1.
     y: class index (n_classes >= 2) or float target (n_classes == 1).
     -> dict(init float64[S], trees = list over iterations of list over sequences of node lists
@@ -89,7 +128,12 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
     offs[1:] = np.cumsum(n_bins)
     flat = bins.astype(np.int64) + offs[:-1][None, :]      # [n, F] global bin ids
     trees = []
-    for _ in range(n_iter):
+    lam_q = float(reg_lambda) * qscale
+    bagging = subsample < 1.0 and subsample_freq > 0
+    in_bag = np.ones(n, dtype=bool)
+    for it in range(n_iter):
+        if bagging and it % subsample_freq == 0:
+            in_bag = rows_in_bag(seed, it // subsample_freq, n, subsample)
         if n_classes == 1:
             g, h = scores - yv[:, None], np.ones((n, 1))
         elif n_classes == 2:
@@ -104,12 +148,13 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
         for s in range(S):
             nodes = [[-1, 0, 0, 0, 0, 0.0]]
             node_of = np.zeros(n, dtype=np.int64)
-            sums = {0: (int(gq[:, s].sum()), int(hq[:, s].sum()), n)}
+            used = feature_used(seed, it, s, F, colsample_bytree)
+            sums = {0: (int(gq[in_bag, s].sum()), int(hq[in_bag, s].sum()), int(in_bag.sum()))}
             active, n_leaves = [0], 1
             for depth in range(max_depth):
                 props = []
                 for leaf in active:
-                    rows = np.nonzero(node_of == leaf)[0]
+                    rows = np.nonzero((node_of == leaf) & in_bag)[0]
                     G, H, cnt = sums[leaf]
                     if cnt < 2 * min_data_in_leaf or H <= 0:
                         continue
@@ -121,10 +166,10 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
                     np.add.at(hh, idx, np.repeat(hq[rows, s], F))
                     np.add.at(hc, idx, 1)
                     best = None
-                    parent = (float(G) * float(G)) / float(H)
+                    parent = (float(G) * float(G)) / (float(H) + lam_q)
                     for f in range(F):
                         nb = int(n_bins[f])
-                        if nb < 3:
+                        if nb < 3 or not used[f]:
                             continue
                         o = int(offs[f])
                         mg, mh, mc = int(hg[o + nb - 1]), int(hh[o + nb - 1]), int(hc[o + nb - 1])
@@ -138,8 +183,8 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
                                     continue
                                 if HL < min_sum_hessian * qscale or HR < min_sum_hessian * qscale:
                                     continue
-                                gain = ((float(GL) * float(GL)) / float(HL) +
-                                        (float(GR) * float(GR)) / float(HR)) - parent
+                                gain = ((float(GL) * float(GL)) / (float(HL) + lam_q) +
+                                        (float(GR) * float(GR)) / (float(HR) + lam_q)) - parent
                                 if gain > 0.0 and (best is None or gain > best[0]):
                                     best = (gain, f, t, ml, GL, HL, CL)
                     if best is not None:
@@ -166,7 +211,7 @@ def train(bins, n_bins, y, n_classes, sample_weight=None, n_iter=300, learning_r
             for i, nd in enumerate(nodes):
                 if nd[0] < 0:
                     G, H, _ = sums[i]
-                    nd[5] = (-(float(G) / float(H)) * learning_rate) if H > 0 else 0.0
+                    nd[5] = (-(float(G) / (float(H) + lam_q)) * learning_rate) if H > 0 else 0.0
             vals = np.array([nd[5] for nd in nodes])
             scores[:, s] = scores[:, s] + vals[node_of]
             it_trees.append([tuple(nd) for nd in nodes])

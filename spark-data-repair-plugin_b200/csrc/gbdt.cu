@@ -48,12 +48,16 @@ struct GbdtState {
     int32_t n_bins[128];
     int32_t bin_off[129];
     int n, F, S, n_classes, max_depth, num_leaves, min_data;
-    double lr, qscale, min_hess_q, factor;
+    double lr, qscale, min_hess_q, factor, lam_q;
+    int col_thr;           // colsample_bytree as a 24-bit threshold, -1 = every feature
+    int bag_thr, bag_freq; // subsample as a 24-bit threshold, bagging period (0 = no bagging)
+    unsigned long long seed;
     // workspace
     double* scores;        // [n][S]
     int32_t* gq;           // [S][n]
     int32_t* hq;           // [S][n]
     uint8_t* node_of;      // [S][n]
+    uint8_t* inbag;        // [n] 1 = the row contributes to the trees of this iteration
     long long* sumG;       // [S][kMaxNodes]
     long long* sumH;
     int32_t* sumC;
@@ -68,6 +72,18 @@ struct GbdtState {
     int32_t* out_count;    // [n_iter][S]
 };
 
+// splitmix64 finaliser (oracle/gbdt.py mix64): feature / row sub-sampling is a pure function of
+// (seed, iteration, sequence, feature) resp. (seed, bag, row), identical on both sides
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned feat_hash(const unsigned long long seed, int it, int s, int f) {
+    return (unsigned)(mix64(seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)it << 40) +
+                            ((unsigned long long)s << 20) + (unsigned long long)f + 1ull) >> 40);
+}
+
 __device__ __forceinline__ double exp_det(double x) {
     x = fmin(fmax(x, -700.0), 700.0);
     const double k = rint(__dmul_rn(x, 1.44269504088896338700e+00));
@@ -81,10 +97,16 @@ __device__ __forceinline__ double exp_det(double x) {
     return ldexp(p, (int)k);
 }
 
-__global__ void __launch_bounds__(kThreads) k_grad(GbdtState st) {
+__global__ void __launch_bounds__(kThreads) k_grad(GbdtState st, int iter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.n) return;
     const int S = st.S;
+    if (st.bag_freq > 0 && iter % st.bag_freq == 0) {  // a new bag every bag_freq iterations
+        const unsigned long long bag = (unsigned long long)(iter / st.bag_freq);
+        const unsigned h = (unsigned)(mix64((st.seed + 1ull) * 0x9E3779B97F4A7C15ull + (bag << 32) +
+                                            (unsigned long long)i) >> 40);
+        st.inbag[i] = h < (unsigned)st.bag_thr ? 1 : 0;
+    }
     const double* sc = st.scores + (size_t)i * S;
     if (st.n_classes == 1) {
         const double g = __dsub_rn(sc[0], st.y_value[i]);
@@ -119,24 +141,30 @@ __global__ void __launch_bounds__(kThreads) k_grad(GbdtState st) {
 // one CTA per sequence: root sums + per-round tree state
 __global__ void __launch_bounds__(kThreads) k_root(GbdtState st) {
     __shared__ long long sg[kThreads / 32], sh[kThreads / 32];
+    __shared__ int sc[kThreads / 32];
     const int s = blockIdx.x;
     long long g = 0, h = 0;
+    int c = 0;
     for (int i = threadIdx.x; i < st.n; i += kThreads) {
+        if (!st.inbag[i]) continue;
         g += st.gq[(size_t)s * st.n + i];
         h += st.hq[(size_t)s * st.n + i];
+        ++c;
     }
     for (int o = 16; o; o >>= 1) {
         g += __shfl_down_sync(0xffffffffu, g, o);
         h += __shfl_down_sync(0xffffffffu, h, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
     }
-    if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = g; sh[threadIdx.x >> 5] = h; }
+    if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = g; sh[threadIdx.x >> 5] = h; sc[threadIdx.x >> 5] = c; }
     __syncthreads();
     if (threadIdx.x == 0) {
         long long G = 0, H = 0;
-        for (int j = 0; j < kThreads / 32; ++j) { G += sg[j]; H += sh[j]; }
+        int C = 0;
+        for (int j = 0; j < kThreads / 32; ++j) { G += sg[j]; H += sh[j]; C += sc[j]; }
         st.sumG[s * kMaxNodes] = G;
         st.sumH[s * kMaxNodes] = H;
-        st.sumC[s * kMaxNodes] = st.n;
+        st.sumC[s * kMaxNodes] = C;
         st.active[s * kMaxLeaves] = 0;
         st.n_active[s] = 1;
         st.n_nodes[s] = 1;
@@ -149,8 +177,10 @@ __global__ void __launch_bounds__(kThreads) k_root(GbdtState st) {
 }
 
 // CTA (s, j): histogram of active leaf j of sequence s in shared memory, then its best split.
-__global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
+__global__ void __launch_bounds__(kThreads) k_level(GbdtState st, int iter) {
     extern __shared__ unsigned char smem_raw[];
+    __shared__ unsigned s_fhash[128];
+    __shared__ int s_fmin;
     const int s = blockIdx.x, j = blockIdx.y;
     Proposal* out = st.props + (s * kMaxLeaves + j);
     if (threadIdx.x == 0) { out->gain = 0.0; out->feature = -1; out->leaf = -1; }
@@ -170,8 +200,18 @@ __global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
     const uint8_t* nof = st.node_of + (size_t)s * st.n;
     const int32_t* gq = st.gq + (size_t)s * st.n;
     const int32_t* hq = st.hq + (size_t)s * st.n;
+    if (st.col_thr >= 0) {  // colsample_bytree: the features tree (iter, s) may split on
+        if (threadIdx.x < st.F) s_fhash[threadIdx.x] = feat_hash(st.seed, iter, s, threadIdx.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int m = 0;
+            for (int f = 1; f < st.F; ++f)
+                if (s_fhash[f] < s_fhash[m]) m = f;
+            s_fmin = m;
+        }
+    }
     for (int i = threadIdx.x; i < st.n; i += kThreads) {
-        if (nof[i] != leaf) continue;
+        if (nof[i] != leaf || !st.inbag[i]) continue;
         const int g = gq[i], h = hq[i];
         const uint8_t* row = st.bins + (size_t)i * st.F;
         for (int f = 0; f < st.F; ++f) {
@@ -186,10 +226,11 @@ __global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
     double best_gain = 0.0;
     int best_key = 0x7fffffff, best_f = -1, best_t = 0, best_ml = 0, best_CL = 0;
     long long best_GL = 0, best_HL = 0;
-    const double parent = __ddiv_rn(__dmul_rn((double)G, (double)G), (double)H);
+    const double parent = __ddiv_rn(__dmul_rn((double)G, (double)G), __dadd_rn((double)H, st.lam_q));
     for (int f = threadIdx.x; f < st.F; f += kThreads) {
         const int nb = st.n_bins[f];
         if (nb < 3) continue;
+        if (st.col_thr >= 0 && !(s_fhash[f] < (unsigned)st.col_thr || f == s_fmin)) continue;
         const int o = st.bin_off[f];
         const long long mg = hg[o + nb - 1], mh = hh[o + nb - 1];
         const int mc = hc[o + nb - 1];
@@ -205,8 +246,8 @@ __global__ void __launch_bounds__(kThreads) k_level(GbdtState st) {
                 if (CL < st.min_data || CR < st.min_data) continue;
                 if ((double)HL < st.min_hess_q || (double)HR < st.min_hess_q) continue;
                 const double gain = __dsub_rn(
-                    __dadd_rn(__ddiv_rn(__dmul_rn((double)GL, (double)GL), (double)HL),
-                              __ddiv_rn(__dmul_rn((double)GR, (double)GR), (double)HR)), parent);
+                    __dadd_rn(__ddiv_rn(__dmul_rn((double)GL, (double)GL), __dadd_rn((double)HL, st.lam_q)),
+                              __ddiv_rn(__dmul_rn((double)GR, (double)GR), __dadd_rn((double)HR, st.lam_q))), parent);
                 if (gain > 0.0 && gain > best_gain) {
                     best_gain = gain; best_f = f; best_t = t; best_ml = ml;
                     best_key = (f << 16) | (t << 1) | ml;
@@ -303,7 +344,7 @@ __global__ void k_finish(GbdtState st, int iter) {
     for (int nidx = threadIdx.x; nidx < n_nodes; nidx += blockDim.x) {
         if (cur[nidx].feature < 0) {
             const long long G = st.sumG[s * kMaxNodes + nidx], H = st.sumH[s * kMaxNodes + nidx];
-            cur[nidx].value = H > 0 ? __dmul_rn(-__ddiv_rn((double)G, (double)H), st.lr) : 0.0;
+            cur[nidx].value = H > 0 ? __dmul_rn(-__ddiv_rn((double)G, __dadd_rn((double)H, st.lam_q)), st.lr) : 0.0;
         }
         st.out[((size_t)iter * st.S + s) * kMaxNodes + nidx] = cur[nidx];
     }
@@ -323,6 +364,7 @@ __global__ void k_init_scores(GbdtState st, const double* init) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.n) return;
     for (int s = 0; s < st.S; ++s) st.scores[(size_t)i * st.S + s] = init[s];
+    st.inbag[i] = 1;
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -336,6 +378,7 @@ int64_t dr_gbdt_workspace_bytes(int32_t n, int32_t n_seq) {
     b += align_up(sizeof(double) * (size_t)n * n_seq);          // scores
     b += 2 * align_up(sizeof(int32_t) * (size_t)n * n_seq);     // gq, hq
     b += align_up((size_t)n * n_seq);                           // node_of
+    b += align_up((size_t)n);                                   // inbag
     b += 2 * align_up(sizeof(long long) * (size_t)n_seq * kMaxNodes);
     b += align_up(sizeof(int32_t) * (size_t)n_seq * kMaxNodes);
     b += align_up(sizeof(int32_t) * (size_t)n_seq * kMaxLeaves);
@@ -371,6 +414,14 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* prm, const uint8_t* bins, c
     st.num_leaves = prm->num_leaves; st.min_data = prm->min_data_in_leaf;
     st.lr = prm->learning_rate; st.qscale = prm->qscale; st.min_hess_q = prm->min_sum_hessian * prm->qscale;
     st.factor = S > 1 ? (double)S / (double)(S - 1) : 1.0;
+    DR_REQUIRE(ctx, prm->reg_lambda >= 0.0, "reg_lambda must be >= 0");
+    DR_REQUIRE(ctx, prm->colsample_bytree > 0.0 && prm->subsample > 0.0, "sampling fractions must be positive");
+    st.lam_q = prm->reg_lambda * prm->qscale;
+    st.col_thr = prm->colsample_bytree >= 1.0 ? -1 : (int)(prm->colsample_bytree * 16777216.0);
+    const bool bagging = prm->subsample < 1.0 && prm->subsample_freq > 0;
+    st.bag_freq = bagging ? prm->subsample_freq : 0;
+    st.bag_thr = bagging ? (int)(prm->subsample * 16777216.0) : 0;
+    st.seed = (unsigned long long)(long long)prm->seed;
     int total = 0;
     for (int f = 0; f < F; ++f) {
         DR_REQUIRE(ctx, n_bins[f] >= 1 && n_bins[f] <= 256, "bins per feature must be in [1, 256]");
@@ -388,6 +439,7 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* prm, const uint8_t* bins, c
     st.gq = (int32_t*)take(sizeof(int32_t) * (size_t)n * S);
     st.hq = (int32_t*)take(sizeof(int32_t) * (size_t)n * S);
     st.node_of = (uint8_t*)take((size_t)n * S);
+    st.inbag = (uint8_t*)take((size_t)n);
     st.sumG = (long long*)take(sizeof(long long) * (size_t)S * kMaxNodes);
     st.sumH = (long long*)take(sizeof(long long) * (size_t)S * kMaxNodes);
     st.sumC = (int32_t*)take(sizeof(int32_t) * (size_t)S * kMaxNodes);
@@ -408,10 +460,10 @@ int dr_gbdt_train(dr_ctx* ctx, const dr_gbdt_params* prm, const uint8_t* bins, c
     k_init_scores<<<row_blocks, kThreads, 0, sm>>>(st, d_init);
     DR_LAUNCHED(ctx);
     for (int it = 0; it < prm->n_iter; ++it) {
-        k_grad<<<row_blocks, kThreads, 0, sm>>>(st);
+        k_grad<<<row_blocks, kThreads, 0, sm>>>(st, it);
         k_root<<<S, kThreads, 0, sm>>>(st);
         for (int depth = 0; depth < prm->max_depth; ++depth) {
-            k_level<<<dim3(S, kMaxLeaves), kThreads, smem, sm>>>(st);
+            k_level<<<dim3(S, kMaxLeaves), kThreads, smem, sm>>>(st, it);
             k_apply<<<(S + 63) / 64, 64, 0, sm>>>(st, depth);
             k_reassign<<<dim3(row_blocks, S), kThreads, 0, sm>>>(st);
         }

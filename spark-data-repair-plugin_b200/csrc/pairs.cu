@@ -7,8 +7,8 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kTile = 256;
+constexpr int kThreads = 512;
+constexpr int kTile = 512;
 
 struct PairParams {
     const int32_t* cols[DR_MAX_COLS];
@@ -20,6 +20,8 @@ struct PairParams {
     const int32_t* off;  // device int32[n_pairs + 1], word/entry offsets relative to the launch
     const int32_t* skip;      // counts only: device, entry (cx) of pair q at skip[skip_off[q] + cx], or nullptr
     const int32_t* skip_off;  // device int32[n_pairs], offsets into `skip`
+    int32_t skip_off0;        // skip offset of the launch's first pair
+    int32_t skip_len;         // skip entries of the launch's pairs
     int n_pairs;
     int64_t n_rows;
     int64_t block_rows;
@@ -31,14 +33,37 @@ __device__ __forceinline__ int64_t block_start(const PairParams& p, int64_t j) {
     return (j * (p.n_rows - p.block_rows)) / (p.n_blocks - 1);
 }
 
+// per-pair metadata staged in shared memory once per CTA (one 128-bit broadcast load per pair and row
+// instead of three dependent global loads)
+struct __align__(16) PairMeta {
+    int32_t x_off, y_off;  // element offsets of the pair's columns in the staged code tile
+    int32_t base_ny;       // first table word / entry of the pair | (dom_y + 1) << 16
+    int32_t skip;          // offset of the pair's entries in the staged skip LUT
+};
+
 template <bool kCount>
 __global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ PairParams p, int table_words,
-                                                    void* __restrict__ out_raw) {
+                                                    int skip_words, void* __restrict__ out_raw) {
     extern __shared__ uint32_t smem[];
     uint32_t* tab = smem;                                                   // table_words
-    uint16_t* codes = reinterpret_cast<uint16_t*>(smem + table_words);      // n_used * kTile
+    PairMeta* meta = reinterpret_cast<PairMeta*>(smem + ((table_words + 3) & ~3));   // n_pairs
+    uint16_t* skip = reinterpret_cast<uint16_t*>(meta + p.n_pairs);        // skip_words * 2 entries
+    uint16_t* codes = skip + 2 * skip_words;                               // n_used * kTile
     for (int i = threadIdx.x; i < table_words; i += kThreads) tab[i] = 0;
+    for (int q = threadIdx.x; q < p.n_pairs; q += kThreads) {
+        const int x = p.px[q], y = p.py[q];
+        PairMeta m;
+        m.x_off = x * kTile;
+        m.y_off = y * kTile;
+        m.base_ny = p.off[q] | ((p.dom[p.used[y]] + 1) << 16);
+        m.skip = kCount && p.skip != nullptr ? p.skip_off[q] - p.skip_off0 : 0;
+        meta[q] = m;
+    }
+    if (kCount && p.skip != nullptr)
+        for (int i = threadIdx.x; i < 2 * skip_words; i += kThreads)
+            skip[i] = i < p.skip_len ? (uint16_t)p.skip[p.skip_off0 + i] : (uint16_t)0xFFFF;
     __syncthreads();
+    const bool use_skip = kCount && p.skip != nullptr;
     const int64_t units_per_block = (p.block_rows + kTile - 1) / kTile;
     const int64_t n_units = units_per_block * p.n_blocks;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -71,15 +96,14 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const __grid_constant__ Pair
         // each thread only reads back its own column of `codes`: no barrier needed
         if (live) {
             for (int q = 0; q < p.n_pairs; ++q) {
-                const int x = __ldg(p.px + q), y = __ldg(p.py + q);
-                const int cx = codes[x * kTile + threadIdx.x], cy = codes[y * kTile + threadIdx.x];
-                const int idx = cx * (p.dom[p.used[y]] + 1) + cy;
-                const int base = __ldg(p.off + q);
+                const PairMeta m = meta[q];
+                const int cx = codes[m.x_off + threadIdx.x], cy = codes[m.y_off + threadIdx.x];
+                const int base = m.base_ny & 0xFFFF;
+                const int idx = cx * (int)((unsigned)m.base_ny >> 16) + cy;
                 if (kCount) {
                     // the most frequent partner of cx is not counted: the host restores it from the column
                     // histogram (dr_cooc_skip) -- on correlated pairs that removes nearly every atomic
-                    if (p.skip == nullptr || __ldg(p.skip + __ldg(p.skip_off + q) + cx) != cy)
-                        atomicAdd(&tab[base + idx], 1u);
+                    if (!use_skip || skip[m.skip + cx] != cy) atomicAdd(&tab[base + idx], 1u);
                 } else {
                     const uint32_t bit = 1u << (idx & 31);
                     uint32_t* w = &tab[base + (idx >> 5)];
@@ -136,21 +160,26 @@ int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n
         for (int i = 0; i < n_cols; ++i) slot_of[i] = -1;
         int q1 = q0;
         int64_t words = 0;
+        auto skip_entries = [&](int qa, int qb) { return skip_off ? (int64_t)(skip_off[qb] - skip_off[qa]) : 0; };
         while (q1 < n_pairs) {
             const int extra = (slot_of[px[q1]] < 0) + (slot_of[py[q1]] < 0);
             const int64_t words_after = off[q1 + 1] - off[q0];
-            const size_t bytes_after = (size_t)words_after * 4 + (size_t)(p.n_used + extra) * kTile * 2;
-            if (q1 > q0 && bytes_after > (size_t)200 * 1024) break;
+            const size_t bytes_after = (size_t)(words_after + 4) * 4 + (size_t)(p.n_used + extra) * kTile * 2 +
+                                       (size_t)(q1 + 1 - q0) * 16 + (size_t)(skip_entries(q0, q1 + 1) + 2) * 2;
+            // 65535 table words: the pair metadata keeps the pair's base in 16 bits
+            if (q1 > q0 && (bytes_after > (size_t)200 * 1024 || words_after > 65535)) break;
             if (slot_of[px[q1]] < 0) { slot_of[px[q1]] = p.n_used; p.used[p.n_used++] = px[q1]; }
             if (slot_of[py[q1]] < 0) { slot_of[py[q1]] = p.n_used; p.used[p.n_used++] = py[q1]; }
             words = words_after;
             ++q1;
         }
-        const size_t smem = (size_t)words * 4 + (size_t)p.n_used * kTile * 2;
-        if (smem > 220 * 1024)
+        const int np = q1 - q0;
+        const int skip_words = (int)((skip_entries(q0, q1) + 1) / 2);
+        const size_t smem = (size_t)((words + 3) & ~(int64_t)3) * 4 + (size_t)np * 16 + (size_t)skip_words * 4 +
+                            (size_t)p.n_used * kTile * 2;
+        if (smem > 220 * 1024 || words > 65535)
             return dr_fail(ctx, DR_ERR_UNSUPPORTED, "pair table of %lld words does not fit in shared memory",
                            (long long)words);
-        const int np = q1 - q0;
         for (int q = 0; q < np; ++q) {
             h[q] = slot_of[px[q0 + q]];
             h[np + q] = slot_of[py[q0 + q]];
@@ -168,6 +197,8 @@ int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n
         p.off = d + 2 * np;
         p.skip = skip;
         p.skip_off = d + 3 * np + 1;
+        p.skip_off0 = skip_off ? (int32_t)skip_off[q0] : 0;
+        p.skip_len = (int32_t)skip_entries(q0, q1);
         p.n_pairs = np;
         p.n_rows = n_rows;
         p.block_rows = block_rows;
@@ -178,7 +209,7 @@ int run_pairs(dr_ctx* ctx, const int32_t* const* cols, const int32_t* dom, int n
         int grid = ctx->sm_count * per_sm;
         if ((int64_t)grid > units) grid = (int)units;
         char* outp = (char*)out + (kCount ? sizeof(int64_t) : sizeof(uint32_t)) * (size_t)off[q0];
-        k_pairs<kCount><<<grid, kThreads, smem, st>>>(p, (int)words, outp);
+        k_pairs<kCount><<<grid, kThreads, smem, st>>>(p, (int)words, skip_words, outp);
         DR_LAUNCHED(ctx);
         DR_CUDA(ctx, cudaStreamSynchronize(st));  // h / scratch are reused by the next range
         q0 = q1;

@@ -43,7 +43,9 @@ class dr_forest_ranked(ctypes.Structure):
 class dr_gbdt_params(ctypes.Structure):
     _fields_ = [("n_rows", c_int32), ("n_features", c_int32), ("n_classes", c_int32), ("n_iter", c_int32),
                 ("max_depth", c_int32), ("num_leaves", c_int32), ("min_data_in_leaf", c_int32),
-                ("learning_rate", c_double), ("min_sum_hessian", c_double), ("qscale", c_double)]
+                ("learning_rate", c_double), ("min_sum_hessian", c_double), ("qscale", c_double),
+                ("reg_lambda", c_double), ("colsample_bytree", c_double), ("subsample", c_double),
+                ("subsample_freq", c_int32), ("seed", c_int32)]
 
 
 _PP = POINTER(c_void_p)
@@ -443,7 +445,8 @@ def _profiled(name, fn):
 
 for _name in ("widen_u8", "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
-              "pair_presence", "cooc", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
+              "pair_presence", "cooc", "cooc_skip", "key_presence", "key_flag", "dc_exists", "combine_counts", "dc_lt_flag",
+              "dc_hash_build", "dc_hash_flag", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill", "gbdt_train"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))
 

@@ -587,29 +587,31 @@ class Engine:
             offs.append(offs[-1] + ((n + 31) // 32 if bits else n))
         return offs
 
-    def launch_pair_presence(self, pairs):
-        """Distinct-pair presence bits on a row sample (the whole table when it is small), not waited
-        for.  -> (pairs, word offsets, device bit words, covers_every_row)"""
+    def launch_pair_presence(self, pairs, full=False):
+        """Distinct-pair presence bits on a row sample (the whole table when it is small or `full`), not
+        waited for.  -> (pairs, word offsets, device bit words, covers_every_row)"""
         attrs = list(dict.fromkeys(a for p in pairs for a in p))
         if len(attrs) > 64:
             raise NotImplementedError("more than 64 discretised attributes")
         idx = {a: i for i, a in enumerate(attrs)}
         offs = self._pair_layout(pairs, bits=True)
         bits = self.torch.zeros(max(offs[-1], 1), dtype=self.torch.int32, device=self.device)
-        block_rows = 256
-        n_blocks = min((self.n_rows + block_rows - 1) // block_rows, PRESENCE_SAMPLE_ROWS // block_rows)
+        block_rows = 512
+        n_blocks = (self.n_rows + block_rows - 1) // block_rows
+        if not full:
+            n_blocks = min(n_blocks, PRESENCE_SAMPLE_ROWS // block_rows)
         covers = n_blocks * block_rows >= self.n_rows
         self.ctx.pair_presence([self.disc_cols[a] for a in attrs], [self.disc_dom[a] for a in attrs],
                                [idx[x] for x, _ in pairs], [idx[y] for _, y in pairs], offs, self.n_rows,
                                block_rows, n_blocks, bits)
         return pairs, offs, bits, covers
 
-    def pair_presence_host(self, launched):
+    def pair_presence_host(self, launched, check_cover=True):
         """-> ({frozenset pair: distinct count seen}, {pair: bool [dom_x+1, dom_y+1]}, exact)"""
         pairs, offs, bits, covers = launched
         words = bits.cpu().numpy().view(np.uint32)
         exact = covers
-        if self.dist is not None:   # the sample is exact only if it covered every shard completely
+        if self.dist is not None and check_cover:   # the sample is exact only if it covered every shard completely
             t = self.torch.tensor([1 if covers else 0], dtype=self.torch.int64, device=self.device)
             self.dist.min_(t)
             exact = bool(int(t.item()))
@@ -629,48 +631,67 @@ class Engine:
         nnz, _, exact = self.pair_presence_host(launched)
         return nnz, exact
 
-    def pair_tables(self, pairs, present=None):
+    def pair_tables(self, pairs, present=None, presence_only=()):
         """Exact co-occurrence tables {(x, y): int64[dom_x+1, dom_y+1]} for `pairs` (over all shards).
         For every x value ONE partner y is left uncounted by the kernel and restored here from the
         column histogram (dr_cooc_skip): the partner that is most frequent overall among those seen
-        with x in the presence sample -- on correlated pairs that removes nearly all atomics."""
-        if not pairs:
-            return {}
-        attrs = list(dict.fromkeys(a for p in pairs for a in p))
+        with x in the presence sample -- on correlated pairs that removes nearly all shared-memory
+        atomics, which are what bounds the kernel.  The kernel sees every pair with the LARGER domain as
+        x (a determinant has one partner per value; the dependent has several).
+        presence_only: pairs for which only the exact distinct-pair count is wanted (full-table
+        presence bits, no atomics); both travel in ONE exchange.  -> (tables, {frozenset: nnz})"""
+        if not pairs and not presence_only:
+            return {}, {}
+        attrs = list(dict.fromkeys(a for p in list(pairs) + list(presence_only) for a in p))
         if len(attrs) > 64:
             raise NotImplementedError("more than 64 discretised attributes")
         need = [a for a in attrs if a not in self._hist_cache]
         self.scan_hist(need, {})
-        idx = {a: i for i, a in enumerate(attrs)}
-        offs = self._pair_layout(pairs, bits=False)
-        skip_off, skip = [0], []
-        for (x, y) in pairs:
-            hy = np.asarray(self._hist_cache[y], dtype=np.int64)
-            pres = None if present is None else present.get((x, y))
-            if pres is None and present is not None and (y, x) in present:
-                pres = present[(y, x)].T
-            if pres is None:
-                lut = np.full(self.disc_dom[x] + 1, int(np.argmax(hy)), dtype=np.int32)
-            else:
-                score = np.where(pres, hy[None, :] + 1, 0)
-                lut = np.where(score.max(axis=1) > 0, np.argmax(score, axis=1), int(np.argmax(hy))).astype(np.int32)
-            skip.append(lut)
-            skip_off.append(skip_off[-1] + len(lut))
-        d_skip = self.torch.from_numpy(np.concatenate(skip)).to(self.device)
-        out = self.torch.zeros(offs[-1], dtype=self.torch.int64, device=self.device)
-        self.ctx.cooc_skip([self.disc_cols[a] for a in attrs], [self.disc_dom[a] for a in attrs],
-                           [idx[x] for x, _ in pairs], [idx[y] for _, y in pairs], offs, self.n_rows, d_skip,
-                           skip_off, out)
-        self.exchange([(out, "sum")])
-        h = out.cpu().numpy()
-        tables = {}
-        for q, (x, y) in enumerate(pairs):
-            tab = h[offs[q]:offs[q + 1]].reshape(self.disc_dom[x] + 1, self.disc_dom[y] + 1).copy()
-            rows = np.arange(tab.shape[0])
-            tab[rows, skip[q]] = 0
-            tab[rows, skip[q]] = np.asarray(self._hist_cache[x], dtype=np.int64) - tab.sum(axis=1)
-            tables[(x, y)] = tab
-        return tables
+        parts, launched_p = [], None
+        if presence_only:
+            launched_p = self.launch_pair_presence(list(presence_only), full=True)
+            parts.append((launched_p[2], "or"))
+        kp, offs, skip, skip_off, out = [], [0], [], [0], None
+        if pairs:
+            for (x, y) in pairs:   # kernel orientation: larger domain first
+                kp.append((x, y) if self.disc_dom[x] >= self.disc_dom[y] else (y, x))
+            idx = {a: i for i, a in enumerate(attrs)}
+            offs = self._pair_layout(kp, bits=False)
+            for (x, y) in kp:
+                hy = np.asarray(self._hist_cache[y], dtype=np.int64)
+                pres = None
+                if present is not None:
+                    pres = present.get((x, y))
+                    if pres is None and (y, x) in present:
+                        pres = present[(y, x)].T
+                if pres is None:
+                    lut = np.full(self.disc_dom[x] + 1, int(np.argmax(hy)), dtype=np.int32)
+                else:
+                    sc = np.where(pres, hy[None, :] + 1, 0)
+                    lut = np.where(sc.max(axis=1) > 0, np.argmax(sc, axis=1), int(np.argmax(hy))).astype(np.int32)
+                skip.append(lut)
+                skip_off.append(skip_off[-1] + len(lut))
+            d_skip = self.torch.from_numpy(np.concatenate(skip)).to(self.device)
+            out = self.torch.zeros(offs[-1], dtype=self.torch.int64, device=self.device)
+            self.ctx.cooc_skip([self.disc_cols[a] for a in attrs], [self.disc_dom[a] for a in attrs],
+                               [idx[x] for x, _ in kp], [idx[y] for _, y in kp], offs, self.n_rows, d_skip,
+                               skip_off, out)
+            parts.append((out, "sum"))
+        self.exchange(parts)
+        tables, nnz = {}, {}
+        if pairs:
+            h = out.cpu().numpy()
+            for q, ((x, y), (kx, ky)) in enumerate(zip(pairs, kp)):
+                tab = h[offs[q]:offs[q + 1]].reshape(self.disc_dom[kx] + 1, self.disc_dom[ky] + 1).copy()
+                rows = np.arange(tab.shape[0])
+                tab[rows, skip[q]] = 0
+                tab[rows, skip[q]] = np.asarray(self._hist_cache[kx], dtype=np.int64) - tab.sum(axis=1)
+                tables[(x, y)] = tab if (kx, ky) == (x, y) else np.ascontiguousarray(tab.T)
+                nnz[frozenset((x, y))] = int(np.count_nonzero(tab))
+        if launched_p is not None:
+            got, _, _ = self.pair_presence_host(launched_p, check_cover=False)
+            nnz.update(got)
+        return tables, nnz
 
     def compute_attr_stats(self, targets, domain_stats, attr_freq_thr, pairwise_thr, max_attrs, presence=None):
         """computeAttrStats (RepairApi.scala:396-477) -> (pairwise_stats, tables, having).
@@ -704,14 +725,28 @@ class Engine:
                     selected[t] = SH.select_scored(cands[t], lower, domain_stats, pairwise_thr, max_attrs)
             else:
                 und = {t: SH.undecided(cands[t], lower, domain_stats, pairwise_thr) for t in scoring}
-                need = uniq([p for t in scoring for p in und[t]] + [p for t in selected for p in selected[t]])
-                tables = self.pair_tables(need, present)
-                nnz = {frozenset(k): int(np.count_nonzero(v)) for k, v in tables.items()}
+                # counted now: per target the `max_attrs` undecided pairs with the smallest lower bounds,
+                # unless the bound is already within 5 % of the threshold -- those (typically pairs of
+                # independent attributes the sample missed a few rare combinations of) only get their exact
+                # distinct count from full-table presence bits; a pair that is selected after all is
+                # counted with the `missing` ones below
+                count_now, count_set = [p for t in selected for p in selected[t]], set()
+                for t in scoring:
+                    ranked = sorted(und[t], key=lambda pr: lower[frozenset(pr)] / float(
+                        max(domain_stats[pr[0]] * domain_stats[pr[1]], 1)))
+                    for pr in ranked[:max_attrs]:
+                        den = float(max(domain_stats[pr[0]] * domain_stats[pr[1]], 1))
+                        if lower[frozenset(pr)] / den < 0.95 * pairwise_thr:
+                            count_now.append(pr)
+                count_now = uniq(count_now)
+                count_set = {frozenset(p) for p in count_now}
+                only_nnz = [p for p in uniq([p for t in scoring for p in und[t]]) if frozenset(p) not in count_set]
+                tables, nnz = self.pair_tables(count_now, present, only_nnz)
                 for t in scoring:
                     selected[t] = SH.select_scored(und[t], nnz, domain_stats, pairwise_thr, max_attrs)
         pairs = [p for t in targets for p in selected[t]]
         missing = [p for p in uniq(pairs) if p not in tables and (p[1], p[0]) not in tables]
-        tables.update(self.pair_tables(missing, present))
+        tables.update(self.pair_tables(missing, present)[0])
         having = SH.having_threshold(self.n_rows_global, attr_freq_thr)
         need_hist = [a for a in disc_attrs if a not in self._hist_cache]
         self.scan_hist(need_hist, {})

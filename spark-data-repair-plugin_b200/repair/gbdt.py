@@ -66,7 +66,8 @@ def initial_scores(y, n_classes, weight):
 
 
 def train_gpu(ctx, device, bins, n_bins, bin_values, y, n_classes, weight, n_iter, learning_rate, max_depth,
-              num_leaves=31, min_data_in_leaf=20, min_sum_hessian=1e-3):
+              num_leaves=31, min_data_in_leaf=20, min_sum_hessian=1e-3, reg_lambda=0.0, colsample_bytree=1.0,
+              subsample=1.0, subsample_freq=0, seed=42):
     """-> flat forest (forest.py layout)."""
     import torch
     from ._native import dr_gbdt_params
@@ -79,7 +80,8 @@ def train_gpu(ctx, device, bins, n_bins, bin_values, y, n_classes, weight, n_ite
     else:
         qscale = float(2 ** quant_bits(n)) / float(np.max(weight))
     prm = dr_gbdt_params(n, F, n_classes, n_iter, max_depth, num_leaves, min_data_in_leaf, learning_rate,
-                         min_sum_hessian, qscale)
+                         min_sum_hessian, qscale, float(reg_lambda), float(colsample_bytree), float(subsample),
+                         int(subsample_freq), int(seed))
     d_bins = torch.from_numpy(np.ascontiguousarray(bins)).to(device)
     d_yc = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32)).to(device) if n_classes >= 2 else None
     d_yv = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(device) if n_classes == 1 else None

@@ -140,7 +140,6 @@ class RepairModel():
         self.row_id = table.row_id
         return self
 
-    @argtype_check
     def setDistributed(self, group: Any = True, device_index: Optional[int] = None) -> "RepairModel":
         """Row-sharded run over the ranks of a ``torch.distributed`` process group (one process per GPU,
         NCCL): every rank passes ITS rows to ``setInput`` and gets the repairs of its rows back.  The
@@ -152,6 +151,7 @@ class RepairModel():
             self.device_index = int(device_index)
         return self
 
+    @argtype_check
     def setRowId(self, row_id: str) -> "RepairModel":
         if not row_id:
             raise ValueError("`row_id` should have at least character")
@@ -399,11 +399,14 @@ class RepairModel():
                           "current_value": pd.array(curs, dtype=object)})
 
 
-def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class):
+def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class, y=None):
     """Model producer: the GPU histogram GBDT (gbdt.py) when every feature is discrete, else
-    scikit-learn's (train.py).  Both use the reference's fixed parameters (train.py:102-115)."""
+    scikit-learn's (train.py).  Both use the reference's fixed parameters (train.py:102-115) and the
+    tuned ones found by search.py (train.py:133-229: TPE-style search under k-fold CV, budget options
+    model.hp.* / model.cv.n_splits)."""
     from . import gbdt as G
-    from .train import _get
+    from . import search as HS
+    from .train import _get, search_options
     binned = None
     if rm.trainer != "sklearn" and is_discrete:
         binned = G.bin_sample(encoders, {f: codes[:, tile_col[f]] for f in features}, dict_sizes)
@@ -411,12 +414,44 @@ def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_value
         bins, n_bins, values = binned
         classes = sorted(set(int(v) for v in y_values.tolist()))
         y_idx = np.searchsorted(np.asarray(classes), y_values).astype(np.int64)
-        w = G.class_weights(y_idx, len(classes), _get(rm.opts, "model.lgb.class_weight") == "balanced")
+        balanced = _get(rm.opts, "model.lgb.class_weight") == "balanced"
         depth = _get(rm.opts, "model.lgb.max_depth")
-        forest = G.train_gpu(engine.ctx, engine.device, bins, n_bins, values, y_idx, len(classes), w,
-                             _get(rm.opts, "model.lgb.n_estimators"), _get(rm.opts, "model.lgb.learning_rate"),
-                             depth if depth > 0 else 31)
-        return {"forest": forest, "class_codes": classes}
+
+        def train(params, rows=None):
+            b, yi = (bins, y_idx) if rows is None else (np.ascontiguousarray(bins[rows]), y_idx[rows])
+            w = G.class_weights(yi, len(classes), balanced)
+            return G.train_gpu(engine.ctx, engine.device, b, n_bins, values, yi, len(classes), w,
+                               _get(rm.opts, "model.lgb.n_estimators"), _get(rm.opts, "model.lgb.learning_rate"),
+                               depth if depth > 0 else 31,
+                               num_leaves=int(min(max(params["num_leaves"], 2), 32)),   # the trainer's node budget
+                               min_data_in_leaf=int(max(params["min_child_samples"], 1)),
+                               min_sum_hessian=float(params["min_child_weight"]),
+                               reg_lambda=float(params["reg_lambda"]),
+                               colsample_bytree=float(params["colsample_bytree"]),
+                               subsample=float(params["subsample"]), subsample_freq=int(params["subsample_freq"]))
+
+        max_evals, no_progress, timeout, n_splits = search_options(rm.opts)
+        params = dict(HS.DEFAULTS)
+        if max_evals > 1 and y is not None:
+            folds = HS.cv_folds(y_idx, True, n_splits)
+            tile = engine.torch.from_numpy(np.ascontiguousarray(codes, dtype=np.int32)).to(engine.device)
+            K = codes.shape[1]
+
+            def evaluate(p):
+                scores = []
+                for tr, va in folds:
+                    spec = {"forest": train(p, tr), "encoders": encoders, "class_codes": classes, "integral": False}
+                    dm = DeviceModel(spec, tile_col, dict_sizes, {}, engine.device)
+                    work = tile.clone()
+                    cells = engine.torch.from_numpy(np.ascontiguousarray(va, dtype=np.int32)).to(engine.device)
+                    dm.predict(engine.ctx, work, K, None, 0, cells, len(va), tile_col[y])
+                    pred = work[cells.to(engine.torch.int64), tile_col[y]].cpu().numpy()
+                    scores.append(HS.score(y_values[va], pred, True))
+                return -float(np.mean(scores))
+
+            params, _, n_eval = HS.search(evaluate, max_evals, no_progress, timeout)
+            rm.last_run.setdefault("search", {})[y] = {"evals": n_eval, "params": params}
+        return {"forest": train(params), "class_codes": classes}
     forest, classes = build_model(X, y_values, is_discrete, num_class, rm.opts)
     return None if forest is None else {"forest": forest, "class_codes": classes}
 
@@ -474,7 +509,7 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps=None):
     if rm.model_provider is not None:
         spec = rm.model_provider(ctx)
     else:
-        spec = _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class)
+        spec = _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_values, is_discrete, num_class, y)
     if spec is None:
         return ("const", None)
     if "const" in spec:

@@ -74,32 +74,66 @@ def flatten_sklearn(est, n_features, n_classes):
     }
 
 
+def search_options(opts):
+    """(max_evals, no_progress_loss, timeout, n_splits) of train.py:72-86."""
+    return (_get(opts, "model.hp.max_evals"), _get(opts, "model.hp.no_progress_loss"), _get(opts, "model.hp.timeout"),
+            _get(opts, "model.cv.n_splits"))
+
+
+def sklearn_estimator(is_discrete, opts, params):
+    """scikit-learn histogram GBDT with the reference's fixed parameters (train.py:102-115) and the tuned
+    ones it has a counterpart for: num_leaves -> max_leaf_nodes, min_child_samples -> min_samples_leaf,
+    reg_lambda -> l2_regularization, colsample_bytree -> max_features (per split instead of per tree);
+    min_child_weight and row sub-sampling have no counterpart and are ignored."""
+    from sklearn.ensemble import HistGradientBoostingClassifier, HistGradientBoostingRegressor
+    common = dict(
+        learning_rate=_get(opts, "model.lgb.learning_rate"),
+        max_iter=_get(opts, "model.lgb.n_estimators"),
+        max_depth=_get(opts, "model.lgb.max_depth") if _get(opts, "model.lgb.max_depth") > 0 else None,
+        max_leaf_nodes=max(2, int(params["num_leaves"])), min_samples_leaf=max(1, int(params["min_child_samples"])),
+        max_bins=min(255, max(2, _get(opts, "model.lgb.max_bin"))),
+        l2_regularization=float(params["reg_lambda"]), early_stopping=False, random_state=42)
+    try:
+        import inspect
+        if "max_features" in inspect.signature(HistGradientBoostingRegressor.__init__).parameters:
+            common["max_features"] = float(min(1.0, max(params["colsample_bytree"], 1e-3)))
+    except (TypeError, ValueError):
+        pass
+    if is_discrete:
+        cw = _get(opts, "model.lgb.class_weight")
+        return HistGradientBoostingClassifier(class_weight="balanced" if cw == "balanced" else None, **common)
+    return HistGradientBoostingRegressor(**common)
+
+
 def build_model(X, y, is_discrete, num_class, opts):
     """-> (flat forest, class labels ascending or None) or (None, None) when training fails
     (the reference swallows failures into PoorModel(None), train.py:227-229).
 
-    Fixed parameters follow train.py:102-115; the seven parameters the reference tunes with
-    hyperopt stay at LightGBM's defaults (num_leaves 31, min_child_samples 20, no subsampling,
-    reg_lambda 0)."""
-    from sklearn.ensemble import HistGradientBoostingClassifier, HistGradientBoostingRegressor
+    Fixed parameters follow train.py:102-115; the seven tuned parameters come from the search of
+    search.py (train.py:133-229) -- LightGBM's defaults when ``model.hp.max_evals`` is 1."""
+    from . import search as HS
     try:
-        common = dict(
-            learning_rate=_get(opts, "model.lgb.learning_rate"),
-            max_iter=_get(opts, "model.lgb.n_estimators"),
-            max_depth=_get(opts, "model.lgb.max_depth") if _get(opts, "model.lgb.max_depth") > 0 else None,
-            max_leaf_nodes=31, min_samples_leaf=20, max_bins=min(255, max(2, _get(opts, "model.lgb.max_bin"))),
-            l2_regularization=0.0, early_stopping=False, random_state=42)
         X = np.asarray(X, dtype=np.float64)
         if X.shape[1] == 0:
             X = np.zeros((X.shape[0], 1))
+        yv = np.asarray(y) if is_discrete else np.asarray(y, dtype=np.float64)
+        max_evals, no_progress, timeout, n_splits = search_options(opts)
+        folds = HS.cv_folds(yv, is_discrete, n_splits) if max_evals > 1 else None
+
+        def evaluate(params):
+            scores = []
+            for tr, va in folds:
+                est = sklearn_estimator(is_discrete, opts, params)
+                est.fit(X[tr], yv[tr])
+                scores.append(HS.score(yv[va], est.predict(X[va]), is_discrete))
+            return -float(np.mean(scores))
+
+        params, _, _ = HS.search(evaluate, max_evals, no_progress, timeout)
+        est = sklearn_estimator(is_discrete, opts, params)
+        est.fit(X, yv)
         if is_discrete:
-            cw = _get(opts, "model.lgb.class_weight")
-            est = HistGradientBoostingClassifier(class_weight="balanced" if cw == "balanced" else None, **common)
-            est.fit(X, np.asarray(y))
             classes = [c.item() if hasattr(c, "item") else c for c in est.classes_]
             return flatten_sklearn(est, X.shape[1], len(classes)), classes
-        est = HistGradientBoostingRegressor(**common)
-        est.fit(X, np.asarray(y, dtype=np.float64))
         return flatten_sklearn(est, X.shape[1], 1), None
     except Exception as e:  # noqa: BLE001
         _logger.warning("Failed to build a stat model because: {}".format(e))

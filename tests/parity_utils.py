@@ -104,6 +104,9 @@ def run_product(inp, row_id, specs, targets=None, thres=80, opts=None, given=Non
         rm.setDiscreteThreshold(thres)
     if given is not None:
         rm.setErrorCells(given)
+    # like the reference's own unit tests (tests/test_model.py:269-273), one evaluation = no search,
+    # unless the test asks for one
+    rm.option("model.hp.max_evals", "1")
     for k, v in (opts or {}).items():
         if k.startswith("_"):
             rm.opts[k] = v

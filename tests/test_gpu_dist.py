@@ -34,7 +34,8 @@ def _specs():
              "targets": ["c00"]}]
 
 
-OPTS = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": 8, "model.max_training_row_num": 3000}
+OPTS = {"error.pairwise_freq_ratio_threshold": 1.0, "model.lgb.n_estimators": 8, "model.max_training_row_num": 3000,
+        "model.hp.max_evals": 1}
 
 
 def _run(table, dist, device_index, mode):

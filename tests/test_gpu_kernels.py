@@ -537,6 +537,41 @@ def test_gbdt_trainer_matches_oracle_bit_for_bit(ctx, n_classes, n, n_iter):
     assert (np.asarray(want["feature"]) >= 0).sum() > n_iter    # the trees actually split
 
 
+@pytest.mark.parametrize("n_classes,kw", [
+    (3, dict(reg_lambda=1.5)), (2, dict(colsample_bytree=0.4)), (4, dict(subsample=0.7, subsample_freq=2)),
+    (1, dict(reg_lambda=0.3, colsample_bytree=0.6, subsample=0.8, subsample_freq=1, num_leaves=9, min_data_in_leaf=4,
+             min_sum_hessian=0.5)),
+    (5, dict(reg_lambda=4.0, colsample_bytree=0.15, subsample=0.55, subsample_freq=3, num_leaves=32))])
+def test_gbdt_trainer_tuned_parameters_match_oracle_bit_for_bit(ctx, n_classes, kw):
+    """The parameters of the reference's search space (train.py:148-156) in the trainer and in its
+    specification: reg_lambda, colsample_bytree (hashed feature subsets), subsample / subsample_freq
+    (hashed bags), num_leaves, min_child_samples, min_child_weight."""
+    from oracle import gbdt as OG
+    from repair import gbdt as PG
+    rng = np.random.default_rng(n_classes * 17)
+    n, n_iter = 900, 7
+    doms = [4, 9, 3, 6, 30, 2, 12, 5]
+    vals = [np.sort(rng.choice(np.arange(-3, 40), size=d, replace=False)).astype(np.float64) for d in doms]
+    n_bins = np.array([d + 1 for d in doms], dtype=np.int32)
+    bins = np.stack([rng.integers(0, d + 1, size=n) for d in doms], axis=1).astype(np.uint8)
+    sig = (bins[:, 0].astype(int) * 3 + bins[:, 4] + (bins[:, 1] > 4) * 5)
+    if n_classes == 1:
+        y, w = sig * 0.37 + rng.normal(size=n), np.ones(n)
+    else:
+        y = ((sig + rng.integers(0, 2, size=n)) % n_classes).astype(np.int64)
+        w = PG.class_weights(y, n_classes, balanced=True)
+    args = dict(num_leaves=15, min_data_in_leaf=10)
+    args.update(kw)
+    want = OG.to_flat_forest(OG.train(bins, n_bins, y, n_classes, w if n_classes > 1 else None, n_iter, 0.1, 5, **args),
+                             vals, len(doms))
+    got = PG.train_gpu(ctx, torch.device("cuda", 0), bins, n_bins, vals, y, n_classes, w, n_iter, 0.1, 5, **args)
+    for k in ("tree_seq", "tree_offset", "feature", "missing_left", "left", "right"):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+    assert np.array_equal(got["threshold"], want["threshold"])
+    assert np.array_equal(got["value"], want["value"])
+    assert (np.asarray(want["feature"]) >= 0).sum() > n_iter
+
+
 def test_byte_stager_double_buffering(ctx):
     """Successive byte batches reach the resident table in order, with the next copy in flight."""
     from repair.table import ByteStager, DeviceTable, EncodedTable

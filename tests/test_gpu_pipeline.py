@@ -336,9 +336,10 @@ def test_arrow_input_gives_the_same_repairs_as_pandas_input():
     from repair import NullErrorDetector, RepairModel
     df = adult()
     want = RepairModel().setInput(df).setRowId("tid").setErrorDetectors([NullErrorDetector()]) \
-        .option("model.lgb.n_estimators", "30").run()
+        .option("model.lgb.n_estimators", "30").option("model.hp.max_evals", "1").run()
     got = RepairModel().setArrowInput(pa.Table.from_pandas(df, preserve_index=False)).setRowId("tid") \
-        .setErrorDetectors([NullErrorDetector()]).option("model.lgb.n_estimators", "30").run()
+        .setErrorDetectors([NullErrorDetector()]).option("model.lgb.n_estimators", "30") \
+        .option("model.hp.max_evals", "1").run()
     assert PU.frame_tuples(got, "tid") == PU.frame_tuples(want, "tid") and len(got) == 7
 
 
