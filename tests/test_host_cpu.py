@@ -319,7 +319,7 @@ def test_oracle_forest_matches_sklearn(kind):
     X = rng.integers(0, 6, size=(n, 7)).astype(float)
     X[rng.random(X.shape) < 0.08] = np.nan
     base = np.nan_to_num(X[:, 0]) + np.nan_to_num(X[:, 3]) * 2
-    opts = {"model.lgb.n_estimators": "40", "model.lgb.learning_rate": "0.1"}
+    opts = {"model.lgb.n_estimators": "40", "model.lgb.learning_rate": "0.1", "model.hp.max_evals": "1"}
     from sklearn.ensemble import HistGradientBoostingClassifier, HistGradientBoostingRegressor
     common = dict(learning_rate=0.1, max_iter=40, max_depth=7, max_leaf_nodes=31, min_samples_leaf=20, max_bins=255,
                   l2_regularization=0.0, early_stopping=False, random_state=42)
