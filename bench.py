@@ -33,10 +33,17 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--rows", type=int, default=100_000_000,
+                    help="rows of the table (strong scaling: sharded over the GPUs; weak scaling: per GPU)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): ONE --rows table sharded rows/N per GPU (BASELINE config 4); "
+                         "weak: --rows per GPU of a N x --rows table")
     ap.add_argument("--cols", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-rows", type=int, default=10000, help="rows of the CPU baseline sample")
+    ap.add_argument("--ref-rows", type=int, default=20000, help="rows of the CPU baseline sample")
+    ap.add_argument("--configs", default="auto",
+                    help="extra wall-clock rows for BASELINE configs: comma list of c2,c3,c5, 'none', or 'auto' "
+                         "(all three on a 1-GPU run of the default size)")
     ap.add_argument("--forests", default="trained", choices=["trained", "random"],
                     help="trained: dr_gbdt_train on the real 10k-row samples (default); random: random-init "
                          "forests of the same architecture")
@@ -122,7 +129,7 @@ def run_oracle_sample(n_rows, n_cols, n_iter):
     threads = 1
     if ckernels.available():
         OF.forest_margins = ckernels.forest_margins  # compiled, OpenMP; checked in tests/test_oracle_c.py
-        threads = ckernels.num_threads()
+        threads = ckernels.use_all_cores()           # (torchrun exports OMP_NUM_THREADS=1)
     spec = synth.SynthSpec.c4(n_rows, n_cols)
     codes = synth.generate_numpy(spec)
     names = synth.column_names(n_cols)
@@ -324,6 +331,200 @@ def verify_step(engine, table, res, out, models, k, n_sample, dist, seed=12345):
     return info
 
 
+# ---------------------------------------------------------------------------------------------
+# NUMA: a rank's host threads (Arrow ingest workers, the pinned chunk ring they fill) belong on the
+# CPU socket its GPU hangs off; 8 ranks sharing one socket's memory controllers is what cost the
+# end-to-end leg 10 % at N=8 in round 1
+# ---------------------------------------------------------------------------------------------
+_FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(local):
+    global _FULL_AFFINITY
+    info = {"bound": False}
+    try:
+        import pynvml
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/{}/numa_node".format(bus.lower()[-12:])
+        node = int(open(path).read().strip())
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node{}/cpulist".format(node)).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus |= set(range(int(a), int(b or a) + 1))
+            cpus &= _FULL_AFFINITY
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info = {"bound": True, "node": node, "cpus": len(cpus)}
+    except Exception as e:  # no NVML / sysfs entry / permission: run unbound
+        info["why"] = "{}: {}".format(type(e).__name__, e)
+    return info
+
+
+def restore_affinity():
+    if _FULL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configs: wall clock through the public API
+# ---------------------------------------------------------------------------------------------
+def other_configs(want, local):
+    import pandas as pd
+    import torch
+    from repair import (ConstraintErrorDetector, GaussianOutlierErrorDetector, NullErrorDetector, RepairModel, synth)
+    golden = os.path.join(ROOT, "tests", "golden")
+    out = {}
+
+    def timed_run(make, **kw):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m = make()
+        frame = m.run(**kw)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, frame, m
+
+    if "c2" in want:   # hospital.csv + hospital_constraints.txt, Null + Constraint detectors (BASELINE config 2)
+        df = pd.read_csv(os.path.join(golden, "hospital.csv"), dtype=str)
+        make = lambda: RepairModel().setInput(df).setRowId("tid").setErrorDetectors(  # noqa: E731
+            [NullErrorDetector(), ConstraintErrorDetector(os.path.join(golden, "hospital_constraints.txt"))]) \
+            .option("model.hp.max_evals", "1")
+        timed_run(make, detect_errors_only=True)                        # warm-up (library load, allocator)
+        t_det, cells, _ = timed_run(make, detect_errors_only=True)
+        t_all, frame, m = timed_run(make)
+        frozen = m.last_run["models"] if "models" in m.last_run else None
+        t_inf = None
+        if frozen is not None:
+            t_inf, _, _ = timed_run(lambda: make().setFrozenModels(frozen))
+        out["C2_hospital"] = {"rows": len(df), "cols": len(df.columns) - 1, "error_cells": int(len(cells)),
+                              "repaired_cells": int(len(frame)), "detect_only_s": round(t_det, 4),
+                              "full_run_with_training_s": round(t_all, 3),
+                              "training_s": round(m.last_run.get("elapsed_training", 0.0), 3),
+                              "full_run_frozen_models_s": None if t_inf is None else round(t_inf, 4),
+                              "how": "RepairModel.run() wall clock, pandas in / pandas out, 300-round models "
+                                     "trained inside the call (no hyper-parameter search)"}
+    if "c5" in want:   # boston.csv: numeric outlier detector + regressor predict (BASELINE config 5)
+        df = pd.read_csv(os.path.join(golden, "boston.csv"))
+        make = lambda: RepairModel().setInput(df).setRowId("tid").setErrorDetectors(  # noqa: E731
+            [NullErrorDetector(), GaussianOutlierErrorDetector(approx_enabled=False)]).option("model.hp.max_evals", "1")
+        timed_run(make, detect_errors_only=True)
+        t_det, cells, _ = timed_run(make, detect_errors_only=True)
+        t_all, frame, m = timed_run(make)
+        out["C5_boston"] = {"rows": len(df), "cols": len(df.columns) - 1, "error_cells": int(len(cells)),
+                            "repaired_cells": int(len(frame)), "detect_only_s": round(t_det, 4),
+                            "full_run_with_training_s": round(t_all, 3),
+                            "training_s": round(m.last_run.get("elapsed_training", 0.0), 3),
+                            "how": "RepairModel.run() wall clock; continuous features: scikit-learn histogram GBDT "
+                                   "trainer, generic float64 forest kernel"}
+    if "c3" in want:   # synthetic 10M x 16, 1% NULLs, NullErrorDetector (BASELINE config 3)
+        n, k = 10_000_000, 16
+        spec = synth.SynthSpec.c3(n, k)
+        dev = torch.device("cuda", local)
+        codes = synth.generate_torch(spec, dev, 0, n)
+        from repair._native import Context
+        ctx = Context(local)
+        tbl = host_arrow_shard(ctx, codes, n, 0, synth.column_names(k), spec.dom)
+        ctx.close()
+        del codes
+        make = lambda: RepairModel().setArrowInput(tbl).setRowId("tid").setErrorDetectors([NullErrorDetector()]) \
+            .option("model.hp.max_evals", "1")  # noqa: E731
+        t_det, cells, _ = timed_run(make, detect_errors_only=True)
+        t_det, cells, _ = timed_run(make, detect_errors_only=True)
+        t_all, frame, m = timed_run(make)
+        frozen = m.last_run["models"]
+        timed_run(lambda: make().setFrozenModels(frozen))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 3
+        ev0.record()
+        for _ in range(steps):
+            t_inf, frame, mi = timed_run(lambda: make().setFrozenModels(frozen))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        out["C3_10Mx16"] = {"rows": n, "cols": k, "error_cells": int(cells.num_rows),
+                            "repaired_cells": int(frame.num_rows), "detect_only_s": round(t_det, 4),
+                            "full_run_with_training_s": round(t_all, 3),
+                            "training_s": round(m.last_run.get("elapsed_training", 0.0), 3),
+                            "ms_per_pass_frozen_models": round(ms, 2), "rows_per_sec": n / (ms / 1e3),
+                            "ingest_s": round(mi.last_run.get("ingest_total_s", 0.0), 4),
+                            "egress_s": round(mi.last_run.get("egress_s", 0.0), 4),
+                            "how": "RepairModel().setArrowInput(host pyarrow.Table).run() -> pyarrow.Table, "
+                                   "host buffers in / host frame out every pass"}
+    return out
+
+
+def host_arrow_shard(ctx, codes_dev, n, lo, names, dom):
+    """The collected shard as the host holds it before ingest: a pyarrow.Table in ordinary (pageable)
+    memory -- int64 `tid`, one dictionary<int8, string> column per attribute ("v%03d" entries), NULLs as
+    Arrow nulls -- what `pyarrow.parquet.read_table(..., read_dictionary=...)` hands over."""
+    import pyarrow as pa
+    import torch
+    words = (n + 31) // 32
+    cols = {"tid": pa.array(np.arange(lo, lo + n, dtype=np.int64))}
+    bits = torch.empty(words, dtype=torch.int32, device=codes_dev.device)
+    for i, nm in enumerate(names):
+        col = codes_dev[i][:n]
+        idx = torch.clamp(col, min=0).to(torch.int8).cpu().numpy()
+        ctx.valid_bits(col, n, bits)
+        valid = bits.cpu().numpy().view(np.uint8)
+        indices = pa.Array.from_buffers(pa.int8(), n, [pa.py_buffer(valid), pa.py_buffer(idx)])
+        d = pa.array(["v%03d" % c for c in range(int(dom[i]))], type=pa.string())
+        cols[nm] = pa.DictionaryArray.from_arrays(indices, d, safe=False)
+    return pa.table(cols)
+
+
+def api_detectors(n_cols):
+    from repair import ConstraintErrorDetector, NullErrorDetector, synth
+    dets = [NullErrorDetector()]
+    fds = synth.fd_constraints(n_cols)
+    if fds:
+        dets.append(ConstraintErrorDetector(constraints=fds))
+    return dets
+
+
+def frames_equal(arrow_frame, out, lo, names, table):
+    """The API's Arrow frame == the encoded frame of the resident-table pass (row ids, attribute, current and
+    repaired dictionary entries), compared attribute chunk by attribute chunk."""
+    by_attr = {a: (np.asarray(rows), np.asarray(cur), np.asarray(rep)) for a, rows, cur, rep in out}
+    if arrow_frame.num_rows != sum(len(v[0]) for v in by_attr.values()):
+        return False
+    pos = 0
+    seen = set()
+    for k in range(arrow_frame["attribute"].num_chunks):
+        att = arrow_frame["attribute"].chunk(k)
+        if len(att) == 0:
+            continue
+        a = att.dictionary[att.indices[0].as_py()].as_py()
+        seen.add(a)
+        rows, cur, rep = by_attr[a]
+        m = len(rows)
+        ids = arrow_frame["tid"].chunk(k).to_numpy()
+        if len(att) != m or not np.array_equal(ids, rows.astype(np.int64) + lo):
+            return False
+        strs = table.by_name[a].strings()
+        for chunk, codes in ((arrow_frame["current_value"].chunk(k), cur), (arrow_frame["repaired"].chunk(k), rep)):
+            d = chunk.dictionary.to_pylist()
+            idx = chunk.indices.fill_null(-1).to_numpy(zero_copy_only=False).astype(np.int64)
+            want = np.asarray(codes, dtype=np.int64)
+            if not np.array_equal(idx < 0, want < 0):
+                return False
+            ok = idx >= 0
+            lut = np.array([strs.index(v) for v in d], dtype=np.int64) if d else np.zeros(0, dtype=np.int64)
+            if ok.any() and not np.array_equal(lut[idx[ok]], want[ok]):
+                return False
+        pos += m
+    return seen == {a for a, v in by_attr.items() if len(v[0])}
+
+
 def b200_arm(args):
     import torch
     from repair import RepairModel, synth
@@ -331,11 +532,12 @@ def b200_arm(args):
     from repair.engine import Dist, Engine
     from repair.errors import ErrorModelOptions
     from repair.model import build_models, repair_cells
-    from repair.table import ByteStager, DeviceTable, EncodedTable
+    from repair.table import DeviceTable, EncodedTable
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist = None
@@ -345,29 +547,22 @@ def b200_arm(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=device)
         dist = Dist()
-    n, k = args.rows, args.cols
-    spec = synth.SynthSpec.c4(n * world, k)
-    lo, hi = rank * n, (rank + 1) * n
+    k = args.cols
+    total_rows = args.rows if args.scaling == "strong" else args.rows * world
+    spec = synth.SynthSpec.c4(total_rows, k)
+    lo, hi = (total_rows * rank) // world, (total_rows * (rank + 1)) // world
+    n = hi - lo
 
-    # ---- setup (untimed): table in HBM + a pinned host copy for the end-to-end leg ----------
+    # ---- setup (untimed): the shard resident in HBM ------------------------------------------------
     codes_dev = synth.generate_torch(spec, device, lo, hi)
     n_pad = codes_dev.shape[1]
-    host = stage = None
-    if not args.no_e2e:
-        # the collected table as the host holds it: one byte per cell (all dictionaries <= 254 entries,
-        # 255 = NULL) in pinned memory; widened to the int32 device layout after the copy
-        stage = torch.where(codes_dev < 0, torch.full_like(codes_dev, 255), codes_dev).to(torch.uint8)
-        host = torch.empty((k, n_pad), dtype=torch.uint8, pin_memory=True)
-        host.copy_(stage)
-    del stage
     names = synth.column_names(k)
     host_np = [np.zeros(0, dtype=np.int32) for i in range(k)]
     table = EncodedTable.from_codes("tid", names, host_np, spec.dom, row_ids=np.arange(lo, hi, dtype=np.int64))
     table.n_rows = n
-    table.row_offset, table.n_rows_global = lo, n * world
+    table.row_offset, table.n_rows_global = lo, total_rows
     dt = DeviceTable(table, device, codes=codes_dev)
     engine = Engine(table, local, dist=dist, device_table=dt)
-    stager = None if host is None else ByteStager(dt, engine.ctx)
     rm = RepairModel()
     rm.opts = dict(OPTS)
     if args.forests == "random":
@@ -376,27 +571,12 @@ def b200_arm(args):
     specs = detector_specs(k)
     continuous = []
 
-    # frozen models: bookkeeping + encoders from a real training sample, random-init trees
+    # frozen models: trained ONCE on the global 10k-row sample (every rank draws the same sample and trains
+    # the same deterministic forests -- engine.valid_training_rows / sample_rows_masked)
     res = engine.detect(specs, [], 80, err_opts)
     torch.cuda.synchronize()
     t_train = time.time()
-    if dist is None:
-        models = build_models(rm, engine, table, res, continuous)
-    else:
-        # rank 0's model specs are broadcast so that every shard applies the same forests
-        import torch.distributed as td
-        payload = [None]
-        if rank == 0:
-            built = build_models(rm, engine, table, res, continuous)
-            payload = [[(y, m[0], (m[1] if m[0] == "const" else m[2]["spec"])) for y, m in built]]
-        td.broadcast_object_list(payload, src=0)
-        from repair.forest import DeviceModel
-        tile_col = {c.name: i for i, c in enumerate(table.columns)}
-        dict_sizes = {c.name: c.dict_size for c in table.columns}
-        models = []
-        for y, kind, body in payload[0]:
-            models.append((y, ("const", body) if kind == "const" else
-                           ("forest", DeviceModel(body, tile_col, dict_sizes, {}, device), {"spec": body})))
+    models = build_models(rm, engine, table, res, continuous)
     torch.cuda.synchronize()
     t_train = time.time() - t_train
     n_trees = sum(m[1].n_trees for _, m in models if m[0] == "forest")
@@ -406,15 +586,9 @@ def b200_arm(args):
     stats = {}
     res_cells = {}
 
-    def step(e2e):
+    def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        if e2e:
-            # this step's bytes cross PCIe on the stager's copy stream (started during the previous
-            # step -- or right now for the very first one) and are widened into the resident table here;
-            # the next step's copy is started so that it overlaps this step's compute
-            stager.next_batch(host)
-            stager.prefetch(host)
         engine.mark("step:begin")
         engine.reset()
         r = engine.detect(specs, [], 80, err_opts)
@@ -437,16 +611,17 @@ def b200_arm(args):
             dist.td.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e, steps, warmup):
+    def timed(steps, warmup):
         for _ in range(warmup):
-            step(e2e)
+            step()
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
             time.sleep(0.3)  # let nvidia-smi finish initialising before the timed region starts
         barrier()
         l0 = engine.ctx.launch_count
-        evs = [step(e2e) for _ in range(steps)]
+        x0 = dist.n_exchanges if dist is not None else 0
+        evs = [step() for _ in range(steps)]
         barrier()
         clocks = sampler.stop() if sampler else None
         tot = evs[0][0].elapsed_time(evs[-1][2]) / steps   # whole span: gaps between steps count too
@@ -454,25 +629,26 @@ def b200_arm(args):
         t = torch.tensor([tot, det], dtype=torch.float64, device=device)
         if dist is not None:
             dist.max_(t)
-        return float(t[0]), float(t[1]), (engine.ctx.launch_count - l0), clocks
+        xs = ((dist.n_exchanges - x0) / steps) if dist is not None else 0
+        return float(t[0]), float(t[1]), (engine.ctx.launch_count - l0), clocks, xs
 
-    ms, ms_det, launches, clocks = timed(False, args.steps, args.warmup)
+    ms, ms_det, launches, clocks, exchanges = timed(args.steps, args.warmup)
     cells = torch.tensor([stats["cells"], stats["out_rows"]], dtype=torch.int64, device=device)
     if dist is not None:
         dist.sum_(cells)
-    total_rows = n * world
     line = {
         "metric": METRIC, "value": total_rows / (ms / 1e3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32 codes / f64 margins", "data": "synthetic",
-        "config": {"workload": "C4 synthetic {} rows x {} cols per GPU ({} rows total), 1% NULLs + 4 FD denial "
-                               "constraints, NULL + Constraint detectors, pairwise_freq_ratio_threshold=1.0, "
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "int32 codes / f64 margins", "data": "synthetic",
+        "config": {"workload": "C4 synthetic {} rows x {} cols in total, {} rows per GPU ({} scaling), 1% NULLs + 4 FD "
+                               "denial constraints, NULL + Constraint detectors, pairwise_freq_ratio_threshold=1.0, "
                                "{} frozen repair models ({} trees: 300 rounds x classes, {}), "
                                "inputs > L2 (no flush needed)".format(
-                                   n, k, total_rows, len(models), n_trees,
+                                   total_rows, k, n, args.scaling, len(models), n_trees,
                                    "trained by dr_gbdt_train on 10k-row samples" if args.forests == "trained"
                                    else "random-init"),
-                   "rows_per_gpu": n, "cols": k, "parallelism": "rows sharded x{}".format(world)},
+                   "rows_total": total_rows, "rows_per_gpu": n, "cols": k,
+                   "parallelism": "rows sharded x{}".format(world)},
         "rows_scanned_per_sec": total_rows / (ms_det / 1e3),
         "cells_repaired_per_sec": int(cells[0]) / max((ms - ms_det) / 1e3, 1e-9),
         "error_cells": int(cells[0]), "repaired_cells_emitted": int(cells[1]),
@@ -480,6 +656,9 @@ def b200_arm(args):
         "gpu_launches": launches, "clocks": clocks,
         "model_training_s": t_train, "forests": args.forests,
     }
+    line["numa"] = numa
+    if dist is not None:
+        line["exchanges_per_step"] = exchanges
 
     # ---- self-check of the last timed step (untimed) -------------------------------------------
     if not args.no_verify:
@@ -501,7 +680,7 @@ def b200_arm(args):
 
     # ---- per-kernel timing (CUDA events on the launching stream) and rooflines ------------------
     engine.ctx.profile = []
-    step(False)
+    step()
     prof = profile_summary(engine.ctx)
     engine.ctx.profile = None
     peaks = {}
@@ -591,23 +770,91 @@ def b200_arm(args):
             print(kname, v, file=sys.stderr)
     if args.trace:
         engine.trace = []
-        step(False)
+        step()
         if rank == 0:
             for label, dt_s in engine.trace:
                 print("trace %-24s %8.2f ms" % (label, dt_s * 1e3), file=sys.stderr)
         engine.trace = None
 
-    # ---- end to end: host buffers in, host frame out, every step --------------------------------
-    if host is not None:
-        e_ms, _, _, _ = timed(True, max(1, min(args.steps, 3)), 1)
+    # ---- end to end THROUGH THE PUBLIC API: host Arrow table in, host Arrow frame out, every step ----------
+    if not args.no_e2e:
+        r_last, out_last = stats["last"]
+        out_resident = [(a, np.array(x), np.array(c), np.array(rp)) for a, x, c, rp in out_last]
+        arrow_tbl = host_arrow_shard(engine.ctx, codes_dev, n, lo, names, spec.dom)
+        h2d = sum(c.nbytes for c in arrow_tbl.columns)   # indices + validity bits + row ids (dictionaries are tiny)
+        last = {}
+
+        def api_step():
+            m = RepairModel().setArrowInput(arrow_tbl).setRowId("tid").setErrorDetectors(api_detectors(k)) \
+                .setFrozenModels(models)
+            for kk, vv in OPTS.items():
+                m.option(kk, vv)
+            m.device_index = local
+            if args.forests == "random":
+                m.model_provider = rm.model_provider
+            if dist is not None:
+                m.setDistributed(True, local)
+            t0 = time.perf_counter()
+            frame = m.run()
+            last.update({"frame": frame, "rm": m, "wall": time.perf_counter() - t0})
+            return frame
+
+        api_step()                       # warm-up: allocator pools, the pinned chunk ring, page faults
+        e_steps = max(1, min(args.steps, 3))
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        parts = {"ingest_s": 0.0, "egress_s": 0.0, "ingest_copy_s": 0.0, "ingest_encode_s": 0.0}
+        for _ in range(e_steps):
+            api_step()
+            lr = last["rm"].last_run
+            parts["ingest_s"] += lr.get("ingest_total_s", 0.0)
+            parts["ingest_copy_s"] += lr.get("ingest_copy_s", 0.0)
+            parts["ingest_encode_s"] += lr.get("ingest_encode_s", 0.0)
+            parts["egress_s"] += lr.get("egress_s", 0.0)
+        ev1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        t = torch.tensor([ev0.elapsed_time(ev1) / e_steps, wall_ms] + [v / e_steps for v in parts.values()],
+                         dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.max_(t)
+        e_ms = float(t[0])
+        frame = last["frame"]
+        d2h = sum(c.nbytes for c in frame.columns)
+        same = frames_equal(frame, out_resident, lo, names, table)
+        flag = torch.tensor([0 if same else 1], dtype=torch.int64, device=device)
+        if dist is not None:
+            dist.sum_(flag)
         line["e2e"] = {"value": total_rows / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
-                       "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(stats["d2h"]),
-                       "note": "every step copies its byte codes from pinned host memory (copy stream, double "
-                               "buffered: the copy of step i+1 overlaps the compute of step i) and reads its "
-                               "result frame back; whole-span device time / steps"}
+                       "wall_ms_per_step": float(t[1]), "steps": e_steps,
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ingest_s": float(t[2]), "egress_s": float(t[3]),
+                       "ingest_copy_s": float(t[4]), "ingest_encode_s": float(t[5]),
+                       "frame_rows": int(frame.num_rows), "frame_equals_resident_pass": int(flag[0]) == 0,
+                       "call": "RepairModel().setArrowInput(pyarrow.Table in pageable host memory).setRowId('tid')"
+                               ".setErrorDetectors([NullErrorDetector(), ConstraintErrorDetector(..)])"
+                               ".setFrozenModels(models).run() -> pyarrow.Table (tid, attribute, current_value, "
+                               "repaired); CUDA events around the calls, max over ranks",
+                       "note": "ingest = Arrow dictionary indices (int8) + validity bits + int64 row ids through the "
+                               "pinned chunk ring (dr_h2d_copy), dictionaries re-encoded on the device; egress = row "
+                               "ids gathered on the device, dictionary indices + validity bits copied back and "
+                               "wrapped as Arrow arrays; models frozen (training is not part of the step)"}
+        del arrow_tbl, frame
+        last.clear()
+
+    # ---- the other BASELINE configs: wall clock through the public API (untimed setup excluded) ------------
+    want = [] if args.configs == "none" else (["c2", "c3", "c5"] if args.configs == "auto" else
+                                              [c.strip() for c in args.configs.split(",") if c.strip()])
+    if args.configs == "auto" and (world != 1 or args.rows != 100_000_000):
+        want = []
+    if want and rank == 0:
+        line["other_configs"] = other_configs(want, local)
 
     # ---- CPU baseline (rank 0, single GPU run only) -----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        restore_affinity()   # the CPU leg gets every host core
         run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)  # untimed: builds the frozen forests
         t_full, rows, ncells, t_det, threads, _ = run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)
         line["cpu_baseline"] = {"value": rows / t_full, "unit": "rows/s", "cores": threads, "kind": "port",

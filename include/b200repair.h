@@ -53,6 +53,37 @@ int64_t dr_launch_count(const dr_ctx* ctx);
  * widened to the int32 table layout here (4x less PCIe traffic than int32 codes). */
 int dr_widen_u8(dr_ctx* ctx, const uint8_t* src, int64_t n, int32_t* dst, void* stream);
 
+/* Arrow ingest (replaces `spark_df.toPandas()` / the view hand-off of model.py:477-480 with the raw Arrow
+ * buffers of the collected table; nothing is re-encoded on the host).
+ *
+ * dr_h2d_copy / dr_d2h_copy: PAGEABLE host memory <-> device through a ring of pinned 4 MB chunks fed by
+ * `n_threads` worker threads (<= 0: a default), each on its own copy stream.  Both calls block until
+ * every byte has arrived; `stream` is synchronised first (its earlier work may still use the buffers).
+ *
+ * dr_index_presence: `used` (device uint32[ceil(dict_size/32)], caller zeroes) gets bit v set iff some
+ * valid row holds dictionary index v.  idx: device array of `width`-byte signed integers (1, 2 or 4:
+ * Arrow int8 / int16 / int32 dictionary indices); validity: device copy of the Arrow validity bitmap
+ * (bit (bit_offset + i) = row i is not NULL) or NULL when the column has no NULLs.
+ * dr_index_remap: dst[i] = lut[idx[i]] (device int32[dict_size], -1 for entries to drop), -1 for NULL
+ * rows and indices outside [0, dict_size).
+ *
+ * dr_ids_unique_i64: RepairApi.checkInputTable's uniqueness gate (RepairApi.scala:53-62) on the device:
+ * one pass when the ids are strictly increasing, else a radix sort + adjacent compare (allocates
+ * 2 * 8 * n bytes for its duration).  *out_unique = 1 / 0.  Synchronises `stream`.
+ * dr_gather_i64: out[i] = col[rows[i]] (row ids of the output cells).
+ * dr_valid_bits: Arrow validity bitmap of a code array, bit i = codes[i] >= 0 (uint32 words). */
+int dr_h2d_copy(dr_ctx* ctx, const void* const* src_host, void* const* dst_dev, const int64_t* bytes, int n_bufs,
+                int n_threads, void* stream);
+int dr_d2h_copy(dr_ctx* ctx, const void* const* src_dev, void* const* dst_host, const int64_t* bytes, int n_bufs,
+                int n_threads, void* stream);
+int dr_index_presence(dr_ctx* ctx, const void* idx, int width, const uint8_t* validity, int64_t bit_offset,
+                      int64_t n_rows, int32_t dict_size, uint32_t* used, void* stream);
+int dr_index_remap(dr_ctx* ctx, const void* idx, int width, const uint8_t* validity, int64_t bit_offset,
+                   int64_t n_rows, const int32_t* lut, int32_t dict_size, int32_t* dst, void* stream);
+int dr_ids_unique_i64(dr_ctx* ctx, const int64_t* ids, int64_t n, int* out_unique, void* stream);
+int dr_gather_i64(dr_ctx* ctx, const int64_t* col, const int32_t* rows, int64_t n, int64_t* out, void* stream);
+int dr_valid_bits(dr_ctx* ctx, const int32_t* codes, int64_t n, uint32_t* bits, void* stream);
+
 /* ---- a2 + a7/a8: NULL scan fused with per-column histograms ------------------------------------
  * Replaces ErrorDetectorApi.detectNullCells (ErrorDetectorApi.scala:30-34,128-157: K_t UNION-ALL
  * scans) and the single-attribute GROUPING SETS of RepairApi.computeFreqStats

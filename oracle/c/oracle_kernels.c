@@ -26,6 +26,15 @@ int o_num_threads(void) {
 #endif
 }
 
+/* bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs ask for the host's cores */
+void o_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* cols: K pointers to int32[n]; hist: int64[sum(dom+1)], slot 0 = NULL */
 void o_scan_hist(const int32_t* const* cols, const int32_t* dom, int k, int64_t n, int64_t* hist) {
     int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (k + 1));

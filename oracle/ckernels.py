@@ -28,6 +28,17 @@ def num_threads():
     return int(lib().o_num_threads())
 
 
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun
+    exports OMP_NUM_THREADS=1 to every rank).  -> the thread count now in force."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().o_set_num_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def _pp(arrays):
     arr = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
     return arr

@@ -57,6 +57,14 @@ _SIGNATURES = {
     "dr_abi_version": (c_int, []),
     "dr_launch_count": (c_int64, [c_void_p]),
     "dr_widen_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_h2d_copy": (c_int, [c_void_p, _PP, _PP, POINTER(c_int64), c_int, c_int, c_void_p]),
+    "dr_d2h_copy": (c_int, [c_void_p, _PP, _PP, POINTER(c_int64), c_int, c_int, c_void_p]),
+    "dr_index_presence": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "dr_index_remap": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int32,
+                               c_void_p, c_void_p]),
+    "dr_ids_unique_i64": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int), c_void_p]),
+    "dr_gather_i64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dr_valid_bits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_scan_hist": (c_int, [c_void_p, _PP, POINTER(c_int32), c_int, c_int64, _PP, c_void_p, c_void_p]),
     "dr_lut_scan": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "dr_quartiles": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double), POINTER(c_int64), c_void_p]),
@@ -211,6 +219,37 @@ class Context:
 
     def widen_u8(self, src, n, dst):
         self._check(self.lib.dr_widen_u8(self._h, _dp(src), n, _dp(dst), self._stream()))
+
+    # ---- Arrow ingest / egress ---------------------------------------------------------------------
+    def h2d_copy(self, host_ptrs, dev_tensors_or_ptrs, nbytes, threads=0):
+        """Pageable host buffers (addresses) -> device (tensors or addresses); blocks until complete."""
+        sp, _k1 = _ptr_array(host_ptrs)
+        dp, _k2 = _ptr_array([d if isinstance(d, int) else d.data_ptr() for d in dev_tensors_or_ptrs])
+        self._check(self.lib.dr_h2d_copy(self._h, sp, dp, _i64_array(nbytes), len(host_ptrs), threads, self._stream()))
+
+    def d2h_copy(self, dev_tensors_or_ptrs, host_ptrs, nbytes, threads=0):
+        sp, _k1 = _ptr_array([d if isinstance(d, int) else d.data_ptr() for d in dev_tensors_or_ptrs])
+        dp, _k2 = _ptr_array(host_ptrs)
+        self._check(self.lib.dr_d2h_copy(self._h, sp, dp, _i64_array(nbytes), len(host_ptrs), threads, self._stream()))
+
+    def index_presence(self, idx_ptr, width, validity_ptr, bit_offset, n_rows, dict_size, used):
+        self._check(self.lib.dr_index_presence(self._h, c_void_p(idx_ptr), width, c_void_p(validity_ptr or 0),
+                                               bit_offset, n_rows, dict_size, _dp(used), self._stream()))
+
+    def index_remap(self, idx_ptr, width, validity_ptr, bit_offset, n_rows, lut_ptr, dict_size, dst_ptr):
+        self._check(self.lib.dr_index_remap(self._h, c_void_p(idx_ptr), width, c_void_p(validity_ptr or 0), bit_offset,
+                                            n_rows, c_void_p(lut_ptr), dict_size, c_void_p(dst_ptr), self._stream()))
+
+    def ids_unique(self, ids, n):
+        out = c_int()
+        self._check(self.lib.dr_ids_unique_i64(self._h, _dp(ids), n, byref(out), self._stream()))
+        return bool(out.value)
+
+    def gather_i64(self, col, rows, n, out):
+        self._check(self.lib.dr_gather_i64(self._h, _dp(col), _dp(rows), n, _dp(out), self._stream()))
+
+    def valid_bits(self, codes, n, bits):
+        self._check(self.lib.dr_valid_bits(self._h, _dp(codes), n, _dp(bits), self._stream()))
 
     # ---- detectors -------------------------------------------------------------------------------
     def scan_hist(self, cols, dom, n_rows, bitmaps, hist):
@@ -443,7 +482,8 @@ def _profiled(name, fn):
     return wrapper
 
 
-for _name in ("widen_u8", "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
+for _name in ("widen_u8", "h2d_copy", "d2h_copy", "index_presence", "index_remap", "ids_unique", "gather_i64", "valid_bits",
+              "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "cooc_skip", "key_presence", "key_flag", "dc_exists", "combine_counts", "dc_lt_flag",
               "dc_hash_build", "dc_hash_flag", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",

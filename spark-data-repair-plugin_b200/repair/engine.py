@@ -130,10 +130,10 @@ class DetectResult:
 
 
 class Engine:
-    def __init__(self, table, device_index=0, dist=None, device_table=None):
+    def __init__(self, table, device_index=0, dist=None, device_table=None, ctx=None):
         import torch
         self.torch = torch
-        self.ctx = Context(device_index)
+        self.ctx = ctx if ctx is not None else Context(device_index)
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
         self.table = table

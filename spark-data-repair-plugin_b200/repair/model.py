@@ -53,9 +53,21 @@ def _as_encoded(obj, row_id, name="input"):
         return obj
     if _is_spark_df(obj):
         obj = obj.toPandas()
-    if type(obj).__module__.startswith("pyarrow") and hasattr(obj, "schema"):
+    if _is_arrow_table(obj):
         return EncodedTable.from_arrow(obj, row_id, name)
     return EncodedTable.from_pandas(obj, row_id, name)
+
+
+def _is_arrow_table(obj):
+    return type(obj).__module__.startswith("pyarrow") and hasattr(obj, "schema")
+
+
+def _maybe_arrow(frame, arrow_io):
+    """Arrow in -> Arrow out (modes whose frame is assembled with pandas are converted at the end)."""
+    if not arrow_io or _is_arrow_table(frame):
+        return frame
+    import pyarrow as pa
+    return pa.Table.from_pandas(frame, preserve_index=False)
 
 
 def select_features(pairwise_stats, y, features, max_training_column_num):
@@ -95,6 +107,7 @@ class RepairModel():
         self.model_provider = None   # callable(ctx) -> model spec; default: _fit (GPU GBDT / scikit-learn)
         self.trainer = "gpu"         # "gpu": dr_gbdt_train when eligible; "sklearn": always train.build_model
         self.distributed = None      # torch.distributed process group (or True = default group): row-sharded run
+        self.frozen_models = None    # models of an earlier run() (setFrozenModels): skips the training phase
         self.last_run: Dict[str, Any] = {}
 
     # ---- setters (same names / checks / messages as the reference) -------------------------------
@@ -129,6 +142,13 @@ class RepairModel():
             raise TypeError("`table` should be provided as pyarrow.Table, got {}".format(type(table).__name__))
         self.db_name = ""
         self.input = table
+        return self
+
+    def setFrozenModels(self, models: Any) -> "RepairModel":
+        """Reuse the repair models an earlier ``run()`` trained (``model.last_run["models"]``) instead of
+        training again: inference-only passes over new batches of the same table (same columns and
+        dictionaries).  The reference retrains on every run (model.py:1001-1052); not part of its API."""
+        self.frozen_models = models
         return self
 
     def setEncodedInput(self, table: EncodedTable) -> "RepairModel":
@@ -285,7 +305,27 @@ class RepairModel():
             maximal_likelihood_repair = True
 
         t0 = time.time()
-        table, input_name = self._resolve_input()
+        from ._native import Context
+        from .engine import Dist, Engine
+        ctx = dt = table = None
+        ingest: Dict[str, Any] = {}
+        arrow_io = _is_arrow_table(self.input)
+        if arrow_io:
+            # raw Arrow buffers -> device, encoded there (no per-row host work); None = needs the host path
+            import torch
+            ctx = Context(self.device_index)
+            try:
+                got = EncodedTable.from_arrow_device(self.input, str(self.row_id), ctx,
+                                                     torch.device("cuda", self.device_index), timings=ingest)
+            except Exception:
+                ctx.close()
+                raise
+            if got is not None:
+                table, dt = got
+                input_name = "input"
+        if table is None:
+            table, input_name = self._resolve_input()
+        ingest.setdefault("ingest_total_s", time.time() - t0)
         continuous = table.continuous_attrs
         _logger.info("input_table: {} ({} rows x {} columns)".format(input_name, table.n_rows, len(table.columns)))
         if maximal_likelihood_repair and len(continuous) != 0:
@@ -303,33 +343,42 @@ class RepairModel():
         for key in _MODEL_OPT:
             self._opt(key)
 
-        from .engine import Dist, Engine
         dist = None
         if self.distributed is not None and self.distributed is not False:
             dist = Dist(None if self.distributed is True else self.distributed)
-            table = table.unify(dist)
-        engine = Engine(table, self.device_index, dist=dist)
+            table = table.unify(dist, dt, ctx)
+        engine = Engine(table, self.device_index, dist=dist, device_table=dt, ctx=ctx)
         try:
             detectors = self.error_detectors or default_detectors(self.targets, table.names)
             _logger.info("[Error Detection Phase] Used error detectors: {}".format(to_list_str(detectors)))
             res = engine.detect([d.spec() for d in detectors], self.targets, self.discrete_thres, err_opts,
                                 self._given_cells(table))
             self.last_run = {"detect": res, "elapsed_detect": time.time() - t0}
+            self.last_run.update(ingest)
             if detect_errors_only:
-                return self._cells_frame(engine, table, res)
+                return _maybe_arrow(self._cells_frame(engine, table, res), arrow_io)
             if sum((res.n_cells_global or res.n_cells).values()) == 0:
                 _logger.info("Any error cell not found, so the input data is already clean")
-                return self._input_frame(table) if repair_data else self._empty_frame(table, repaired=True)
+                return _maybe_arrow(self._input_frame(table) if repair_data else
+                                    self._empty_frame(table, repaired=True), arrow_io)
             if len(res.target_columns) == 0:
                 raise ValueError("At least one valid discretizable feature is needed to repair error cells, "
                                  "but no such feature found")
             if compute_repair_candidate_prob or maximal_likelihood_repair:
                 out = self._run_pmf_modes(engine, table, res, continuous, compute_repair_prob, compute_repair_score,
                                           repair_data, maximal_likelihood_repair)
+            elif arrow_io and not repair_data and not self.repair_by_rules and not engine.dt.cont_index:
+                # Arrow in, Arrow out: the frame is assembled from device-side arrays, no Python object per cell
+                t1 = time.time()
+                models = self.frozen_models if self.frozen_models is not None else \
+                    build_models(self, engine, table, res, continuous)
+                self.last_run["models"] = models
+                self.last_run["elapsed_training"] = time.time() - t1
+                out = repair_cells_encoded(self, engine, table, res, models, arrow=True)
             else:
-                out = repair_cells(self, engine, table, res, continuous, repair_data)
+                out = repair_cells(self, engine, table, res, continuous, repair_data, models=self.frozen_models)
             _logger.info("!!!Total Processing time is {}(s)!!!".format(time.time() - t0))
-            return out
+            return _maybe_arrow(out, arrow_io)
         finally:
             self.last_run["gpu_launches"] = engine.ctx.launch_count
             engine.close()
@@ -665,10 +714,73 @@ def _repair_cells_pmf(rm, engine, table, res, continuous):
     return out
 
 
-def repair_cells_encoded(rm, engine, table, res, models):
+def _arrow_cells_frame(engine, table, seg, idx, n_keep, rows_all, cur_all, rep_all):
+    """The filtered (row id, attribute, current_value, repaired) frame as a ``pyarrow.Table`` built from
+    device-side arrays: row ids gathered on the device, dictionary indices + Arrow validity bits copied
+    into fresh host buffers (dr_d2h_copy) that the Arrow arrays wrap without another copy; string
+    columns are dictionary arrays over the column dictionaries (one chunk per attribute)."""
+    import pyarrow as pa
+    torch = engine.torch
+    dev = engine.device
+    m = max(n_keep, 1)
+    words = (m + 31) // 32
+    rows_k = torch.empty(m, dtype=torch.int32, device=dev)
+    codes_k = torch.empty((2, m), dtype=torch.int32, device=dev)
+    bits_k = torch.zeros((2, words), dtype=torch.int32, device=dev)
+    ids_k = None
+    if n_keep:
+        engine.ctx.gather(rows_all, idx, n_keep, rows_k)
+        engine.ctx.gather(cur_all, idx, n_keep, codes_k[0])
+        engine.ctx.gather(rep_all, idx, n_keep, codes_k[1])
+        engine.ctx.valid_bits(codes_k[0], n_keep, bits_k[0])
+        engine.ctx.valid_bits(codes_k[1], n_keep, bits_k[1])
+        if engine.dt.ids is not None:
+            ids_k = torch.empty(m, dtype=torch.int64, device=dev)
+            engine.ctx.gather_i64(engine.dt.ids, rows_k, n_keep, ids_k)
+    # where each attribute's cells start among the kept ones
+    starts = torch.tensor([o for _, o, _ in seg] + [sum(n for _, _, n in seg)], dtype=torch.int32, device=dev)
+    bounds = torch.searchsorted(idx[:n_keep].contiguous(), starts).cpu().numpy() if n_keep else \
+        np.zeros(len(seg) + 1, dtype=np.int64)
+    h_codes = np.empty((2, m), dtype=np.int32)
+    h_bits = np.empty((2, words), dtype=np.uint32)
+    src, dst, size = [codes_k, bits_k], [h_codes.ctypes.data, h_bits.ctypes.data], [h_codes.nbytes, h_bits.nbytes]
+    if ids_k is not None:
+        h_ids = np.empty(m, dtype=np.int64)
+        src.append(ids_k); dst.append(h_ids.ctypes.data); size.append(h_ids.nbytes)
+    else:
+        h_rows = np.empty(m, dtype=np.int32)
+        src.append(rows_k); dst.append(h_rows.ctypes.data); size.append(h_rows.nbytes)
+    engine.ctx.d2h_copy(src, dst, size)
+    if ids_k is None:
+        h_ids = np.asarray(table.row_ids)[h_rows[:n_keep].astype(np.int64)]
+    ids = pa.array(h_ids[:n_keep])
+    big = [pa.Array.from_buffers(pa.int32(), n_keep, [pa.py_buffer(h_bits[j]), pa.py_buffer(h_codes[j])])
+           for j in range(2)]
+    names = pa.array([a for a, _, _ in seg], type=pa.string())
+    attr, cur, rep = [], [], []
+    for i, ((a, _, _), lo, hi) in enumerate(zip(seg, bounds[:-1], bounds[1:])):
+        lo, hi = int(lo), int(hi)
+        if hi == lo:
+            continue
+        strs = pa.array(table.by_name[a].strings(), type=pa.string())
+        attr.append(pa.DictionaryArray.from_arrays(pa.array(np.full(hi - lo, i, dtype=np.int32)), names, safe=False))
+        cur.append(pa.DictionaryArray.from_arrays(big[0].slice(lo, hi - lo), strs, safe=False))
+        rep.append(pa.DictionaryArray.from_arrays(big[1].slice(lo, hi - lo), strs, safe=False))
+    if not cur:
+        empty = pa.array([], type=pa.string())
+        return pa.table({table.row_id: ids, "attribute": empty, "current_value": empty, "repaired": empty})
+    # (one chunk per attribute in every column: chunk layouts must agree)
+    offs = [0] + [int(b) for b in np.cumsum([len(c) for c in cur])]
+    id_chunks = [ids.slice(lo, hi - lo) for lo, hi in zip(offs[:-1], offs[1:])]
+    return pa.table({table.row_id: pa.chunked_array(id_chunks), "attribute": pa.chunked_array(attr),
+                     "current_value": pa.chunked_array(cur), "repaired": pa.chunked_array(rep)})
+
+
+def repair_cells_encoded(rm, engine, table, res, models, arrow=False):
     """Default-mode repair of an all-discrete table with frozen models, everything device-side:
     -> [(attr, row positions int32, current codes, repaired codes)] already filtered like
-    model.py:1401.  One D2H of the result at the end (pinned), no per-attribute host round trips."""
+    model.py:1401.  One D2H of the result at the end (pinned), no per-attribute host round trips.
+    arrow: -> the same frame as a ``pyarrow.Table`` (_arrow_cells_frame)."""
     torch = engine.torch
     targets = res.target_columns
     K = len(table.columns)
@@ -678,6 +790,9 @@ def repair_cells_encoded(rm, engine, table, res, models):
     rm.last_run["n_error_cells"] = E
     if E == 0:
         rm.last_run["n_dirty_rows"] = 0
+        if arrow:
+            import pyarrow as pa
+            return pa.Table.from_pandas(rm._empty_frame(table, repaired=True), preserve_index=False)
         return []
     engine.mark("repair:start")
     rows_all = torch.empty(E, dtype=torch.int32, device=engine.device)
@@ -710,6 +825,12 @@ def repair_cells_encoded(rm, engine, table, res, models):
     engine.ctx.changed_bitmap(cur_all, rep_all, E, keep)
     idx = engine.bitmap_rows(keep, E)
     n_keep = int(idx.numel())
+    if arrow:
+        t_e = time.time()
+        frame = _arrow_cells_frame(engine, table, seg, idx, n_keep, rows_all, cur_all, rep_all)
+        rm.last_run["egress_s"] = time.time() - t_e
+        rm.last_run["n_out_cells"] = n_keep
+        return frame
     host = engine.pinned_i32(4 * max(n_keep, 1)).view(4, max(n_keep, 1))  # reused across runs
     packed = torch.empty((4, max(n_keep, 1)), dtype=torch.int32, device=engine.device)
     if n_keep:

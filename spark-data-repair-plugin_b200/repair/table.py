@@ -17,7 +17,18 @@ class Column:
     ``codes``: int32 index into it, -1 = NULL;  ``values``: float64 (NaN = NULL) for numerics."""
 
     def __init__(self, name, kind, dictionary, codes, values=None):
-        self.name, self.kind, self.dictionary, self.codes, self.values = name, kind, dictionary, codes, values
+        self.name, self.kind, self.dictionary, self.values = name, kind, dictionary, values
+        self._codes = codes      # host int32 array, or a callable that fetches it (device-resident ingest)
+
+    @property
+    def codes(self):
+        if callable(self._codes):
+            self._codes = self._codes()
+        return self._codes
+
+    @codes.setter
+    def codes(self, v):
+        self._codes = v
 
     @property
     def dict_size(self):
@@ -87,17 +98,77 @@ def _encode_strings(name, series):
     return Column(name, "str", uniq, codes, None)
 
 
+def _arrow_gate(tbl, row_id, name):
+    """checkInputTable's schema gate (RepairApi.scala:34-52) on a pyarrow schema -> {column: kind}."""
+    import pyarrow as pa
+    if row_id not in tbl.column_names:
+        raise AnalysisException("Column '{}' does not exist in table '{}'".format(row_id, name))
+    kinds, bad = {}, []
+    for f in tbl.schema:
+        t = f.type.value_type if pa.types.is_dictionary(f.type) else f.type
+        if pa.types.is_boolean(t):
+            bad.append("boolean")
+        elif pa.types.is_integer(t):
+            kinds[f.name] = "int"
+        elif pa.types.is_floating(t):
+            kinds[f.name] = "float"
+        elif pa.types.is_string(t) or pa.types.is_large_string(t):
+            kinds[f.name] = "str"
+        elif pa.types.is_timestamp(t):
+            bad.append("timestamp")
+        elif pa.types.is_date(t):
+            bad.append("date")
+        else:
+            bad.append(str(t))
+    if bad:
+        raise AnalysisException("Supported types are {}, but unsupported ones found: {}".format(
+            _SUPPORTED_MSG, ",".join(bad)))
+    if not tbl.num_columns >= 3:
+        raise AnalysisException("A least three columns (`{}` columns + two more ones) in table '{}'".format(
+            row_id, name))
+    return kinds
+
+
+def _sorted_dictionary(entries, used):
+    """Arrow dictionary entries + which of them occur -> (sorted dictionary of the occurring non-null
+    entries as str objects, int32 LUT old index -> code in it or -1)."""
+    used = np.asarray(used, dtype=bool) & np.array([e is not None for e in entries], dtype=bool) \
+        if len(entries) else np.zeros(0, dtype=bool)
+    keep = np.nonzero(used)[0]
+    strs = [str(entries[i]) for i in keep]
+    order = keep[np.argsort(np.array(strs, dtype=object), kind="stable")] if len(keep) else keep
+    # two dictionary entries may print alike (never for strings; kept for safety): first one wins the code
+    uniq, lut = [], np.full(len(entries), -1, dtype=np.int32)
+    for i in order:
+        v = str(entries[i])
+        if not uniq or uniq[-1] != v:
+            uniq.append(v)
+        lut[i] = len(uniq) - 1
+    return np.array(uniq, dtype=object), lut
+
+
 class EncodedTable:
     """The collected input: row ids + encoded columns (row id excluded)."""
 
-    def __init__(self, row_id, row_ids, row_id_kind, columns, name="input"):
-        self.row_id, self.row_ids, self.row_id_kind = row_id, row_ids, row_id_kind
+    def __init__(self, row_id, row_ids, row_id_kind, columns, name="input", n_rows=None):
+        self.row_id, self._row_ids, self.row_id_kind = row_id, row_ids, row_id_kind
         self.columns = list(columns)
         self.name = name
-        self.n_rows = len(row_ids)
+        self.n_rows = len(row_ids) if n_rows is None else int(n_rows)
         self.by_name = {c.name: c for c in self.columns}
         self.row_offset = 0      # first global row of this shard
         self.n_rows_global = self.n_rows
+
+    @property
+    def row_ids(self):
+        """Host array of the row ids (a device-resident ingest only materialises it when asked)."""
+        if callable(self._row_ids):
+            self._row_ids = self._row_ids()
+        return self._row_ids
+
+    @row_ids.setter
+    def row_ids(self, v):
+        self._row_ids = v
 
     @property
     def names(self):
@@ -169,31 +240,7 @@ class EncodedTable:
         dictionaries (one entry per distinct value) are sorted and turned into Python strings."""
         import pyarrow as pa
         import pyarrow.compute as pc
-        if row_id not in tbl.column_names:
-            raise AnalysisException("Column '{}' does not exist in table '{}'".format(row_id, name))
-        kinds, bad = {}, []
-        for f in tbl.schema:
-            t = f.type.value_type if pa.types.is_dictionary(f.type) else f.type
-            if pa.types.is_boolean(t):
-                bad.append("boolean")
-            elif pa.types.is_integer(t):
-                kinds[f.name] = "int"
-            elif pa.types.is_floating(t):
-                kinds[f.name] = "float"
-            elif pa.types.is_string(t) or pa.types.is_large_string(t):
-                kinds[f.name] = "str"
-            elif pa.types.is_timestamp(t):
-                bad.append("timestamp")
-            elif pa.types.is_date(t):
-                bad.append("date")
-            else:
-                bad.append(str(t))
-        if bad:
-            raise AnalysisException("Supported types are {}, but unsupported ones found: {}".format(
-                _SUPPORTED_MSG, ",".join(bad)))
-        if not tbl.num_columns >= 3:
-            raise AnalysisException("A least three columns (`{}` columns + two more ones) in table '{}'".format(
-                row_id, name))
+        kinds = _arrow_gate(tbl, row_id, name)
         n_distinct = int(pc.count_distinct(tbl[row_id], mode="all").as_py())
         if n_distinct != tbl.num_rows:
             raise AnalysisException(
@@ -239,6 +286,151 @@ class EncodedTable:
         return cls(row_id, np.asarray(ids.to_numpy(zero_copy_only=False)), kinds[row_id], cols, name)
 
     @classmethod
+    def from_arrow_device(cls, tbl, row_id, ctx, device, name="input", threads=0, timings=None):
+        """Device-side ingest of an all-discrete ``pyarrow.Table``: the raw Arrow buffers (dictionary
+        indices as int8 / int16 / int32, validity bits, int64 row ids) cross PCIe as they are
+        (``dr_h2d_copy``: pageable memory through a pinned chunk ring, several threads), the device finds
+        the dictionary entries that occur (``dr_index_presence``), the host sorts the dictionaries (one
+        entry per distinct value) and the device rewrites the indices as int32 codes of the sorted
+        dictionaries (``dr_index_remap``).  Row-id uniqueness is checked on the device too.  No per-row
+        work on the host, no host copy of the codes (``Column.codes`` fetches them on demand).
+        -> (EncodedTable, DeviceTable), or None when the table needs the host path of ``from_arrow``
+        (numeric attributes, row ids that are not NULL-free integers, an empty table)."""
+        import time
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        import torch
+        kinds = _arrow_gate(tbl, row_id, name)
+        attrs = [f.name for f in tbl.schema if f.name != row_id]
+        n = tbl.num_rows
+        id_type = tbl.schema.field(row_id).type
+        if n == 0 or any(kinds[a] != "str" for a in attrs) or not pa.types.is_integer(id_type) or \
+                tbl[row_id].null_count != 0:
+            return None
+        t0 = time.perf_counter()
+        # ---- row ids: to the device, uniqueness there ------------------------------------------------
+        ids_col = tbl[row_id] if id_type == pa.int64() else pc.cast(tbl[row_id], pa.int64())
+        ids_dev = torch.empty(n, dtype=torch.int64, device=device)
+        src, dst, size, off = [], [], [], 0
+        for ch in ids_col.chunks:
+            if len(ch):
+                src.append(ch.buffers()[1].address + ch.offset * 8)
+                dst.append(ids_dev.data_ptr() + off * 8)
+                size.append(len(ch) * 8)
+                off += len(ch)
+        ctx.h2d_copy(src, dst, size, threads)
+        if not ctx.ids_unique(ids_dev, n):
+            n_distinct = int(pc.count_distinct(tbl[row_id], mode="all").as_py())
+            raise AnalysisException(
+                "Uniqueness does not hold in column '{}' of table '{}' (# of distinct '{}': {}, # of rows: {})".format(
+                    row_id, name, row_id, n_distinct, n))
+        # ---- attribute columns: what has to travel ---------------------------------------------------
+        plan = []   # per attribute: (entries, width, [(idx address, validity address or 0, bit offset, rows)])
+        for a in attrs:
+            col = tbl[a]
+            if not pa.types.is_dictionary(col.type):
+                col = pc.dictionary_encode(col)          # plain strings: Arrow's C++ hash kernel, on the host
+            if col.num_chunks > 1:
+                col = col.unify_dictionaries()
+            it = col.type.index_type
+            if pa.types.is_unsigned_integer(it) or it.bit_width > 32:
+                col = col.cast(pa.dictionary(pa.int32(), col.type.value_type))
+                it = pa.int32()
+            width = it.bit_width // 8
+            chunks = [ch for ch in col.chunks if len(ch)]
+            entries = chunks[0].dictionary.to_pylist()
+            parts = []
+            for ch in chunks:
+                bufs = ch.indices.buffers()
+                vbuf = ch.buffers()[0] if ch.null_count else None
+                parts.append((ch, bufs[1].address + ch.offset * width,
+                              (vbuf.address + ch.offset // 8) if vbuf is not None else 0, ch.offset % 8, len(ch)))
+            plan.append((entries, width, parts))
+        table_cols = [None] * len(attrs)
+        n_pad = (n + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN or ROW_ALIGN
+        codes = torch.empty((len(attrs), n_pad), dtype=torch.int32, device=device)
+        if n_pad > n:
+            codes[:, n:].fill_(-1)
+        al = lambda b: (b + 255) // 256 * 256
+        budget = 8 << 30   # raw bytes staged on the device at a time
+        g0 = 0
+        t_copy = t_remap = 0.0
+        while g0 < len(attrs):
+            g1, total = g0, 0
+            while g1 < len(attrs):
+                need = sum(al(r * plan[g1][1]) + (al((r + bo + 7) // 8) if va else 0) for _, _, va, bo, r in plan[g1][2])
+                if g1 > g0 and total + need > budget:
+                    break
+                total += need
+                g1 += 1
+            stage = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+            base = stage.data_ptr()
+            src, dst, size, where, pos = [], [], [], {}, 0
+            for i in range(g0, g1):
+                _, width, parts = plan[i]
+                for j, (_, ia, va, bo, r) in enumerate(parts):
+                    src.append(ia); dst.append(base + pos); size.append(r * width)
+                    d_idx = base + pos
+                    pos += al(r * width)
+                    d_val = 0
+                    if va:
+                        nb = (r + bo + 7) // 8
+                        src.append(va); dst.append(base + pos); size.append(nb)
+                        d_val = base + pos
+                        pos += al(nb)
+                    where[(i, j)] = (d_idx, d_val)
+            t1 = time.perf_counter()
+            ctx.h2d_copy(src, dst, size, threads)
+            t_copy += time.perf_counter() - t1
+            t1 = time.perf_counter()
+            # which dictionary entries occur (one small read-back for the whole group)
+            uoff = [0]
+            for i in range(g0, g1):
+                uoff.append(uoff[-1] + (len(plan[i][0]) + 31) // 32)
+            used = torch.zeros(max(uoff[-1], 1), dtype=torch.int32, device=device)
+            for i in range(g0, g1):
+                entries, width, parts = plan[i]
+                if not entries:
+                    continue
+                for j, (_, _, _, bo, r) in enumerate(parts):
+                    d_idx, d_val = where[(i, j)]
+                    ctx.index_presence(d_idx, width, d_val, bo, r, len(entries), used[uoff[i - g0]:])
+            used_h = used.cpu().numpy().view(np.uint32)
+            luts, loff = [], [0]
+            for i in range(g0, g1):
+                entries = plan[i][0]
+                bits = np.unpackbits(used_h[uoff[i - g0]:uoff[i - g0 + 1]].view(np.uint8), bitorder="little")[:len(entries)]
+                dictionary, lut = _sorted_dictionary(entries, bits.astype(bool))
+                luts.append(lut)
+                loff.append(loff[-1] + len(lut))
+                table_cols[i] = Column(attrs[i], "str", dictionary, None, None)
+            d_lut = torch.from_numpy(np.concatenate(luts + [np.zeros(1, dtype=np.int32)])).to(device)
+            for i in range(g0, g1):
+                entries, width, parts = plan[i]
+                row = 0
+                for j, (_, _, _, bo, r) in enumerate(parts):
+                    d_idx, d_val = where[(i, j)]
+                    ctx.index_remap(d_idx, width, d_val, bo, r, d_lut.data_ptr() + 4 * loff[i - g0], len(entries),
+                                    codes[i].data_ptr() + 4 * row)
+                    row += r
+            torch.cuda.current_stream().synchronize()
+            t_remap += time.perf_counter() - t1
+            del stage
+            g0 = g1
+
+        def ids_host():
+            return np.asarray(ids_col.to_numpy(zero_copy_only=False))
+        t = cls(row_id, ids_host, kinds[row_id], table_cols, name, n_rows=n)
+        dt = DeviceTable(t, device, codes=codes)
+        dt.ids = ids_dev
+        for i, c in enumerate(table_cols):
+            c._codes = (lambda i=i: dt.codes[i][:n].cpu().numpy())
+        if timings is not None:
+            timings.update({"ingest_copy_s": t_copy, "ingest_encode_s": t_remap,
+                            "ingest_total_s": time.perf_counter() - t0})
+        return t, dt
+
+    @classmethod
     def from_codes(cls, row_id, names, codes, dict_sizes, name="input", row_ids=None, dictionaries=None):
         """Pre-encoded discrete table (already label-encoded upstream, e.g. Arrow dictionary pages
         or the synthetic generator): ``codes[k]`` int32, -1 = NULL; value c of column k prints as
@@ -260,11 +452,13 @@ class EncodedTable:
         ids = self.row_ids[np.asarray(positions, dtype=np.int64)]
         return ids
 
-    def unify(self, dist):
+    def unify(self, dist, device_table=None, ctx=None):
         """Row-sharded input (every rank collected its own rows): makes the dictionaries GLOBAL -- the
         sorted union of the shards' dictionaries, so that a code means the same value on every GPU and
         the count tensors of the shards add up -- and records the shard's place in the global table.
-        Only dictionaries (one entry per distinct value) and row counts cross the wire."""
+        Only dictionaries (one entry per distinct value) and row counts cross the wire.  With a
+        `device_table` (device-side Arrow ingest) the resident codes are re-labelled in place on the
+        device (dr_index_remap) and no host copy of them is made."""
         import torch.distributed as td
         local = [(c.name, c.kind, list(c.dictionary) if c.kind == "str" else np.asarray(c.dictionary, dtype=np.float64))
                  for c in self.columns]
@@ -289,12 +483,23 @@ class EncodedTable:
                 merged = np.unique(np.concatenate([np.asarray(g[1][i][2], dtype=np.float64) for g in gathered]))
                 lut = np.searchsorted(merged, np.asarray(c.dictionary, dtype=np.float64)).astype(np.int32)
                 values = c.values
-            codes = np.where(c.codes >= 0, np.r_[lut, np.int32(-1)][c.codes], -1).astype(np.int32) if len(lut) else \
-                np.full(len(c.codes), -1, dtype=np.int32)
+            if device_table is not None:
+                import torch
+                col = device_table.codes[device_table.col_index[c.name]]
+                if len(lut) and not np.array_equal(lut, np.arange(len(lut))):
+                    d_lut = torch.from_numpy(lut).to(col.device)
+                    ctx.index_remap(col.data_ptr(), 4, 0, 0, self.n_rows, d_lut.data_ptr(), len(lut), col.data_ptr())
+                    torch.cuda.current_stream().synchronize()   # d_lut is released on return
+                codes = (lambda col=col, n=self.n_rows: col[:n].cpu().numpy())
+            else:
+                codes = np.where(c.codes >= 0, np.r_[lut, np.int32(-1)][c.codes], -1).astype(np.int32) if len(lut) else \
+                    np.full(len(c.codes), -1, dtype=np.int32)
             cols.append(Column(c.name, kind, merged, codes, values))
-        t = EncodedTable(self.row_id, self.row_ids, self.row_id_kind, cols, self.name)
+        t = EncodedTable(self.row_id, self._row_ids, self.row_id_kind, cols, self.name, n_rows=self.n_rows)
         t.row_offset = int(sum(counts[:dist.rank]))
         t.n_rows_global = int(sum(counts))
+        if device_table is not None:
+            device_table.table = t
         return t
 
     def shard(self, rank, world):
@@ -351,6 +556,7 @@ class DeviceTable:
                     torch.cuda.current_stream().synchronize()
         self.values = values
         self.col_index = {c.name: i for i, c in enumerate(table.columns)}
+        self.ids = None   # device int64 row ids (device-side Arrow ingest), else None
 
     def col(self, name):
         return self.codes[self.col_index[name]]

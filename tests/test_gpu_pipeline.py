@@ -340,6 +340,8 @@ def test_arrow_input_gives_the_same_repairs_as_pandas_input():
     got = RepairModel().setArrowInput(pa.Table.from_pandas(df, preserve_index=False)).setRowId("tid") \
         .setErrorDetectors([NullErrorDetector()]).option("model.lgb.n_estimators", "30") \
         .option("model.hp.max_evals", "1").run()
+    assert isinstance(got, pa.Table)   # Arrow in, Arrow out
+    got = got.to_pandas()
     assert PU.frame_tuples(got, "tid") == PU.frame_tuples(want, "tid") and len(got) == 7
 
 

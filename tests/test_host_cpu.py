@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "missing export: " + sym
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 2
+    assert lib.dr_abi_version() == 3
     raw = ctypes.CDLL(_native.LIB_PATH)
     for sym in declared:
         getattr(raw, sym)
