@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- one "step" = one pass of the hot path (error detection -> attribute statistics ->
-weak-label domain analysis -> repair-model inference -> encoded (tid, attribute, current, repaired)
-frame) over one synthetic N x K categorical table (config C4 of SURVEY.md section 8d).
+weak-label domain analysis -> repair-model inference -> (tid, attribute, current, repaired) frame) over
+one synthetic N x K categorical table (config C4 of SURVEY.md section 8d).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--cols C] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--cols C] [--scaling strong|weak]
+                  [--impl reference]
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL); rows are sharded (weak scaling: every rank
-holds R rows of one global G*R-row table) and the only exchange is the all-reduce of the count
-tensors.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Default = STRONG scaling: ONE R-row table,
+rows sharded R/N per GPU (BASELINE config 4); --scaling weak keeps R rows per GPU.  The only exchange
+is the packed count-tensor collective of each pass phase.  `value` times the pass with the shard
+resident in HBM; `e2e` times RepairModel().setArrowInput(host table).run() -> host Arrow frame.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import json
@@ -40,7 +43,8 @@ def parse_args():
                          "weak: --rows per GPU of a N x --rows table")
     ap.add_argument("--cols", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-rows", type=int, default=20000, help="rows of the CPU baseline sample")
+    ap.add_argument("--ref-rows", type=int, default=0,
+                    help="rows of the CPU arm's sample (0 = as many as fit the time budget, 20k..200k)")
     ap.add_argument("--configs", default="auto",
                     help="extra wall-clock rows for BASELINE configs: comma list of c2,c3,c5, 'none', or 'auto' "
                          "(all three on a 1-GPU run of the default size)")
@@ -118,9 +122,42 @@ OPTS = {"error.pairwise_freq_ratio_threshold": "1.0", "model.hp.max_evals": "1"}
 _ORACLE_RF = {}
 
 
-def run_oracle_sample(n_rows, n_cols, n_iter):
+def gpu_trained_specs(args):
+    """The frozen models of the b200 arm for the CPU arm: same table, same detect pass, same global 10k-row
+    training samples, same deterministic trainer (dr_gbdt_train) -> {target: model spec}.  Untimed setup;
+    needs a GPU (the CPU arm falls back to random-init forests of the same architecture without one)."""
+    import torch
+    from repair import RepairModel, synth
+    from repair.engine import Engine
+    from repair.errors import ErrorModelOptions
+    from repair.model import build_models
+    from repair.table import DeviceTable, EncodedTable
+    k = args.cols
+    total_rows = args.rows if args.scaling == "strong" else args.rows * max(args.gpus, 1)
+    device = torch.device("cuda", 0)
+    spec = synth.SynthSpec.c4(total_rows, k)
+    codes_dev = synth.generate_torch(spec, device, 0, total_rows)
+    names = synth.column_names(k)
+    table = EncodedTable.from_codes("tid", names, [np.zeros(0, dtype=np.int32)] * k, spec.dom,
+                                    row_ids=np.arange(total_rows, dtype=np.int64))
+    table.n_rows = table.n_rows_global = total_rows
+    engine = Engine(table, 0, device_table=DeviceTable(table, device, codes=codes_dev))
+    rm = RepairModel()
+    rm.opts = dict(OPTS)
+    res = engine.detect(detector_specs(k), [], 80, ErrorModelOptions.resolve(rm.opts))
+    models = build_models(rm, engine, table, res, [])
+    out = {y: (m[2]["spec"] if m[0] == "forest" else {"const": m[1]}) for y, m in models}
+    engine.close()
+    del engine, codes_dev, models
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_oracle_sample(n_rows, n_cols, n_iter, trained=None):
     """One pass of the oracle pipeline over the first `n_rows` rows of the C4 table.
-    -> (seconds, rows, error cells, seconds of the detect phase, threads used)"""
+    trained: {target: spec} of gpu_trained_specs -- the oracle then evaluates the SAME forests as the b200
+    arm, under the encoders they were trained with; else random-init forests of the same architecture.
+    -> (seconds, rows, error cells, seconds of the detect phase, threads used, repaired cells, fallbacks)"""
     from oracle import ckernels
     from oracle import forest as OF
     from oracle import repair as OR
@@ -136,8 +173,23 @@ def run_oracle_sample(n_rows, n_cols, n_iter):
     tbl = OTable(["tid"] + names, ["int"] + ["str"] * n_cols,
                  [np.arange(n_rows, dtype=np.float64)] + [c.astype(np.int64) for c in codes])
     rf = _ORACLE_RF.setdefault(n_iter, random_forest_provider(n_iter))  # forests are built once
+    fallbacks = []
 
     def provider(ctx):
+        t = (trained or {}).get(ctx["y"])
+        if t is not None and "const" in t:
+            return {"const": t["const"]}
+        if t is not None:
+            same = len(t["encoders"]) == len(ctx["encoders"]) and all(
+                pe["attr"] == oe["attr"] and pe["type"] == oe["type"] and
+                (pe["type"] == "cont" or len(pe["categories"]) == len(oe["categories"]))
+                for pe, oe in zip(t["encoders"], ctx["encoders"]))
+            if same:
+                for pe, oe in zip(t["encoders"], ctx["encoders"]):   # the encoders the forest was trained with
+                    if pe["type"] != "cont":
+                        oe["categories"] = [None if c < 0 else int(c) for c in pe["categories"]]
+                return {"forest": t["forest"], "classes": [int(c) for c in t["class_codes"]]}
+            fallbacks.append(ctx["y"])   # the sample saw a different set of categories: random-init stand-in
         octx = dict(ctx)
         octx["encoders"] = [dict(e) for e in ctx["encoders"]]
         spec_ = rf(octx)
@@ -150,30 +202,59 @@ def run_oracle_sample(n_rows, n_cols, n_iter):
     t0 = time.time()
     out = OR.run(tbl, "tid", detector_specs(n_cols), None, 80, None, o_opts, provider)
     t_full = time.time() - t0
-    return t_full, n_rows, len(cells), t_detect, threads, len(out)
+    return t_full, n_rows, len(cells), t_detect, threads, len(out), fallbacks
 
 
 def reference_arm(args):
+    """The reference's CPU path (restated: oracle/, NumPy + OpenMP C) on a bounded sample of the b200 arm's
+    workload: the first R rows of the same table, the same detectors and options, the same frozen forests.
+    R is chosen so that the whole --steps/--warmup run stays within minutes; the pass has a fixed cost
+    (pair statistics over the 32 x 31 attribute pairs), so a 10k-row pass is timed as well and the line
+    reports the marginal rate of the linear fit next to the plain rows / seconds of the sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times = []
-    info = None
-    run_oracle_sample(args.ref_rows, args.cols, N_ESTIMATORS)  # untimed: builds the frozen forests
+    trained, forests = None, "random-init (no GPU to train them on)"
+    try:
+        import torch
+        if args.forests == "trained" and torch.cuda.is_available():
+            t0 = time.time()
+            trained = gpu_trained_specs(args)
+            forests = "the b200 arm's frozen forests (dr_gbdt_train, {:.0f} s of untimed setup)".format(time.time() - t0)
+    except Exception as e:  # noqa: BLE001
+        forests = "random-init (training them failed: {}: {})".format(type(e).__name__, e)
+    small = 10000
+    run_oracle_sample(small, args.cols, N_ESTIMATORS, trained)          # untimed: builds / loads the forests
+    t_small = run_oracle_sample(small, args.cols, N_ESTIMATORS, trained)[0]
+    rows = args.ref_rows
+    if rows <= 0:   # auto: as many rows as (steps + warmup) passes fit into ~3 minutes, assuming ~half of the
+        budget = 180.0 / max(args.steps + args.warmup, 1)                # small pass is fixed cost
+        rows = int(small * max(1.0, (budget - 0.5 * t_small) / max(0.5 * t_small, 1e-3)))
+        rows = int(min(max(rows, 2 * small), 200000) // 1000 * 1000)
+    times, info = [], None
     for i in range(args.warmup + args.steps):
-        info = run_oracle_sample(args.ref_rows, args.cols, N_ESTIMATORS)
+        info = run_oracle_sample(rows, args.cols, N_ESTIMATORS, trained)
         if i >= args.warmup:
             times.append(info[0])
     t = float(np.mean(times))
     value = info[1] / t
+    per_row = (t - t_small) / max(rows - small, 1)
+    fixed = t_small - per_row * small
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32 codes / f64 margins", "data": "synthetic",
-        "config": {"workload": "C4 synthetic {} rows x {} cols (bounded sample of the {}-row table), NULL + FD "
-                               "detectors, 300-round random-init forests".format(info[1], args.cols, args.rows)},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "int32 codes / f64 margins", "data": "synthetic",
+        "config": {"workload": "C4 synthetic: first {} rows (bounded sample) of the {}-row x {}-col table, 1% NULLs + 4 FD "
+                               "denial constraints, NULL + Constraint detectors, pairwise_freq_ratio_threshold=1.0, "
+                               "{}".format(info[1], args.rows, args.cols, forests),
+                   "rows_total": args.rows, "rows_in_sample": info[1], "cols": args.cols},
         "cells_repaired_per_sec": info[2] / max(t - info[3], 1e-9),
         "rows_scanned_per_sec": info[1] / info[3],
+        "fit": {"rows": [small, rows], "seconds": [t_small, t], "fixed_s": fixed,
+                "marginal_rows_per_sec": (1.0 / per_row) if per_row > 0 else None,
+                "note": "seconds(rows) = fixed_s + rows / marginal_rows_per_sec; extrapolated to the full table the "
+                        "CPU pass tends to the marginal rate"},
+        "targets_on_random_forests": info[6],
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": info[4], "kind": "port",
                          "sample": "first {} rows of the C4 table; oracle (NumPy + OpenMP C forest) full pass".format(
                              info[1])},
@@ -855,12 +936,16 @@ def b200_arm(args):
     # ---- CPU baseline (rank 0, single GPU run only) -----------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         restore_affinity()   # the CPU leg gets every host core
-        run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)  # untimed: builds the frozen forests
-        t_full, rows, ncells, t_det, threads, _ = run_oracle_sample(args.ref_rows, k, N_ESTIMATORS)
+        trained = {y: (m[2]["spec"] if m[0] == "forest" else {"const": m[1]}) for y, m in models} \
+            if args.forests == "trained" else None
+        rows_cpu = args.ref_rows if args.ref_rows > 0 else 20000
+        run_oracle_sample(10000, k, N_ESTIMATORS, trained)  # untimed: first touch of the forests, thread pool
+        t_full, rows, ncells, t_det, threads, _, fb = run_oracle_sample(rows_cpu, k, N_ESTIMATORS, trained)
         line["cpu_baseline"] = {"value": rows / t_full, "unit": "rows/s", "cores": threads, "kind": "port",
-                                "sample": "first {} rows of the C4 table, oracle full pass in {:.1f} s "
-                                          "(detect phase {:.1f} s)".format(rows, t_full, t_det),
-                                "cells_repaired_per_sec": ncells / max(t_full - t_det, 1e-9)}
+                                "sample": "first {} rows of the C4 table with the same frozen forests, oracle full "
+                                          "pass in {:.1f} s (detect phase {:.1f} s)".format(rows, t_full, t_det),
+                                "cells_repaired_per_sec": ncells / max(t_full - t_det, 1e-9),
+                                "targets_on_random_forests": fb}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

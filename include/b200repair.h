@@ -275,6 +275,27 @@ int dr_domain_score(dr_ctx* ctx, const int32_t* rows, int64_t n_cells, const int
                     const int64_t* hist_t, const int64_t* tau, int64_t n_total_rows, double beta,
                     int32_t* out_top1, double* out_prob, uint8_t* out_weak, void* stream);
 
+/* The same analysis for ALL targets of a pass in three launches, applied to the error bitmaps in place:
+ * a cell's verdict only depends on its correlated values, so the top-1 candidate is computed once per
+ * combination of correlated values (the per-cell loop of dr_domain_score, identical doubles) and the pass
+ * over the cells is a table look-up driven by the bitmap -- bits of cells whose current value is their
+ * top-1 candidate are cleared (errors.py:507-530); removed[i] (device int64, accumulated) counts them.
+ * DR_ERR_UNSUPPORTED when a target has more than 2^20 combinations (use dr_domain_score).  Synchronises
+ * `stream`. */
+typedef struct dr_domain_target {
+    const int32_t* target;    /* device int32[n_rows]: discretised target column */
+    uint32_t* bitmap;         /* device: error cells of the target, updated in place */
+    const int64_t* hist_t;    /* device int64[dom_t + 1], HAVING applied */
+    int32_t dom_t;
+    int32_t n_corr;           /* 1 .. 8 */
+    const int32_t* corr[8];   /* device columns of the correlated attributes */
+    const int64_t* cooc[8];   /* device int64[(dom_c + 1) * (dom_t + 1)], HAVING applied */
+    int64_t tau[8];
+    int32_t dom_c[8];
+} dr_domain_target;
+int dr_domain_prune(dr_ctx* ctx, const dr_domain_target* targets, int n_targets, int64_t n_rows,
+                    int64_t n_total_rows, double beta, int64_t* removed, void* stream);
+
 /* ---- a10: repair base = error cells masked to NULL, restricted to the rows that matter ---------
  * Replaces RepairApi.convertErrorCellsToNull (RepairApi.scala:171-211) and the dirty/clean split
  * (model.py:550-555) without materialising the N x K masked table: gathers the given rows into a

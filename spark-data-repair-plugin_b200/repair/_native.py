@@ -40,6 +40,12 @@ class dr_forest_ranked(ctypes.Structure):
     ]
 
 
+class dr_domain_target(ctypes.Structure):
+    _fields_ = [("target", c_void_p), ("bitmap", c_void_p), ("hist_t", c_void_p), ("dom_t", c_int32),
+                ("n_corr", c_int32), ("corr", c_void_p * 8), ("cooc", c_void_p * 8), ("tau", c_int64 * 8),
+                ("dom_c", c_int32 * 8)]
+
+
 class dr_gbdt_params(ctypes.Structure):
     _fields_ = [("n_rows", c_int32), ("n_features", c_int32), ("n_classes", c_int32), ("n_iter", c_int32),
                 ("max_depth", c_int32), ("num_leaves", c_int32), ("min_data_in_leaf", c_int32),
@@ -98,6 +104,8 @@ _SIGNATURES = {
                         POINTER(c_int64), c_int64, c_void_p, c_void_p]),
     "dr_domain_score": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, _PP, POINTER(c_int32), _PP, c_int,
                                 c_void_p, POINTER(c_int64), c_int64, c_double, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "dr_domain_prune": (c_int, [c_void_p, POINTER(dr_domain_target), c_int, c_int64, c_int64, c_double, c_void_p,
                                 c_void_p]),
     "dr_gather_rows_masked": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "dr_gather_rows_masked_f64": (c_int, [c_void_p, _PP, _PP, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -403,6 +411,19 @@ class Context:
                                              tp, len(corr), _dp(hist_t), _i64_array(tau), n_total, beta,
                                              _dp(out_top1), _dp(out_prob), _dp(out_weak), self._stream()))
 
+    def domain_prune(self, targets, n_rows, n_total, beta, removed):
+        """targets: [(target col, bitmap, hist_t ptr, dom_t, [(corr col, cooc ptr, dom_c, tau)])] -- pointers
+        are device addresses (ints) or tensors; removed: device int64[len(targets)], accumulated."""
+        arr = (dr_domain_target * max(len(targets), 1))()
+        ptr = lambda x: x if isinstance(x, int) else x.data_ptr()  # noqa: E731
+        for i, (tcol, bitmap, hist, dom_t, corr) in enumerate(targets):
+            d = arr[i]
+            d.target, d.bitmap, d.hist_t, d.dom_t, d.n_corr = ptr(tcol), ptr(bitmap), ptr(hist), dom_t, len(corr)
+            for j, (ccol, cooc, dom_c, tau) in enumerate(corr):
+                d.corr[j], d.cooc[j], d.dom_c[j], d.tau[j] = ptr(ccol), ptr(cooc), dom_c, tau
+        self._check(self.lib.dr_domain_prune(self._h, arr, len(targets), n_rows, n_total, beta, _dp(removed),
+                                             self._stream()))
+
     # ---- repair base / tile ----------------------------------------------------------------------
     def gather_rows_masked(self, cols, bitmaps, rows, n, out, f64=False, null_out=None):
         """null_out (int32 codes only): int32 [K][words] that receives the NULL bitmap of every tile column."""
@@ -486,7 +507,7 @@ for _name in ("widen_u8", "h2d_copy", "d2h_copy", "index_presence", "index_remap
               "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
               "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "cooc_skip", "key_presence", "key_flag", "dc_exists", "combine_counts", "dc_lt_flag",
-              "dc_hash_build", "dc_hash_flag", "domain_score", "gather_rows_masked", "tile_null_bitmap", "gather",
+              "dc_hash_build", "dc_hash_flag", "domain_score", "domain_prune", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill", "gbdt_train"):
     setattr(Context, _name, _profiled(_name, getattr(Context, _name)))
 

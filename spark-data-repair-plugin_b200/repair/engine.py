@@ -756,38 +756,67 @@ class Engine:
         return stats, tables, having
 
     # ---- a9: weak-label domain analysis --------------------------------------------------------
-    def prune_weak_labels(self, res, tables, having, continuous, max_attrs_domains, alpha, beta):
+    def prune_weak_labels(self, res, tables, having, continuous, max_attrs_domains, alpha, beta, keep_scores=False):
         """Cells whose current value is the top-1 candidate of the naive-Bayes domain analysis are not
-        errors (errors.py:507-530).  One scoring launch per target, no host round trip in the loop."""
-        removed = self.torch.zeros(1, dtype=self.torch.int64, device=self.device)
+        errors (errors.py:507-530).  All targets in ONE call (dr_domain_prune: top-1 per combination of
+        correlated values, then a bitmap-driven look-up): the count tables of every target travel in one
+        host->device copy and nothing comes back.  keep_scores (tests) / targets with too many
+        combinations take the per-cell kernel (dr_domain_score), one launch per target."""
+        torch = self.torch
+        work = []
         for t in res.target_columns:
             corr = res.pairwise_stats.get(t, [])[:max_attrs_domains]
-            if t in continuous or not corr or t not in res.bitmaps:
+            if t in continuous or not corr or t not in res.bitmaps or int(res.n_cells.get(t, 0)) == 0:
                 continue
-            n = int(res.n_cells.get(t, 0))
-            if n == 0:
-                continue
-            rows = self.bitmap_rows(res.bitmaps[t], count=n)
-            dom_t = self.disc_dom[t]
             hist_t = SH.apply_having(self._hist_cache[t], having).astype(np.int64)
-            cooc, dom_c, taus, ccols = [], [], [], []
+            items = []
             for a, _ in corr:
                 tab = tables[(t, a)].T if (t, a) in tables else tables[(a, t)]
                 tab = SH.apply_having(np.ascontiguousarray(tab), having).astype(np.int64)  # [dom_a+1, dom_t+1]
-                cooc.append(self.torch.from_numpy(np.ascontiguousarray(tab)).to(self.device))
-                dom_c.append(self.disc_dom[a])
-                taus.append(SH.tau_for(alpha, self.n_rows_global, res.domain_stats[a], res.domain_stats[t]))
-                ccols.append(self.disc_cols[a])
-            top1 = self.torch.empty(n, dtype=self.torch.int32, device=self.device)
-            prob = self.torch.empty(n, dtype=self.torch.float64, device=self.device)
-            weak = self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
-            self.ctx.domain_score(rows, n, self.disc_cols[t], dom_t, ccols, dom_c, cooc,
-                                  self.torch.from_numpy(hist_t).to(self.device), taus, self.n_rows_global, beta,
-                                  top1, prob, weak)
-            self.ctx.bitmap_clear_rows(res.bitmaps[t], rows, weak, n)
-            removed += weak.sum()
-            res.last_domain = (rows, top1, prob, weak)
+                items.append((a, np.ascontiguousarray(tab).reshape(-1), self.disc_dom[a],
+                              SH.tau_for(alpha, self.n_rows_global, res.domain_stats[a], res.domain_stats[t])))
+            work.append((t, hist_t, items))
+        removed = torch.zeros(max(len(work), 1), dtype=torch.int64, device=self.device)
         res.weak_removed_dev = removed
+        if not work:
+            return removed
+        combos_ok = all(np.prod([float(d + 1) for _, _, d, _ in items]) <= (1 << 20) and len(items) <= 8
+                        for _, _, items in work)
+        if combos_ok and not keep_scores and not getattr(self, "domain_per_cell", False):
+            parts, offs = [], []
+            for t, hist_t, items in work:
+                offs.append(sum(len(p) for p in parts))
+                parts.append(hist_t)
+                for _, tab, _, _ in items:
+                    offs.append(sum(len(p) for p in parts))
+                    parts.append(tab)
+            # (running offsets computed incrementally: the lists are short)
+            flat = torch.from_numpy(np.concatenate(parts)).to(self.device)
+            base, k, targets = flat.data_ptr(), 0, []
+            for t, hist_t, items in work:
+                h_ptr = base + 8 * offs[k]
+                k += 1
+                corr = []
+                for a, tab, dom_c, tau in items:
+                    corr.append((self.disc_cols[a], base + 8 * offs[k], dom_c, tau))
+                    k += 1
+                targets.append((self.disc_cols[t], res.bitmaps[t], h_ptr, self.disc_dom[t], corr))
+            self.ctx.domain_prune(targets, self.n_rows, self.n_rows_global, beta, removed)
+            self._domain_flat = flat   # stays alive until the next pass (the call above synchronised anyway)
+            return removed
+        for i, (t, hist_t, items) in enumerate(work):
+            n = int(res.n_cells.get(t, 0))
+            rows = self.bitmap_rows(res.bitmaps[t], count=n)
+            cooc = [torch.from_numpy(tab).to(self.device) for _, tab, _, _ in items]
+            top1 = torch.empty(n, dtype=torch.int32, device=self.device)
+            prob = torch.empty(n, dtype=torch.float64, device=self.device)
+            weak = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self.ctx.domain_score(rows, n, self.disc_cols[t], self.disc_dom[t], [self.disc_cols[a] for a, _, _, _ in items],
+                                  [d for _, _, d, _ in items], cooc, torch.from_numpy(hist_t).to(self.device),
+                                  [tau for _, _, _, tau in items], self.n_rows_global, beta, top1, prob, weak)
+            self.ctx.bitmap_clear_rows(res.bitmaps[t], rows, weak, n)
+            removed[i] += weak.sum()
+            res.last_domain = (rows, top1, prob, weak)
         return removed
 
     # ---- ErrorModel.detect -----------------------------------------------------------------------
@@ -860,10 +889,12 @@ class Engine:
                         seen.add(frozenset(pr))
                         scored.append(pr)
         pres_launched = self.launch_pair_presence(scored) if scored and len(res.disc_attrs) <= 64 else None
+        self.mark("detect:local 1 launched")
         self.exchange(ex1 + [(h, "sum") for _, _, h in launched] +
                       ([(pres_launched[2], "or")] if pres_launched else []))
         self._absorb_hists(launched)
         presence = self.pair_presence_host(pres_launched) if pres_launched else None
+        self.mark("detect:hists + presence on the host")
         for fn in after:        # local 2: flags that needed the global tables / counts
             fn()
         res.bitmaps = bitmaps
@@ -877,6 +908,7 @@ class Engine:
             self.exchange([(t, "sum")])
             glob = [int(v) for v in t.cpu().numpy()]
         res.n_cells_global = dict(zip(names_b, glob))
+        self.mark("detect:flags + cell counts")
         if sum(glob) == 0:
             res.domain_stats = {}
             return res
@@ -891,11 +923,13 @@ class Engine:
             res.target_columns, res.domain_stats, opts["error.attr_freq_ratio_threshold"],
             opts["error.pairwise_freq_ratio_threshold"], max_attrs, presence)
         res.pairwise_stats = stats
+        self.mark("detect:attribute statistics")
         if given_cells is None:
             self.prune_weak_labels(res, tables, having, continuous, opts["error.max_attrs_to_compute_domains"],
                                    opts["error.domain_threshold_alpha"], opts["error.domain_threshold_beta"])
             res.n_cells = dict(zip(res.bitmaps.keys(),
                                    self.ctx.bitmap_count_many(list(res.bitmaps.values()), self.n_rows)))
+            self.mark("detect:domain analysis")
         return res
 
     # ---- cell frames -----------------------------------------------------------------------------

@@ -430,3 +430,28 @@ def test_fd_constraint_with_a_huge_key_space_uses_the_hash_table(monkeypatch):
         got, want, _ = PU.run_both_frame(df, "tid", [{"type": "constraint", "constraints": cons}], mode="detect")
         assert got == want and len(got) > 50, cons
     assert len(calls) == 3
+
+
+def test_domain_pruning_in_one_call_equals_the_per_cell_kernel():
+    """dr_domain_prune (top-1 per combination of correlated values, bitmap-driven, all targets at once) clears
+    exactly the bits the per-cell kernel dr_domain_score + dr_bitmap_clear_rows clears."""
+    from repair.engine import Engine
+    from repair.errors import ErrorModelOptions
+    from repair.table import EncodedTable
+    spec, names, codes, enc, specs = PU.synth_inputs(60000, 16, seed=3, c4=True)
+    opts = ErrorModelOptions.resolve({"error.pairwise_freq_ratio_threshold": "1.0",
+                                      "error.domain_threshold_beta": "0.3"})
+    got = {}
+    for per_cell in (False, True):
+        eng = Engine(enc, 0)
+        eng.domain_per_cell = per_cell
+        try:
+            res = eng.detect(specs, [], 80, opts)
+            got[per_cell] = ({a: b.cpu().numpy().copy() for a, b in res.bitmaps.items()}, dict(res.n_cells),
+                             int(res.weak_removed_dev.sum().item()), dict(res.n_cells_detected))
+        finally:
+            eng.close()
+    assert got[False][1] == got[True][1] and got[False][2] == got[True][2]
+    assert got[False][2] > 0 and got[False][1] != got[False][3]          # something was pruned
+    for a in got[True][0]:
+        assert np.array_equal(got[False][0][a], got[True][0][a]), a
