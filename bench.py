@@ -180,16 +180,16 @@ def run_oracle_sample(n_rows, n_cols, n_iter, trained=None):
         if t is not None and "const" in t:
             return {"const": t["const"]}
         if t is not None:
+            # (the sample may have seen fewer categories than the training sample of the full table -- e.g. no
+            # NULL in a column -- which is harmless: the forest is evaluated under ITS encoders)
             same = len(t["encoders"]) == len(ctx["encoders"]) and all(
-                pe["attr"] == oe["attr"] and pe["type"] == oe["type"] and
-                (pe["type"] == "cont" or len(pe["categories"]) == len(oe["categories"]))
-                for pe, oe in zip(t["encoders"], ctx["encoders"]))
+                pe["attr"] == oe["attr"] and pe["type"] == oe["type"] for pe, oe in zip(t["encoders"], ctx["encoders"]))
             if same:
                 for pe, oe in zip(t["encoders"], ctx["encoders"]):   # the encoders the forest was trained with
                     if pe["type"] != "cont":
                         oe["categories"] = [None if c < 0 else int(c) for c in pe["categories"]]
                 return {"forest": t["forest"], "classes": [int(c) for c in t["class_codes"]]}
-            fallbacks.append(ctx["y"])   # the sample saw a different set of categories: random-init stand-in
+            fallbacks.append(ctx["y"])   # different features / encoder types: random-init stand-in
         octx = dict(ctx)
         octx["encoders"] = [dict(e) for e in ctx["encoders"]]
         spec_ = rf(octx)
@@ -886,7 +886,8 @@ def b200_arm(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         t0 = time.perf_counter()
-        parts = {"ingest_s": 0.0, "egress_s": 0.0, "ingest_copy_s": 0.0, "ingest_encode_s": 0.0}
+        parts = {"ingest_s": 0.0, "egress_s": 0.0, "ingest_copy_s": 0.0, "ingest_encode_s": 0.0,
+                 "engine_ready_s": 0.0, "detect_done_s": 0.0, "repair_done_s": 0.0, "total_s": 0.0}
         for _ in range(e_steps):
             api_step()
             lr = last["rm"].last_run
@@ -894,6 +895,8 @@ def b200_arm(args):
             parts["ingest_copy_s"] += lr.get("ingest_copy_s", 0.0)
             parts["ingest_encode_s"] += lr.get("ingest_encode_s", 0.0)
             parts["egress_s"] += lr.get("egress_s", 0.0)
+            for kk in ("engine_ready_s", "detect_done_s", "repair_done_s", "total_s"):
+                parts[kk] += lr.get(kk, 0.0)
         ev1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3 / e_steps
@@ -913,6 +916,8 @@ def b200_arm(args):
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "ingest_s": float(t[2]), "egress_s": float(t[3]),
                        "ingest_copy_s": float(t[4]), "ingest_encode_s": float(t[5]),
+                       "stamps_s": {"engine_ready": float(t[6]), "detect_done": float(t[7]), "repair_done": float(t[8]),
+                                    "run_returned": float(t[9])},
                        "frame_rows": int(frame.num_rows), "frame_equals_resident_pass": int(flag[0]) == 0,
                        "call": "RepairModel().setArrowInput(pyarrow.Table in pageable host memory).setRowId('tid')"
                                ".setErrorDetectors([NullErrorDetector(), ConstraintErrorDetector(..)])"

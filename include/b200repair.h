@@ -186,6 +186,10 @@ int dr_bitmap_count_many(dr_ctx* ctx, const uint32_t* const* bitmaps, int n_bitm
                          int64_t* out_counts, void* stream);
 int dr_bitmap_to_rows_async(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows, int32_t* out_rows, int64_t count,
                             void* stream);
+/* The same ordered compaction for up to DR_MAX_COUNT_MANY bitmaps (all over n_rows rows) in three launches;
+ * counts[i] = popcount of bitmap i (0: skipped), out_rows[i]: device int32[counts[i]].  Asynchronous. */
+int dr_bitmaps_to_rows_many(dr_ctx* ctx, const uint32_t* const* bitmaps, int n_bitmaps, int64_t n_rows,
+                            int32_t* const* out_rows, const int64_t* counts, void* stream);
 int dr_bitmap_gather(dr_ctx* ctx, const uint32_t* src, const int32_t* rows, int64_t n, uint32_t* out,
                      void* stream);
 int dr_bitmap_clear_rows(dr_ctx* ctx, uint32_t* bitmap, const int32_t* rows, const uint8_t* flags, int64_t n,

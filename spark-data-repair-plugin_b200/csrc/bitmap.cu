@@ -26,8 +26,8 @@ __device__ __forceinline__ uint32_t tail_mask(int64_t word, int64_t n_rows) {
 // ---- ordered compaction -------------------------------------------------------------------------
 constexpr int kWordsPerBlock = 1024;  // 32 Ki rows per block
 
-__global__ void __launch_bounds__(kThreads) k_block_popc(const uint32_t* __restrict__ bm, int64_t n_rows,
-                                                         int64_t n_words, unsigned long long* __restrict__ counts) {
+__device__ __forceinline__ void block_popc(const uint32_t* __restrict__ bm, int64_t n_rows, int64_t n_words,
+                                           unsigned long long* __restrict__ counts) {
     __shared__ unsigned int warp_sum[kThreads / 32];
     const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock;
     unsigned int c = 0;
@@ -45,8 +45,13 @@ __global__ void __launch_bounds__(kThreads) k_block_popc(const uint32_t* __restr
     }
 }
 
+__global__ void __launch_bounds__(kThreads) k_block_popc(const uint32_t* __restrict__ bm, int64_t n_rows,
+                                                         int64_t n_words, unsigned long long* __restrict__ counts) {
+    block_popc(bm, n_rows, n_words, counts);
+}
+
 // exclusive scan of the per-block counts, one CTA; counts[n_blocks] receives the total
-__global__ void __launch_bounds__(1024) k_scan_counts(unsigned long long* __restrict__ counts, int n_blocks) {
+__device__ __forceinline__ void scan_counts(unsigned long long* __restrict__ counts, int n_blocks) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long carry;
     if (threadIdx.x == 0) carry = 0;
@@ -80,10 +85,13 @@ __global__ void __launch_bounds__(1024) k_scan_counts(unsigned long long* __rest
     if (threadIdx.x == 0) counts[n_blocks] = carry;
 }
 
-__global__ void __launch_bounds__(kThreads) k_write_rows(const uint32_t* __restrict__ bm, int64_t n_rows,
-                                                         int64_t n_words,
-                                                         const unsigned long long* __restrict__ offsets,
-                                                         int32_t* __restrict__ out, int64_t capacity) {
+__global__ void __launch_bounds__(1024) k_scan_counts(unsigned long long* __restrict__ counts, int n_blocks) {
+    scan_counts(counts, n_blocks);
+}
+
+__device__ __forceinline__ void write_rows(const uint32_t* __restrict__ bm, int64_t n_rows, int64_t n_words,
+                                           const unsigned long long* __restrict__ offsets,
+                                           int32_t* __restrict__ out, int64_t capacity) {
     __shared__ unsigned int warp_sum[kThreads / 32];
     __shared__ unsigned long long block_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -118,6 +126,13 @@ __global__ void __launch_bounds__(kThreads) k_write_rows(const uint32_t* __restr
         if (threadIdx.x == 0) block_base += total;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(kThreads) k_write_rows(const uint32_t* __restrict__ bm, int64_t n_rows,
+                                                         int64_t n_words,
+                                                         const unsigned long long* __restrict__ offsets,
+                                                         int32_t* __restrict__ out, int64_t capacity) {
+    write_rows(bm, n_rows, n_words, offsets, out, capacity);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bitmap_gather(const uint32_t* __restrict__ src,
@@ -396,6 +411,28 @@ __global__ void __launch_bounds__(kThreads) k_popc_many(const __grid_constant__ 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(totals + blockIdx.y, local);
 }
 
+// ordered compaction of many bitmaps in three launches: blockIdx.y = bitmap
+struct ManyRows {
+    int32_t* out[DR_MAX_COUNT_MANY];
+    long long capacity[DR_MAX_COUNT_MANY];
+};
+__global__ void __launch_bounds__(kThreads) k_block_popc_many(const __grid_constant__ ManyBitmaps p, int64_t n_rows,
+                                                              int64_t n_words, int n_blocks,
+                                                              unsigned long long* __restrict__ counts) {
+    block_popc(p.bm[blockIdx.y], n_rows, n_words, counts + (size_t)blockIdx.y * (n_blocks + 1));
+}
+__global__ void __launch_bounds__(1024) k_scan_counts_many(unsigned long long* __restrict__ counts, int n_blocks) {
+    scan_counts(counts + (size_t)blockIdx.x * (n_blocks + 1), n_blocks);
+}
+__global__ void __launch_bounds__(kThreads) k_write_rows_many(const __grid_constant__ ManyBitmaps p,
+                                                              const __grid_constant__ ManyRows o, int64_t n_rows,
+                                                              int64_t n_words, int n_blocks,
+                                                              const unsigned long long* __restrict__ counts) {
+    if (o.capacity[blockIdx.y] <= 0) return;
+    write_rows(p.bm[blockIdx.y], n_rows, n_words, counts + (size_t)blockIdx.y * (n_blocks + 1), o.out[blockIdx.y],
+               o.capacity[blockIdx.y]);
+}
+
 inline int grid_rows(const dr_ctx* ctx, int64_t n) { return dr_grid_for(ctx, n, kThreads, kCtasPerSm); }
 
 }  // namespace
@@ -496,6 +533,41 @@ int dr_bitmap_to_rows_async(dr_ctx* ctx, const uint32_t* bitmap, int64_t n_rows,
     if (rc) return rc;
     k_write_rows<<<n_blocks, kThreads, 0, st>>>(bitmap, n_rows, (n_rows + 31) >> 5,
                                                 (const unsigned long long*)ctx->scratch, out_rows, count);
+    DR_LAUNCHED(ctx);
+    return DR_OK;
+}
+
+int dr_bitmaps_to_rows_many(dr_ctx* ctx, const uint32_t* const* bitmaps, int n_bitmaps, int64_t n_rows,
+                            int32_t* const* out_rows, const int64_t* counts, void* stream) {
+    if (!ctx) return DR_ERR_INVALID;
+    if (n_bitmaps <= 0 || n_rows <= 0) return DR_OK;
+    DR_REQUIRE(ctx, bitmaps && out_rows && counts, "null pointer");
+    DR_REQUIRE(ctx, n_bitmaps <= DR_MAX_COUNT_MANY, "too many bitmaps for one call");
+    const int64_t n_words = (n_rows + 31) >> 5;
+    const int64_t n_blocks = (n_words + kWordsPerBlock - 1) / kWordsPerBlock;
+    DR_REQUIRE(ctx, n_blocks < 65536 * 16, "bitmap too large");
+    ManyBitmaps p;
+    ManyRows o;
+    bool any = false;
+    for (int i = 0; i < n_bitmaps; ++i) {
+        DR_REQUIRE(ctx, bitmaps[i] != nullptr && counts[i] >= 0 && (counts[i] == 0 || out_rows[i]), "null bitmap / list");
+        p.bm[i] = bitmaps[i];
+        o.out[i] = out_rows[i];
+        o.capacity[i] = counts[i];
+        any |= counts[i] > 0;
+    }
+    if (!any) return DR_OK;
+    int rc = dr_ensure_scratch(ctx, sizeof(unsigned long long) * (size_t)(n_blocks + 1) * (size_t)n_bitmaps);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* cnt = (unsigned long long*)ctx->scratch;
+    k_block_popc_many<<<dim3((unsigned)n_blocks, (unsigned)n_bitmaps), kThreads, 0, st>>>(p, n_rows, n_words,
+                                                                                       (int)n_blocks, cnt);
+    DR_LAUNCHED(ctx);
+    k_scan_counts_many<<<n_bitmaps, 1024, 0, st>>>(cnt, (int)n_blocks);
+    DR_LAUNCHED(ctx);
+    k_write_rows_many<<<dim3((unsigned)n_blocks, (unsigned)n_bitmaps), kThreads, 0, st>>>(p, o, n_rows, n_words,
+                                                                                       (int)n_blocks, cnt);
     DR_LAUNCHED(ctx);
     return DR_OK;
 }

@@ -17,10 +17,25 @@ __device__ __forceinline__ void rows_to_bitmap(int64_t n_rows, uint32_t* __restr
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_pad = (n_rows + 31) & ~(int64_t)31;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pad; r += stride) {
+    constexpr int kUnroll = 4;   // four independent rows per thread: their loads are in flight together
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; r + (kUnroll - 1) * stride < n_pad; r += kUnroll * stride) {
+        bool bit[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int64_t rr = r + j * stride;
+            bit[j] = rr < n_rows ? pred(rr) : false;
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const unsigned w = __ballot_sync(0xffffffffu, bit[j]);
+            if (lane == 0 && w != 0) atomicOr(bm + ((r + j * stride) >> 5), w);  // RED.OR: no load stall
+        }
+    }
+    for (; r < n_pad; r += stride) {
         const bool bit = r < n_rows ? pred(r) : false;
         const unsigned w = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0 && w != 0) atomicOr(bm + (r >> 5), w);  // RED.OR: no load stall in the stream
+        if (lane == 0 && w != 0) atomicOr(bm + (r >> 5), w);
     }
 }
 
@@ -108,7 +123,24 @@ __global__ void __launch_bounds__(kThreads) k_dc_fd_build_smem(const __grid_cons
     for (int i = threadIdx.x; i < key_space; i += kThreads) { s_lo[i] = INT32_MAX; s_hi[i] = INT32_MIN; }
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    constexpr int kUnroll = 4;   // loads of four rows first, then the table checks
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; r + (kUnroll - 1) * stride < n_rows; r += kUnroll * stride) {
+        int64_t key[kUnroll];
+        int v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            key[j] = row_key(k, r + j * stride);
+            v[j] = __ldcs(b_col + r + j * stride) + 1;
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            if (key[j] < 0 || key[j] >= key_space) continue;
+            if (v[j] < s_lo[key[j]]) atomicMin(s_lo + key[j], v[j]);
+            if (v[j] > s_hi[key[j]]) atomicMax(s_hi + key[j], v[j]);
+        }
+    }
+    for (; r < n_rows; r += stride) {
         const int64_t key = row_key(k, r);
         if (key < 0 || key >= key_space) continue;
         const int v = __ldcs(b_col + r) + 1;

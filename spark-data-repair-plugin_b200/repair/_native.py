@@ -91,6 +91,7 @@ _SIGNATURES = {
     "dr_bitmap_count": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dr_bitmap_count_many": (c_int, [c_void_p, _PP, c_int, c_int64, POINTER(c_int64), c_void_p]),
     "dr_bitmap_to_rows_async": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "dr_bitmaps_to_rows_many": (c_int, [c_void_p, _PP, c_int, c_int64, _PP, POINTER(c_int64), c_void_p]),
     "dr_bitmap_to_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dr_bitmap_rows_after_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "dr_tile_null_bitmaps": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
@@ -337,6 +338,14 @@ class Context:
         self._check(self.lib.dr_bitmap_to_rows_async(self._h, _dp(bitmap), n_rows, _dp(out_rows), count,
                                                      self._stream()))
 
+    def bitmaps_to_rows_many(self, bitmaps, n_rows, outs, counts):
+        """Ordered compaction of several bitmaps with known popcounts (three launches per 128 bitmaps)."""
+        for i in range(0, len(bitmaps), 128):
+            bp, _k1 = _ptr_array([b.data_ptr() for b in bitmaps[i:i + 128]])
+            op, _k2 = _ptr_array([o.data_ptr() if c else 0 for o, c in zip(outs[i:i + 128], counts[i:i + 128])])
+            self._check(self.lib.dr_bitmaps_to_rows_many(self._h, bp, len(bitmaps[i:i + 128]), n_rows, op,
+                                                         _i64_array(counts[i:i + 128]), self._stream()))
+
     def bitmap_to_rows(self, bitmap, n_rows, out_rows, capacity):
         n = c_int64()
         self._check(self.lib.dr_bitmap_to_rows(self._h, _dp(bitmap), n_rows, _dp(out_rows), capacity, byref(n),
@@ -505,7 +514,7 @@ def _profiled(name, fn):
 
 for _name in ("widen_u8", "h2d_copy", "d2h_copy", "index_presence", "index_remap", "ids_unique", "gather_i64", "valid_bits",
               "scan_hist", "lut_scan", "quartiles", "range_flag", "dc_const", "dc_fd_build", "dc_fd_flag", "bitmap_or",
-              "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
+              "bitmap_andnot", "bitmap_count", "bitmap_count_many", "bitmap_to_rows_async", "bitmaps_to_rows_many", "bitmap_to_rows", "bitmap_rows_after_count", "tile_null_bitmaps", "changed_bitmap", "bitmap_gather", "bitmap_clear_rows", "discretize",
               "pair_presence", "cooc", "cooc_skip", "key_presence", "key_flag", "dc_exists", "combine_counts", "dc_lt_flag",
               "dc_hash_build", "dc_hash_flag", "domain_score", "domain_prune", "gather_rows_masked", "tile_null_bitmap", "gather",
               "tile_gather", "lookup_sorted", "forest_predict", "forest_predict_ranked", "tile_fill", "gbdt_train"):

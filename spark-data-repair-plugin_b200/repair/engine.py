@@ -890,10 +890,17 @@ class Engine:
                         scored.append(pr)
         pres_launched = self.launch_pair_presence(scored) if scored and len(res.disc_attrs) <= 64 else None
         self.mark("detect:local 1 launched")
+        # (sharded: "did the presence sample cover every shard completely" rides in the same collective)
+        cover = None
+        if pres_launched and self.dist is not None:
+            cover = self.torch.tensor([1 if pres_launched[3] else 0], dtype=self.torch.int64, device=self.device)
         self.exchange(ex1 + [(h, "sum") for _, _, h in launched] +
-                      ([(pres_launched[2], "or")] if pres_launched else []))
+                      ([(pres_launched[2], "or")] if pres_launched else []) +
+                      ([(cover, "min")] if cover is not None else []))
         self._absorb_hists(launched)
-        presence = self.pair_presence_host(pres_launched) if pres_launched else None
+        presence = self.pair_presence_host(pres_launched, check_cover=False) if pres_launched else None
+        if cover is not None:
+            presence = (presence[0], presence[1], bool(int(cover.item())))
         self.mark("detect:hists + presence on the host")
         for fn in after:        # local 2: flags that needed the global tables / counts
             fn()

@@ -2,8 +2,9 @@
 sample, computes class weights / initial scores, runs the whole boosting loop on the device and
 flattens the result into the exchange format of ``forest.py``.
 
-Eligibility: every feature discrete (label-encoded attribute behind a sum / ordinal encoder), at most
-128 encoded features and 255 distinct values per feature.  Other models (continuous features) use
+Eligibility: every feature discrete (label-encoded attribute behind a sum / ordinal encoder) and at
+most 128 encoded features; a feature with more than 254 distinct encoded values is binned like
+LightGBM's max_bin does (adjacent values share a bin).  Other models (continuous features) use
 ``train.build_model`` (scikit-learn)."""
 import numpy as np
 
@@ -12,6 +13,7 @@ from .forest import encoder_lut
 NODE_DTYPE = np.dtype([("feature", np.int16), ("thr_bin", np.uint8), ("missing_left", np.uint8), ("left", np.uint8),
                        ("right", np.uint8), ("pad", np.uint8, (2,)), ("value", np.float64)])
 MAX_NODES = 64
+MAX_BINS = 254   # real bins per feature (one more is the missing bin; bins travel as bytes)
 
 
 def quant_bits(n_rows):
@@ -31,10 +33,25 @@ def bin_sample(encoders, sample_codes, dict_sizes):
         for j in range(lut.shape[1]):
             col = lut[:, j]
             vals = np.unique(col[~np.isnan(col)])
-            if len(vals) > 254:
-                return None
-            bin_of = np.full(len(col), len(vals), dtype=np.uint8)           # missing bin
             ok = ~np.isnan(col)
+            if len(vals) > MAX_BINS:
+                # more distinct values than bins (LightGBM: max_bin = 255, train.py:106): adjacent values
+                # share a bin, bins of about equal sample counts; thresholds only fall between bins
+                enc = col[codes + 1]
+                cnt = np.bincount(np.searchsorted(vals, enc[~np.isnan(enc)]), minlength=len(vals)).astype(np.float64)
+                edge = np.floor(np.cumsum(cnt) / max(cnt.sum(), 1.0) * MAX_BINS - 1e-9).astype(np.int64)
+                group = np.minimum(np.maximum.accumulate(np.clip(edge, 0, MAX_BINS - 1)), MAX_BINS - 1)
+                _, group = np.unique(group, return_inverse=True)      # dense bin ids, in value order
+                n_real = int(group.max()) + 1
+                upper = np.array([vals[group == b].max() for b in range(n_real)])
+                lower = np.array([vals[group == b].min() for b in range(n_real)])
+                bin_of = np.full(len(col), n_real, dtype=np.uint8)           # missing bin
+                bin_of[ok] = group[np.searchsorted(vals, col[ok])].astype(np.uint8)
+                cols.append(bin_of[codes + 1])
+                n_bins.append(n_real + 1)
+                values.append(np.stack([upper, lower]))
+                continue
+            bin_of = np.full(len(col), len(vals), dtype=np.uint8)           # missing bin
             bin_of[ok] = np.searchsorted(vals, col[ok]).astype(np.uint8)
             cols.append(bin_of[codes + 1])
             n_bins.append(len(vals) + 1)
@@ -107,12 +124,16 @@ def flatten(nodes, counts, init, bin_values, n_features, n_classes):
     feat = flat["feature"].astype(np.int32)
     leaf = feat < 0
     thr = np.zeros(len(flat))
-    max_bins = max(len(v) for v in bin_values)
-    tab = np.zeros((n_features, max_bins + 1))
-    for f, v in enumerate(bin_values):
-        tab[f, :len(v)] = v
+    # a bin holds one encoded value (1-D entry) or a run of adjacent values (2 x n entry: largest / smallest
+    # value of every bin): the threshold sits midway between the split bin's largest and the next bin's smallest
+    hi_lo = [(v, v) if np.ndim(v) == 1 else (v[0], v[1]) for v in bin_values]
+    max_bins = max(len(h) for h, _ in hi_lo)
+    tab_hi, tab_lo = np.zeros((n_features, max_bins + 1)), np.zeros((n_features, max_bins + 1))
+    for f, (h, l) in enumerate(hi_lo):
+        tab_hi[f, :len(h)] = h
+        tab_lo[f, :len(l)] = l
     fi, ti = np.where(leaf, 0, feat), flat["thr_bin"].astype(np.int64)
-    thr = np.where(leaf, 0.0, (tab[fi, ti] + tab[fi, np.minimum(ti + 1, max_bins)]) / 2.0)
+    thr = np.where(leaf, 0.0, (tab_hi[fi, ti] + tab_lo[fi, np.minimum(ti + 1, max_bins)]) / 2.0)
     return {
         "n_features": int(n_features), "n_classes": int(n_classes), "baseline": np.asarray(init, dtype=np.float64),
         "tree_seq": np.tile(np.arange(S, dtype=np.int32), n_iter), "tree_offset": tree_offset,

@@ -348,6 +348,7 @@ class RepairModel():
             dist = Dist(None if self.distributed is True else self.distributed)
             table = table.unify(dist, dt, ctx)
         engine = Engine(table, self.device_index, dist=dist, device_table=dt, ctx=ctx)
+        ingest["engine_ready_s"] = time.time() - t0
         try:
             detectors = self.error_detectors or default_detectors(self.targets, table.names)
             _logger.info("[Error Detection Phase] Used error detectors: {}".format(to_list_str(detectors)))
@@ -355,6 +356,7 @@ class RepairModel():
                                 self._given_cells(table))
             self.last_run = {"detect": res, "elapsed_detect": time.time() - t0}
             self.last_run.update(ingest)
+            self.last_run["detect_done_s"] = time.time() - t0
             if detect_errors_only:
                 return _maybe_arrow(self._cells_frame(engine, table, res), arrow_io)
             if sum((res.n_cells_global or res.n_cells).values()) == 0:
@@ -375,6 +377,7 @@ class RepairModel():
                 self.last_run["models"] = models
                 self.last_run["elapsed_training"] = time.time() - t1
                 out = repair_cells_encoded(self, engine, table, res, models, arrow=True)
+                self.last_run["repair_done_s"] = time.time() - t0
             else:
                 out = repair_cells(self, engine, table, res, continuous, repair_data, models=self.frozen_models)
             _logger.info("!!!Total Processing time is {}(s)!!!".format(time.time() - t0))
@@ -382,6 +385,7 @@ class RepairModel():
         finally:
             self.last_run["gpu_launches"] = engine.ctx.launch_count
             engine.close()
+            self.last_run["total_s"] = time.time() - t0
 
     # ---- pmf / score / maximal-likelihood modes (model.py:1350-1390) -------------------------------
     def _run_pmf_modes(self, engine, table, res, continuous, compute_repair_prob, compute_repair_score,
@@ -496,7 +500,7 @@ def _fit(rm, engine, encoders, codes, tile_col, features, dict_sizes, X, y_value
                     dm.predict(engine.ctx, work, K, None, 0, cells, len(va), tile_col[y])
                     pred = work[cells.to(engine.torch.int64), tile_col[y]].cpu().numpy()
                     scores.append(HS.score(y_values[va], pred, True))
-                return -float(np.mean(scores))
+                return -float(np.mean(scores)), [-float(v) for v in scores]
 
             params, _, n_eval = HS.search(evaluate, max_evals, no_progress, timeout)
             rm.last_run.setdefault("search", {})[y] = {"evals": n_eval, "params": params}
@@ -596,13 +600,26 @@ def run_chain(engine, table, models, tile, ctile, D):
     # a model only fills its own column, so the work-list sizes can all be taken now, in one round trip
     null_counts = engine.ctx.bitmap_count_many([all_null[i] for i in range(K)], D)
     engine.mark("chain:null bitmaps")
+    # the work lists of all discrete targets in one batched compaction (three launches instead of 2-3 per model)
+    disc = [y for y, _ in models if not table.by_name[y].continuous and null_counts[tile_col[y]] > 0]
+    lists = {}
+    if disc:
+        sizes = [null_counts[tile_col[y]] for y in disc]
+        flat = torch.empty(sum(sizes), dtype=torch.int32, device=engine.device)
+        outs, o = [], 0
+        for sz in sizes:
+            outs.append(flat[o:o + sz])
+            o += sz
+        engine.ctx.bitmaps_to_rows_many([all_null[tile_col[y]] for y in disc], D, outs, sizes)
+        lists = dict(zip(disc, outs))
+    empty = torch.zeros(0, dtype=torch.int32, device=engine.device)
     for y, m in models:
         ycol = table.by_name[y]
         if ycol.continuous:
             engine.ctx.tile_null_bitmap(ctile, D, n_cc, cont_idx[y], nullbits, f64=True)
             todo = engine.bitmap_rows(nullbits, D)
         else:
-            todo = engine.bitmap_rows(all_null[tile_col[y]], D, count=null_counts[tile_col[y]])
+            todo = lists.get(y, empty)
         n = int(todo.numel())
         engine.mark("chain:cells of " + y)
         if n == 0:
@@ -800,11 +817,12 @@ def repair_cells_encoded(rm, engine, table, res, models, arrow=False):
     rep_all = torch.empty(E, dtype=torch.int32, device=engine.device)
     seg, off = [], 0
     for a in attrs:
-        n = res.n_cells[a]
-        rows = engine.bitmap_rows(res.bitmaps[a], out=rows_all[off:off + n], count=n)
-        engine.ctx.gather(engine.dt.col(a), rows, n, cur_all[off:off + n])
-        seg.append((a, off, n))
-        off += n
+        seg.append((a, off, res.n_cells[a]))
+        off += res.n_cells[a]
+    engine.ctx.bitmaps_to_rows_many([res.bitmaps[a] for a in attrs], engine.n_rows,
+                                    [rows_all[o:o + n] for _, o, n in seg], [n for _, _, n in seg])
+    for a, o, n in seg:
+        engine.ctx.gather(engine.dt.col(a), rows_all[o:o + n], n, cur_all[o:o + n])
     engine.mark("repair:cell lists")
     drows, tile, ctile = engine.build_dirty_tile(res, targets)
     D = int(drows.numel())

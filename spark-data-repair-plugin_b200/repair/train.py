@@ -126,7 +126,7 @@ def build_model(X, y, is_discrete, num_class, opts):
                 est = sklearn_estimator(is_discrete, opts, params)
                 est.fit(X[tr], yv[tr])
                 scores.append(HS.score(yv[va], est.predict(X[va]), is_discrete))
-            return -float(np.mean(scores))
+            return -float(np.mean(scores)), [-float(v) for v in scores]
 
         params, _, _ = HS.search(evaluate, max_evals, no_progress, timeout)
         est = sklearn_estimator(is_discrete, opts, params)

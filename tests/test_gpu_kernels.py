@@ -191,6 +191,14 @@ def test_bitmap_ops(ctx, n):
     rows2 = torch.full((max(cnt, 1),), -7, dtype=torch.int32, device="cuda")
     ctx.bitmap_to_rows_async(da, n, rows2, cnt)
     assert np.array_equal(rows2[:cnt].cpu().numpy(), np.nonzero(bits_a)[0].astype(np.int32))
+    # ordered compaction of several bitmaps at once (an empty one among them is skipped)
+    zero = torch.zeros_like(da)
+    cb = int(bits_b0.sum())
+    outs = [torch.full((max(c, 1),), -7, dtype=torch.int32, device="cuda") for c in (cnt, 0, cb)]
+    ctx.bitmaps_to_rows_many([da, zero, db], n, outs, [cnt, 0, cb])
+    assert np.array_equal(outs[0][:cnt].cpu().numpy(), np.nonzero(bits_a)[0].astype(np.int32))
+    assert np.array_equal(outs[2][:cb].cpu().numpy(), np.nonzero(bits_b0)[0].astype(np.int32))
+    assert int(outs[1][0]) == -7
     d2 = da.clone()
     ctx.bitmap_or(d2, db, n)
     if n:  # whole words are combined; n == 0 touches nothing
