@@ -7,7 +7,7 @@ import numpy as np
 import pandas as pd
 
 from . import catalog
-from .utils import AnalysisException, argtype_check
+from .utils import AnalysisException, argtype_check, row_positions
 
 
 def _to_double(v):
@@ -58,19 +58,16 @@ class RepairMisc():
             raise AnalysisException("Table '{}' must have '{}', 'attribute', and 'repaired' columns".format(
                 self.opts["repair_updates"], row_id))
         out = table.copy()
-        pos = {}
-        for i, k in enumerate(out[row_id].tolist()):
-            pos[str(k)] = i
+        ids = out[row_id].to_numpy()
         for attr, grp in updates.groupby("attribute", sort=False):
             if attr not in out.columns or attr == row_id:
                 continue
             col = out[attr]
-            rows, vals = [], []
-            for k, v in zip(grp[row_id].tolist(), grp["repaired"].tolist()):
-                i = pos.get(str(k))
-                if i is not None:
-                    rows.append(i)
-                    vals.append(None if v is None or (isinstance(v, float) and v != v) else v)
+            # vectorised join on the row id (no Python dict over the table's rows)
+            pos, found = row_positions(ids, grp[row_id].to_numpy())
+            rows = pos[found].tolist()
+            vals = [None if v is None or (isinstance(v, float) and v != v) else v
+                    for v, f in zip(grp["repaired"].tolist(), found.tolist()) if f]
             if not rows:
                 continue
             if pd.api.types.is_integer_dtype(col.dtype):

@@ -3,11 +3,11 @@ the B200 pipeline.  Setter names, argument checks, option keys, error messages, 
 the output schema ``(row_id, attribute, current_value, repaired)`` are the reference's; the work
 behind ``run()`` is ``engine.Engine`` (CUDA) instead of Spark SQL + pandas UDFs.
 
-Inputs: a pandas ``DataFrame`` (a pyspark ``DataFrame`` is collected once with ``toPandas()``), the
-name of a table registered in ``repair.catalog``, or a pre-encoded ``EncodedTable``.
-Modes implemented in this version: default, ``detect_errors_only``, ``repair_data``; the pmf /
-score / maximal-likelihood modes validate their arguments like the reference and then raise
-``NotImplementedError`` ("next").
+Inputs: a pandas ``DataFrame`` (a pyspark ``DataFrame`` is collected once with ``toPandas()``), a
+``pyarrow.Table`` (``setArrowInput``: device-side ingest, Arrow frame out), the name of a table
+registered in ``repair.catalog``, or a pre-encoded ``EncodedTable``.  Every running mode of the
+reference is implemented: default, ``detect_errors_only``, ``repair_data``, the pmf / prob / score modes
+and maximal-likelihood repair.
 """
 import logging
 import time
@@ -24,7 +24,7 @@ from .errors import ErrorDetector, ErrorModelOptions, default_detectors
 from .forest import DeviceModel, encode_matrix, encoder_type, first_seen
 from .table import EncodedTable
 from .train import build_model, train_option_keys, validate_options
-from .utils import argtype_check, cell_to_string, get_option_value, to_list_str
+from .utils import argtype_check, cell_to_string, get_option_value, row_positions, to_list_str
 
 _logger = logging.getLogger("repair")
 
@@ -264,13 +264,10 @@ class RepairModel():
             return None
         df = self.error_cells if isinstance(self.error_cells, DataFrame) else catalog.table(str(self.error_cells))
         keep = set(self.targets) if self.targets else set(table.names) | {table.row_id}
-        pos_of = {str(v): i for i, v in enumerate(table.row_ids.tolist())}
-        positions, attrs = [], []
-        for rid, a in zip(df[str(self.row_id)].tolist(), df["attribute"].tolist()):
-            if a in keep and a in table.by_name and str(rid) in pos_of:
-                positions.append(pos_of[str(rid)])
-                attrs.append(a)
-        return positions, attrs
+        attr = df["attribute"].to_numpy(dtype=object)
+        pos, found = row_positions(table.row_ids, df[str(self.row_id)].to_numpy())
+        ok = found & np.array([a in keep and a in table.by_name for a in attr.tolist()], dtype=bool)
+        return pos[ok].tolist(), attr[ok].tolist()
 
     # ---- run -------------------------------------------------------------------------------------
     def run(self, detect_errors_only: bool = False, compute_repair_candidate_prob: bool = False,
@@ -415,10 +412,14 @@ class RepairModel():
         top = P.maximal_likelihood_repair(scored, int(self.repair_delta))
         if repair_data:
             frame = self._input_frame(table)
-            pos_of = {v: i for i, v in enumerate(table.row_ids.tolist())}
-            for r, a, _, rep in top:
+            pos, _ = row_positions(table.row_ids, [r for r, _, _, _ in top])
+            by_attr: Dict[str, Any] = {}
+            for p_, (_, a, _, rep) in zip(pos.tolist(), top):
+                by_attr.setdefault(a, []).append((p_, rep))
+            for a, cells in by_attr.items():
                 col = frame[a].to_numpy(dtype=object, copy=True)
-                col[pos_of[r]] = rep
+                for p_, rep in cells:
+                    col[p_] = rep
                 frame[a] = col
             return frame
         return DataFrame({rid: [c[0] for c in top], "attribute": [c[1] for c in top],

@@ -191,3 +191,34 @@ def cell_to_string(kind, v):
     if v != v:
         return None
     return str(int(v)) if kind == "int" else double_to_string(v)
+
+
+def row_positions(row_ids, wanted):
+    """Vectorised join of `wanted` row ids against the table's `row_ids` (compared as strings, like the
+    reference's CAST(.. AS STRING) joins): -> (positions int64, found bool) per wanted id.  No Python dict
+    over the table: integer ids take a binary search (directly when the ids are increasing, else through one
+    argsort), everything else pandas' hashed ``Index.get_indexer``."""
+    import numpy as np
+    import pandas as pd
+    ids = np.asarray(row_ids)
+    want = np.asarray(list(wanted) if not isinstance(wanted, np.ndarray) else wanted)
+    n = len(ids)
+    if n == 0 or len(want) == 0:
+        return np.zeros(len(want), dtype=np.int64), np.zeros(len(want), dtype=bool)
+    if ids.dtype.kind in "iu":
+        as_int = pd.to_numeric(pd.Series(want), errors="coerce")
+        ok = as_int.notna().to_numpy() & (as_int.fillna(0) % 1 == 0).to_numpy()
+        w = as_int.fillna(0).to_numpy().astype(np.int64)
+        if bool(np.all(ids[1:] > ids[:-1])):
+            pos = np.searchsorted(ids, w)
+            pos = np.minimum(pos, n - 1)
+            found = ok & (ids[pos] == w)
+        else:
+            order = np.argsort(ids, kind="stable")
+            p = np.minimum(np.searchsorted(ids[order], w), n - 1)
+            pos = order[p]
+            found = ok & (ids[pos] == w)
+        return pos.astype(np.int64), found
+    idx = pd.Index(pd.Series(ids).astype(str))
+    pos = idx.get_indexer(pd.Index(pd.Series(want).astype(str)))
+    return np.maximum(pos, 0).astype(np.int64), pos >= 0
