@@ -8,6 +8,7 @@ import numpy as np
 from .utils import AnalysisException, cell_to_string
 
 _SUPPORTED_MSG = "tinyint,float,smallint,string,double,int,bigint"  # RepairBase.scala:41-44 order as Spark prints it
+INGEST_GROUP_COLS = 8   # Arrow columns per copy / encode group of the device-side ingest
 ROW_ALIGN = 128  # rows are padded so that every column starts 512-byte aligned (128-bit loads)
 
 
@@ -352,18 +353,72 @@ class EncodedTable:
         if n_pad > n:
             codes[:, n:].fill_(-1)
         al = lambda b: (b + 255) // 256 * 256
-        budget = 8 << 30   # raw bytes staged on the device at a time
-        g0 = 0
+        # Columns travel in groups: while the worker threads copy group g + 1, the device finds the dictionary
+        # entries of group g that occur (side stream), and group g's indices are re-encoded as soon as its
+        # dictionaries are sorted -- only the last group's encode is not hidden behind a copy.
+        budget = 4 << 30   # raw bytes of one group on the device
+        side = torch.cuda.Stream(device=device)
         t_copy = t_remap = 0.0
+        keep_alive = []
+
+        def launch_presence(g0, g1, where):
+            uoff = [0]
+            for i in range(g0, g1):
+                uoff.append(uoff[-1] + (len(plan[i][0]) + 31) // 32)
+            with torch.cuda.stream(side):
+                used = torch.zeros(max(uoff[-1], 1), dtype=torch.int32, device=device)
+                for i in range(g0, g1):
+                    entries, width, parts = plan[i]
+                    if not entries:
+                        continue
+                    for j, (_, _, _, bo, r) in enumerate(parts):
+                        d_idx, d_val = where[(i, j)]
+                        ctx.index_presence(d_idx, width, d_val, bo, r, len(entries), used[uoff[i - g0]:])
+                used_h = torch.empty(used.shape, dtype=torch.int32, pin_memory=True)
+                used_h.copy_(used, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
+            return uoff, used, used_h, done
+
+        def finish(g0, g1, where, pres):
+            """Sorted dictionaries of the group (host, one entry per distinct value) -> LUTs -> re-encode."""
+            uoff, used, used_h, done = pres
+            done.synchronize()
+            bits_all = used_h.numpy().view(np.uint32)
+            luts, loff = [], [0]
+            for i in range(g0, g1):
+                entries = plan[i][0]
+                bits = np.unpackbits(bits_all[uoff[i - g0]:uoff[i - g0 + 1]].view(np.uint8),
+                                     bitorder="little")[:len(entries)]
+                dictionary, lut = _sorted_dictionary(entries, bits.astype(bool))
+                luts.append(lut)
+                loff.append(loff[-1] + len(lut))
+                table_cols[i] = Column(attrs[i], "str", dictionary, None, None)
+            with torch.cuda.stream(side):
+                d_lut = torch.from_numpy(np.concatenate(luts + [np.zeros(1, dtype=np.int32)])).to(device)
+                for i in range(g0, g1):
+                    entries, width, parts = plan[i]
+                    row = 0
+                    for j, (_, _, _, bo, r) in enumerate(parts):
+                        d_idx, d_val = where[(i, j)]
+                        ctx.index_remap(d_idx, width, d_val, bo, r, d_lut.data_ptr() + 4 * loff[i - g0], len(entries),
+                                        codes[i].data_ptr() + 4 * row)
+                        row += r
+            keep_alive.append((d_lut, used, used_h))
+
+        side.wait_stream(torch.cuda.current_stream())   # (the padding fill of `codes`)
+        pending = None
+        g0 = 0
         while g0 < len(attrs):
             g1, total = g0, 0
-            while g1 < len(attrs):
+            while g1 < len(attrs) and g1 - g0 < INGEST_GROUP_COLS:
                 need = sum(al(r * plan[g1][1]) + (al((r + bo + 7) // 8) if va else 0) for _, _, va, bo, r in plan[g1][2])
                 if g1 > g0 and total + need > budget:
                     break
                 total += need
                 g1 += 1
             stage = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+            keep_alive.append(stage)
             base = stage.data_ptr()
             src, dst, size, where, pos = [], [], [], {}, 0
             for i in range(g0, g1):
@@ -380,43 +435,22 @@ class EncodedTable:
                         pos += al(nb)
                     where[(i, j)] = (d_idx, d_val)
             t1 = time.perf_counter()
-            ctx.h2d_copy(src, dst, size, threads)
+            ctx.h2d_copy(src, dst, size, threads)        # blocks; the previous group's kernels run meanwhile
             t_copy += time.perf_counter() - t1
             t1 = time.perf_counter()
-            # which dictionary entries occur (one small read-back for the whole group)
-            uoff = [0]
-            for i in range(g0, g1):
-                uoff.append(uoff[-1] + (len(plan[i][0]) + 31) // 32)
-            used = torch.zeros(max(uoff[-1], 1), dtype=torch.int32, device=device)
-            for i in range(g0, g1):
-                entries, width, parts = plan[i]
-                if not entries:
-                    continue
-                for j, (_, _, _, bo, r) in enumerate(parts):
-                    d_idx, d_val = where[(i, j)]
-                    ctx.index_presence(d_idx, width, d_val, bo, r, len(entries), used[uoff[i - g0]:])
-            used_h = used.cpu().numpy().view(np.uint32)
-            luts, loff = [], [0]
-            for i in range(g0, g1):
-                entries = plan[i][0]
-                bits = np.unpackbits(used_h[uoff[i - g0]:uoff[i - g0 + 1]].view(np.uint8), bitorder="little")[:len(entries)]
-                dictionary, lut = _sorted_dictionary(entries, bits.astype(bool))
-                luts.append(lut)
-                loff.append(loff[-1] + len(lut))
-                table_cols[i] = Column(attrs[i], "str", dictionary, None, None)
-            d_lut = torch.from_numpy(np.concatenate(luts + [np.zeros(1, dtype=np.int32)])).to(device)
-            for i in range(g0, g1):
-                entries, width, parts = plan[i]
-                row = 0
-                for j, (_, _, _, bo, r) in enumerate(parts):
-                    d_idx, d_val = where[(i, j)]
-                    ctx.index_remap(d_idx, width, d_val, bo, r, d_lut.data_ptr() + 4 * loff[i - g0], len(entries),
-                                    codes[i].data_ptr() + 4 * row)
-                    row += r
-            torch.cuda.current_stream().synchronize()
+            pres = launch_presence(g0, g1, where)
+            if pending is not None:
+                finish(*pending)
+            pending = (g0, g1, where, pres)
             t_remap += time.perf_counter() - t1
-            del stage
             g0 = g1
+        t1 = time.perf_counter()
+        if pending is not None:
+            finish(*pending)
+        torch.cuda.current_stream().wait_stream(side)
+        side.synchronize()
+        keep_alive.clear()
+        t_remap += time.perf_counter() - t1
 
         def ids_host():
             return np.asarray(ids_col.to_numpy(zero_copy_only=False))

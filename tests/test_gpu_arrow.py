@@ -59,10 +59,13 @@ def _synthetic(n=3000, seed=5):
 
 
 @pytest.mark.parametrize("variant", ["plain", "dict8", "dict32_unused", "dict_u8", "chunked", "sliced", "offset5"])
-def test_device_ingest_equals_host_ingest(variant):
+def test_device_ingest_equals_host_ingest(variant, monkeypatch):
     import torch
+    from repair import table as T
     from repair._native import Context
     from repair.table import EncodedTable
+    if variant in ("chunked", "dict8"):
+        monkeypatch.setattr(T, "INGEST_GROUP_COLS", 1 if variant == "chunked" else 3)   # several pipelined groups
     df = _synthetic()
     tbl = _arrow_variants(df)[variant]
     want = EncodedTable.from_arrow(tbl, "tid")

@@ -69,6 +69,21 @@ def _worker(rank, world, port, backend, out_dir):
         td.all_gather_object(gathered, got)
         result[mode] = sorted((t for part in gathered for t in part), key=lambda t: (int(t[0]), t[1]))
         assert rm.last_run["gpu_launches"] > 0
+    # the same shard as a pyarrow.Table whose dictionaries are rank-local (first-seen order, only the values
+    # the shard holds): device-side ingest + dictionary unification on the device must give the same repairs
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from repair import RepairModel
+    cols = {"tid": pa.array(np.arange(lo, hi, dtype=np.int64))}
+    for nm, c in zip(names, mine):
+        strs = pa.array([None if v < 0 else "v%03d" % v for v in c.tolist()], type=pa.string())
+        cols[nm] = pc.dictionary_encode(strs)
+    rma = RepairModel().setArrowInput(pa.table(cols)).setRowId("tid").setErrorDetectors(PU.make_detectors(_specs()))
+    for k, v in OPTS.items():
+        rma.option(k, str(v))
+    frame = rma.setDistributed(True, dev).run()
+    assert isinstance(frame, pa.Table)
+    assert PU.frame_tuples(frame.to_pandas(), "tid") == got, "Arrow ingest of the shard differs from the encoded input"
     if rank == 0:
         full = EncodedTable.from_codes("tid", names, synth.generate_numpy(spec), spec.dom)
         for mode in ("detect", "repair"):
