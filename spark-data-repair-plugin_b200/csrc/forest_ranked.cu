@@ -136,10 +136,19 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
     unsigned char* s_feat = smem_raw + kStages * sizeof(ChunkBuf) + kStages * 16;
     const int t = threadIdx.x;
     const int depth = F.max_depth;
-    // the CTA's chunk stream: every tile it owns walks chunks 0 .. n_chunks - 1; chunk k of the stream
-    // lives in buffer k % kStages
-    const int64_t first = (int64_t)blockIdx.x * T, step = (int64_t)gridDim.x * T;
-    const uint32_t n_tiles = first < p.n_cells ? (uint32_t)((p.n_cells - first + step - 1) / step) : 0u;
+    // Balanced partition: every CTA owns a contiguous, equal share of the cells and walks it in n_tiles
+    // EQUAL tiles of tile_cells <= T cells (a multiple of 32).  A tile pass costs what its warps cost (the
+    // kernel is bound by shared-memory wavefronts, i.e. by active warps), so a share of 845 cells is two
+    // passes of 14 warps instead of a full one and a 333-cell one that both wait for every chunk: the
+    // surplus warps of the CTA retire right after the set-up.  The CTA's chunk stream: every tile walks
+    // chunks 0 .. n_chunks - 1; chunk k of the stream lives in buffer k % kStages.
+    const int64_t c0 = (p.n_cells * (int64_t)blockIdx.x / (int64_t)gridDim.x + 31) & ~(int64_t)31;
+    const int64_t c1_raw = (p.n_cells * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x + 31) & ~(int64_t)31;
+    const int64_t c1 = blockIdx.x + 1 == gridDim.x ? p.n_cells : (c1_raw < p.n_cells ? c1_raw : p.n_cells);
+    const int64_t share = c1 > c0 ? c1 - c0 : 0;
+    const uint32_t n_tiles = (uint32_t)((share + T - 1) / T);
+    const int tile_cells = n_tiles ? (int)((((share + n_tiles - 1) / n_tiles) + 31) & ~(int64_t)31) : 0;
+    const uint32_t n_warps = (uint32_t)(tile_cells / 32);   // warps that take part in the chunk hand-over
     const uint32_t n_stream = n_tiles * (uint32_t)F.n_chunks;
 
     auto issue = [&](uint32_t k) {  // one thread: start the TMA copies of stream chunk k
@@ -163,6 +172,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         for (uint32_t k = 0; k < (uint32_t)kStages && k < n_stream; ++k) issue(k);
     }
     __syncthreads();  // the only CTA-wide barrier: from here on warps meet through the mbarriers / counters
+    if (t >= tile_cells) return;  // (whole warps: tile_cells is a multiple of 32)
 
     // ---- consumer warps: one cell per thread; the feature tile is private to the thread ----
     unsigned char* my_feat = kWide ? s_feat + 4 * t : s_feat + (size_t)t * p.feat_stride;
@@ -170,9 +180,10 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
     const uint32_t feat = kWide ? smem_u32(s_feat) : smem_u32(my_feat);
     const uint32_t lane_off = 4u * (uint32_t)t;
     uint32_t k = 0;
-    for (int64_t base = (int64_t)blockIdx.x * T; base < p.n_cells; base += (int64_t)gridDim.x * T) {
-        const int64_t i = base + t;
-        const bool live = i < p.n_cells;
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        const int64_t i = c0 + (int64_t)tile * tile_cells + t;
+        const bool live = i < c1;
+        const bool warp_live = (i - (t & 31)) < c1;   // (warp-uniform: does lane 0 of this warp have a cell)
         const int64_t row = live ? p.cells[i] : 0;
         {
             // rank tile of this thread's cell (eight slots at a time, loads first: the tile row and the
@@ -232,7 +243,8 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             const uint32_t nodes = smem_u32(buf[b].node);
             const double* __restrict__ leaves = buf[b].leaf;
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
-            const int n_trees = F.chunk_tree_off[c + 1] - F.chunk_tree_off[c];
+            // a warp without a live cell (the tail of the share's last tile) only takes part in the hand-over
+            const int n_trees = warp_live ? F.chunk_tree_off[c + 1] - F.chunk_tree_off[c] : 0;
             for (int q = 0; q < n_trees; q += kIlp) {
                 uint32_t w[kIlp];
                 int lb[kIlp];
@@ -278,7 +290,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             __syncwarp();
             if ((t & 31) == 0) {
                 __threadfence_block();
-                if (atomicAdd(&done[b], 1u) == (uint32_t)(T / 32 - 1)) {
+                if (atomicAdd(&done[b], 1u) == n_warps - 1u) {
                     done[b] = 0;
                     __threadfence_block();
                     if (k + kStages < n_stream) {

@@ -207,6 +207,29 @@ class Context:
             self.lib.dr_ctx_destroy(self._h)
             self._h = None
 
+    # One pooled context per device for the public API: a RepairModel.run() borrows it instead of creating
+    # (cudaMallocHost + cudaMalloc) and destroying (cudaFree: a device synchronisation) its own, and the scratch
+    # buffer it has grown stays grown for the next run.  A dr_ctx is not thread-safe: one run at a time per device.
+    _pool = {}
+
+    @classmethod
+    def acquire(cls, device_index):
+        ctx = cls._pool.pop(int(device_index), None)
+        if ctx is None or not getattr(ctx, "_h", None):
+            ctx = cls(device_index)
+        ctx.profile = None
+        ctx.launches_at_acquire = ctx.launch_count
+        return ctx
+
+    @classmethod
+    def release(cls, ctx):
+        if ctx is None or not getattr(ctx, "_h", None):
+            return
+        if int(ctx.device_index) in cls._pool:
+            ctx.close()
+        else:
+            cls._pool[int(ctx.device_index)] = ctx
+
     def __del__(self):
         try:
             self.close()

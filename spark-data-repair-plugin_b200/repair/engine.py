@@ -115,6 +115,31 @@ class Dist:
             t.copy_(buf[lo:hi].view(t.shape))
 
 
+class _PresenceMap:
+    """{(x, y): bool [dom_x + 1, dom_y + 1]} over the packed presence bits of a pair_presence launch; a
+    pair's matrix is only unpacked when somebody asks for it (the skip tables of the few counted pairs)."""
+
+    def __init__(self, pairs, offs, words, dom):
+        self._at = {p: q for q, p in enumerate(pairs)}
+        self._offs, self._words, self._dom, self._cache = offs, words, dom, {}
+
+    def __contains__(self, key):
+        return key in self._at
+
+    def __getitem__(self, key):
+        if key not in self._cache:
+            q = self._at[key]
+            x, y = key
+            n_e = (self._dom[x] + 1) * (self._dom[y] + 1)
+            w = self._words[self._offs[q]:self._offs[q + 1]]
+            b = np.unpackbits(w.view(np.uint8), bitorder="little")[:n_e].astype(bool)
+            self._cache[key] = b.reshape(self._dom[x] + 1, self._dom[y] + 1)
+        return self._cache[key]
+
+    def get(self, key, default=None):
+        return self[key] if key in self._at else default
+
+
 class DetectResult:
     def __init__(self):
         self.bitmaps = {}            # attr -> device int32 words (noisy / error cells)
@@ -133,7 +158,8 @@ class Engine:
     def __init__(self, table, device_index=0, dist=None, device_table=None, ctx=None):
         import torch
         self.torch = torch
-        self.ctx = ctx if ctx is not None else Context(device_index)
+        self.ctx = ctx if ctx is not None else Context.acquire(device_index)
+        self._launches0 = self.ctx.launch_count
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
         self.table = table
@@ -607,7 +633,7 @@ class Engine:
         return pairs, offs, bits, covers
 
     def pair_presence_host(self, launched, check_cover=True):
-        """-> ({frozenset pair: distinct count seen}, {pair: bool [dom_x+1, dom_y+1]}, exact)"""
+        """-> ({frozenset pair: distinct count seen}, {pair: bool [dom_x+1, dom_y+1]} (decoded on demand), exact)"""
         pairs, offs, bits, covers = launched
         words = bits.cpu().numpy().view(np.uint32)
         exact = covers
@@ -615,14 +641,15 @@ class Engine:
             t = self.torch.tensor([1 if covers else 0], dtype=self.torch.int64, device=self.device)
             self.dist.min_(t)
             exact = bool(int(t.item()))
-        nnz, present = {}, {}
-        for q, (x, y) in enumerate(pairs):
-            w = words[offs[q]:offs[q + 1]]
-            n_e = (self.disc_dom[x] + 1) * (self.disc_dom[y] + 1)
-            b = np.unpackbits(w.view(np.uint8), bitorder="little")[:n_e].astype(bool)
-            present[(x, y)] = b.reshape(self.disc_dom[x] + 1, self.disc_dom[y] + 1)
-            nnz[frozenset((x, y))] = int(b.sum())
-        return nnz, present, exact
+        # distinct counts of all pairs at once: popcount per word, summed per pair segment (bits past a pair's
+        # last entry are never set by the kernel)
+        pc = np.unpackbits(words.view(np.uint8)).reshape(-1, 32).sum(axis=1, dtype=np.int64) if len(words) else \
+            np.zeros(0, dtype=np.int64)
+        cum = np.concatenate([[0], np.cumsum(pc)])
+        o = np.asarray(offs, dtype=np.int64)
+        counts = cum[np.minimum(o[1:], len(pc))] - cum[np.minimum(o[:-1], len(pc))]
+        nnz = {frozenset(p): int(c) for p, c in zip(pairs, counts.tolist())}
+        return nnz, _PresenceMap(pairs, offs, words, self.disc_dom), exact
 
     def pair_nnz_lower_bounds(self, pairs):
         """distinct-pair counts on a row sample (exact when the sample covers the table)."""
@@ -1042,5 +1069,10 @@ class Engine:
         self._raw_cache = {}
         self.disc_cols, self.disc_dom = {}, {}
 
+    @property
+    def launches(self):
+        """Kernels launched through this engine's context since the engine was created."""
+        return self.ctx.launch_count - self._launches0
+
     def close(self):
-        self.ctx.close()
+        Context.release(self.ctx)

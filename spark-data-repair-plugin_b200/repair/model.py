@@ -305,17 +305,19 @@ class RepairModel():
         from ._native import Context
         from .engine import Dist, Engine
         ctx = dt = table = None
+        launches0 = 0
         ingest: Dict[str, Any] = {}
         arrow_io = _is_arrow_table(self.input)
         if arrow_io:
             # raw Arrow buffers -> device, encoded there (no per-row host work); None = needs the host path
             import torch
-            ctx = Context(self.device_index)
+            ctx = Context.acquire(self.device_index)
+            launches0 = ctx.launch_count
             try:
                 got = EncodedTable.from_arrow_device(self.input, str(self.row_id), ctx,
                                                      torch.device("cuda", self.device_index), timings=ingest)
             except Exception:
-                ctx.close()
+                Context.release(ctx)
                 raise
             if got is not None:
                 table, dt = got
@@ -380,7 +382,7 @@ class RepairModel():
             _logger.info("!!!Total Processing time is {}(s)!!!".format(time.time() - t0))
             return _maybe_arrow(out, arrow_io)
         finally:
-            self.last_run["gpu_launches"] = engine.ctx.launch_count
+            self.last_run["gpu_launches"] = engine.launches + (engine._launches0 - launches0 if ctx is not None else 0)
             engine.close()
             self.last_run["total_s"] = time.time() - t0
 
