@@ -397,8 +397,11 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  *              add, load word[bits 8-23].  A LEAF is (own index << 8): slot 0, never carries, the
  *              walk stays put -- every tree is walked max_depth levels without a branch.
  *   leaf values: the LAST level only computes the index c of the node the walk ends on (no load of
- *              that node's word); its value is leaf_value[chunk_leaf_off[chunk] + bias + c], where
- *              bias (signed) is the second header word of the tree.  The host orders the nodes of a
+ *              that node's word); its value is slot chunk_leaf_off[chunk] + bias + c of the leaf table, where
+ *              bias (signed) is the second header word of the tree.  The table is stored as 32-bit words,
+ *              chunk by chunk: chunk c with L = chunk_leaf_off[c+1] - chunk_leaf_off[c] slots occupies
+ *              leaf_value[2 * chunk_leaf_off[c] ..): the L low words of its float64 values, then the L high
+ *              words (two conflict-free 32-bit shared-memory loads instead of one 64-bit load).  The host orders the nodes of a
  *              tree so that all leaves sit in its tail and stores values for that tail only.
  *   max_depth: deepest leaf of any tree.
  *   Forest chunks are streamed into shared memory by the TMA engine (cp.async.bulk, double buffered).
@@ -406,9 +409,9 @@ int dr_forest_predict(dr_ctx* ctx, const dr_forest* forest, int32_t* tile, int n
  *   sequence chunk_seq[c] (never straddling a sequence; every sequence has at least one tree), at
  *   most DR_RANKED_CHUNK_TREES trees, DR_RANKED_CHUNK_NODES node words and DR_RANKED_CHUNK_LEAVES leaf
  *   values; its words are node_word[chunk_node_off[c] .. chunk_node_off[c+1]), its leaf values
- *   leaf_value[chunk_leaf_off[c] ..), its tree headers tree_hdr[2 * chunk_hdr_off[c] ..): two words
- *   per tree = (root node word, value bias).  chunk_node_off is a multiple of 4, chunk_leaf_off and
- *   chunk_hdr_off multiples of 2 (16-byte TMA granules). */
+ *   the leaf planes described above, its tree headers tree_hdr[2 * chunk_hdr_off[c] ..): two words
+ *   per tree = (root node word, value bias).  chunk_node_off and chunk_leaf_off are multiples of 4,
+ *   chunk_hdr_off a multiple of 2 (16-byte TMA granules). */
 #define DR_RANKED_CHUNK_NODES 4096
 #define DR_RANKED_CHUNK_LEAVES 2560
 #define DR_RANKED_CHUNK_TREES 256
@@ -423,7 +426,7 @@ typedef struct dr_forest_ranked {
     const int32_t* chunk_hdr_off;
     const uint32_t* tree_hdr;
     const uint32_t* node_word;
-    const double* leaf_value;
+    const uint32_t* leaf_value;   /* float64 leaf values, per chunk: low words of its leaves, then high words */
     const double* baseline;
     const int32_t* slot_col;      /* int32[n_slots]: tile column the slot reads */
     const int32_t* rank_lut_off;  /* int32[n_slots + 1] */

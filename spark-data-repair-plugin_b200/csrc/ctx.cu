@@ -3,7 +3,7 @@
 
 extern "C" {
 
-int dr_abi_version(void) { return 3; }
+int dr_abi_version(void) { return 4; }
 
 int dr_ctx_create(int device, dr_ctx** out) {
     if (!out) return DR_ERR_INVALID;

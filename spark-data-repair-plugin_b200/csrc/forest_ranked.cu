@@ -117,8 +117,21 @@ __device__ __forceinline__ uint32_t last_node(uint32_t w, uint32_t feat, uint32_
 
 constexpr int kChunkTrees = DR_RANKED_CHUNK_TREES;
 
+// value of chunk-relative leaf slot `at`: low and high word planes, kChunkLeaves words apart
+__device__ __forceinline__ double leaf_value(uint32_t planes, int at) {
+    const uint32_t a = planes + 4u * (uint32_t)at;
+    uint32_t lo, hi;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(hi) : "r"(a), "n"(DR_RANKED_CHUNK_LEAVES * 4));
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 struct __align__(16) ChunkBuf {
-    double leaf[kChunkLeaves];
+    // float64 leaf values as two planes of 32-bit words: a 64-bit load of 32 random leaves costs 3 wavefronts
+    // (measured: leaves l and l + 16 of a tree share a bank pair), two 32-bit loads of <= 31 consecutive
+    // words are conflict free, 2 wavefronts
+    uint32_t leaf_lo[kChunkLeaves];
+    uint32_t leaf_hi[kChunkLeaves];
     uint32_t node[kChunkNodes];
     uint2 hdr[kChunkTrees];  // per tree of the chunk: (root node word, value bias), chunk relative
 };
@@ -157,9 +170,12 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
         const int l0 = F.chunk_leaf_off[c], l1 = F.chunk_leaf_off[c + 1];
         const int h0 = F.chunk_hdr_off[c], h1 = F.chunk_hdr_off[c + 1];
         const uint32_t nb = (uint32_t)(n1 - n0) * 4u, lb = (uint32_t)(l1 - l0) * 8u, hb = (uint32_t)(h1 - h0) * 8u;
+        // (chunk_leaf_off is a multiple of 4: each plane of (l1 - l0) words is a whole number of 16-byte granules)
         mbar_expect_tx(&full[b], nb + lb + hb);
         bulk_g2s(buf[b].node, F.node_word + n0, nb, &full[b]);
-        bulk_g2s(buf[b].leaf, F.leaf_value + l0, lb, &full[b]);
+        // chunk c's values sit at leaf_value[2 * l0 ..): its low words, then its high words
+        bulk_g2s(buf[b].leaf_lo, F.leaf_value + 2 * (size_t)l0, lb / 2, &full[b]);
+        bulk_g2s(buf[b].leaf_hi, F.leaf_value + 2 * (size_t)l0 + (size_t)(l1 - l0), lb / 2, &full[b]);
         bulk_g2s(buf[b].hdr, F.tree_hdr + 2 * (size_t)h0, hb, &full[b]);
     };
 
@@ -241,7 +257,7 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
             }
             while (!mbar_try_wait(&full[b], (k / kStages) & 1)) {}
             const uint32_t nodes = smem_u32(buf[b].node);
-            const double* __restrict__ leaves = buf[b].leaf;
+            const uint32_t leaves = smem_u32(buf[b].leaf_lo);
             const uint4* __restrict__ hdr4 = reinterpret_cast<const uint4*>(buf[b].hdr);
             // a warp without a live cell (the tail of the share's last tile) only takes part in the hand-over
             const int n_trees = warp_live ? F.chunk_tree_off[c + 1] - F.chunk_tree_off[c] : 0;
@@ -278,10 +294,11 @@ k_forest_predict_ranked(const __grid_constant__ RankedParams p) {
                 // last level: the index of the final node is enough, its value is stored per node
                 if (depth > 0) {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (int)last_node<kWide, T>(w[j], feat, lane_off)];
+                    for (int j = 0; j < kIlp; ++j)
+                        pend[j] = leaf_value(leaves, lb[j] + (int)last_node<kWide, T>(w[j], feat, lane_off));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < kIlp; ++j) pend[j] = leaves[lb[j] + (int)__byte_perm(w[j], 0, 0x4421)];
+                    for (int j = 0; j < kIlp; ++j) pend[j] = leaf_value(leaves, lb[j] + (int)__byte_perm(w[j], 0, 0x4421));
                 }
                 n_pend = n_trees - q < kIlp ? n_trees - q : kIlp;
             }

@@ -331,7 +331,7 @@ def ranked_image(rk, order, seq_tree_off):
     """Device layout of a rank-coded forest: trees grouped by sequence (`order`) and cut into chunks
     of whole trees that fit the kernel's shared-memory buffers (never straddling a sequence; a
     multiple of RANKED_GROUP trees except at the end of a sequence).  Every chunk starts on a 16-byte
-    boundary of the node / leaf / header arrays (TMA granules); child indices are rebased to the
+    boundary of the node / leaf-plane / header arrays (TMA granules); child indices are rebased to the
     chunk; tree_hdr holds, per tree, (root word, value bias) relative to the chunk: the value of the
     chunk-relative node c a walk ends on is leaf[chunk_leaf_off + bias + c] (bias is a signed int32)."""
     toff = np.asarray(rk["tree_offset"], dtype=np.int64)
@@ -358,13 +358,13 @@ def ranked_image(rk, order, seq_tree_off):
     cto = np.asarray(chunk_tree_off, dtype=np.int64)
     c_nodes, c_leaves, c_trees = nc[cto[1:]] - nc[cto[:-1]], lc[cto[1:]] - lc[cto[:-1]], cto[1:] - cto[:-1]
     chunk_node_off = np.r_[0, np.cumsum((c_nodes + 3) // 4 * 4)]
-    chunk_leaf_off = np.r_[0, np.cumsum((c_leaves + 1) // 2 * 2)]
+    chunk_leaf_off = np.r_[0, np.cumsum((c_leaves + 3) // 4 * 4)]
     chunk_hdr_off = np.r_[0, np.cumsum((c_trees + 1) // 2 * 2)]
     chunk_of_tree = np.repeat(np.arange(len(c_trees)), c_trees)
     node_in_chunk = nc[:-1] - nc[cto[:-1]][chunk_of_tree]          # first node of each tree, chunk relative
     leaf_in_chunk = lc[:-1] - lc[cto[:-1]][chunk_of_tree]
     word = np.zeros(max(int(chunk_node_off[-1]), 4), dtype=np.uint32)
-    leaf = np.zeros(max(int(chunk_leaf_off[-1]), 2), dtype=np.float64)
+    leaf = np.zeros(max(int(chunk_leaf_off[-1]), 4), dtype=np.float64)
     hdr = np.zeros((max(int(chunk_hdr_off[-1]), 2), 2), dtype=np.uint32)
     tree_new = np.repeat(np.arange(len(order)), n_sizes)
     within = np.arange(int(n_sizes.sum())) - np.repeat(nc[:-1], n_sizes)
@@ -380,7 +380,15 @@ def ranked_image(rk, order, seq_tree_off):
     hdr[slot, 0] = word[roots] if len(order) else 0
     bias = leaf_in_chunk - (node_in_chunk + np.asarray(rk["first_leaf"], dtype=np.int64)[order])
     hdr[slot, 1] = bias.astype(np.int32).view(np.uint32) if len(order) else 0
-    return {"word": word, "leaf": leaf, "tree_hdr": hdr.reshape(-1),
+    # device form of the leaf table: per chunk the low words of its float64 values, then the high words
+    # (two 32-bit planes: conflict-free shared-memory loads, see forest_ranked.cu)
+    halves = leaf.view(np.uint32).reshape(-1, 2)
+    split = np.zeros(2 * len(leaf), dtype=np.uint32)
+    for c in range(len(c_trees)):
+        a, b = int(chunk_leaf_off[c]), int(chunk_leaf_off[c + 1])
+        split[2 * a:2 * a + (b - a)] = halves[a:b, 0]
+        split[2 * a + (b - a):2 * b] = halves[a:b, 1]
+    return {"word": word, "leaf": leaf, "leaf_split": split, "tree_hdr": hdr.reshape(-1),
             "chunk_tree_off": cto.astype(np.int32), "chunk_seq": np.asarray(chunk_seq, dtype=np.int32),
             "chunk_node_off": chunk_node_off.astype(np.int32), "chunk_leaf_off": chunk_leaf_off.astype(np.int32),
             "chunk_hdr_off": chunk_hdr_off.astype(np.int32)}
@@ -462,7 +470,7 @@ class DeviceModel:
             from ._native import dr_forest_ranked
             self._keep.update({
                 "r_node_word": dev(img["word"].view(np.int32), np.int32),
-                "r_leaf_value": dev(img["leaf"], np.float64),
+                "r_leaf_value": dev(img["leaf_split"].view(np.int32), np.int32),
                 "r_chunk_tree_off": dev(img["chunk_tree_off"], np.int32),
                 "r_chunk_seq": dev(img["chunk_seq"], np.int32),
                 "r_chunk_node_off": dev(img["chunk_node_off"], np.int32),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), "missing export: " + sym
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
-    assert lib.dr_abi_version() == 3
+    assert lib.dr_abi_version() == 4
     raw = ctypes.CDLL(_native.LIB_PATH)
     for sym in declared:
         getattr(raw, sym)
@@ -479,7 +479,14 @@ def test_ranked_image_padding_and_chunks():
     rk, img, off, order, got = _image_margins(spec, dict_sizes, codes)
     cto, cs = img["chunk_tree_off"], img["chunk_seq"]
     cn, cl, ch = img["chunk_node_off"], img["chunk_leaf_off"], img["chunk_hdr_off"]
-    assert np.all(cn % 4 == 0) and np.all(cl % 2 == 0) and np.all(ch % 2 == 0)
+    assert np.all(cn % 4 == 0) and np.all(cl % 4 == 0) and np.all(ch % 2 == 0)
+    # the device form of the leaf table: per chunk the low words of its float64 values, then the high words
+    sp = img["leaf_split"]
+    assert sp.dtype == np.uint32 and len(sp) == 2 * len(img["leaf"])
+    for c in range(len(cs)):
+        a, b = int(cl[c]), int(cl[c + 1])
+        back = (sp[2 * a + (b - a):2 * b].astype(np.uint64) << np.uint64(32)) | sp[2 * a:2 * a + (b - a)].astype(np.uint64)
+        assert np.array_equal(back.view(np.float64), img["leaf"][a:b])
     assert cto[0] == 0 and cto[-1] == len(order) and np.all(np.diff(cto) > 0) and len(cs) == len(cto) - 1
     for c in range(len(cs)):
         assert off[cs[c]] <= cto[c] and cto[c + 1] <= off[cs[c] + 1]                    # inside one sequence
