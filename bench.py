@@ -646,6 +646,7 @@ def b200_arm(args):
     engine = Engine(table, local, dist=dist, device_table=dt)
     rm = RepairModel()
     rm.opts = dict(OPTS)
+    rm.borrow_encoded_output = True   # the step reads its frame in place; verify / e2e take copies below
     if args.forests == "random":
         rm.model_provider = random_forest_provider(N_ESTIMATORS)
     err_opts = ErrorModelOptions.resolve(rm.opts)

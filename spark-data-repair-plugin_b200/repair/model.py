@@ -108,6 +108,7 @@ class RepairModel():
         self.trainer = "gpu"         # "gpu": dr_gbdt_train when eligible; "sklearn": always train.build_model
         self.distributed = None      # torch.distributed process group (or True = default group): row-sharded run
         self.frozen_models = None    # models of an earlier run() (setFrozenModels): skips the training phase
+        self.borrow_encoded_output = False   # encoded result arrays may alias a reusable pinned buffer (bench loop)
         self.last_run: Dict[str, Any] = {}
 
     # ---- setters (same names / checks / messages as the reference) -------------------------------
@@ -867,8 +868,12 @@ def repair_cells_encoded(rm, engine, table, res, models, arrow=False):
     out = []
     # (int32 needles: a wider type would make numpy convert the whole 10^7-element haystack first)
     bounds = np.searchsorted(h[0, :n_keep], np.asarray([o for _, o, _ in seg] + [E], dtype=np.int32))
+    # The arrays are copies unless the caller asked to borrow the engine's pinned staging buffer
+    # (rm.borrow_encoded_output: valid until the next pass on the same engine -- bench.py's timed loop).
+    borrow = getattr(rm, "borrow_encoded_output", False)
     for (a, _, _), lo, hi in zip(seg, bounds[:-1], bounds[1:]):
-        out.append((a, h[1, lo:hi], h[2, lo:hi], h[3, lo:hi]))  # views of the engine's pinned staging buffer
+        part = (h[1, lo:hi], h[2, lo:hi], h[3, lo:hi])
+        out.append((a,) + (part if borrow else tuple(np.array(x) for x in part)))
     return out
 
 
