@@ -919,6 +919,7 @@ def b200_arm(args):
                        "ingest_copy_s": float(t[4]), "ingest_encode_s": float(t[5]),
                        "stamps_s": {"engine_ready": float(t[6]), "detect_done": float(t[7]), "repair_done": float(t[8]),
                                     "run_returned": float(t[9])},
+                       "ingest_detail_rank0_last_step": {kk: lr.get(kk) for kk in ("ingest_ids_s", "ingest_encode_phases")},
                        "frame_rows": int(frame.num_rows), "frame_equals_resident_pass": int(flag[0]) == 0,
                        "call": "RepairModel().setArrowInput(pyarrow.Table in pageable host memory).setRowId('tid')"
                                ".setErrorDetectors([NullErrorDetector(), ConstraintErrorDetector(..)])"

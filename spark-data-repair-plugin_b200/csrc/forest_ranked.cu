@@ -368,7 +368,10 @@ extern "C" int dr_forest_predict_ranked(dr_ctx* ctx, const dr_forest_ranked* for
         return dr_fail(ctx, DR_ERR_UNSUPPORTED, "the wide rank tile does not fit a forest with %d slots", f.n_slots);
     auto launch = [&](auto kernel, int threads, size_t smem, int per_sm) -> int {
         DR_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = dr_grid_for(ctx, n_cells, threads, per_sm);
+        // one warp's worth of cells is the unit of work (balanced partition in the kernel): a few thousand
+        // cells spread over all SMs instead of filling a handful of 512-cell CTAs that each stream the whole
+        // forest alone -- the launch of an FD-flagged target (~10^4 cells) took 1.4 ms whatever the table size
+        const int grid = dr_grid_for(ctx, n_cells, 32, per_sm);
         kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
         return DR_OK;
     };

@@ -85,8 +85,37 @@ def _encode_numeric(name, kind, arr):
     return Column(name, kind, uniq, codes, vals)
 
 
+def _encode_arrow_strings(name, arr):
+    """pyarrow string / dictionary<string> array (one chunk) -> Column: Arrow's C++ dictionary_encode, then only
+    the dictionary (one entry per distinct value) is sorted and turned into Python strings."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    if not pa.types.is_dictionary(arr.type):
+        arr = pc.dictionary_encode(arr)
+    idx = arr.indices
+    valid = np.asarray(idx.is_valid())
+    raw = np.asarray(idx.fill_null(0).to_numpy(zero_copy_only=False), dtype=np.int64)
+    entries = arr.dictionary.to_pylist()
+    # a Parquet dictionary page may list values the rows never use: keep what occurs, sorted
+    used = np.zeros(len(entries), dtype=bool)
+    used[raw[valid]] = True
+    dictionary, lut = _sorted_dictionary(entries, used)
+    codes = np.where(valid, lut[raw], -1).astype(np.int32) if len(entries) else np.full(len(raw), -1, dtype=np.int32)
+    return Column(name, "str", dictionary, codes, None)
+
+
 def _encode_strings(name, series):
     import pandas as pd
+    if series.dtype == object or str(series.dtype) in ("string", "str"):
+        # all-string columns (the usual case) never become one Python object per cell: Arrow encodes them;
+        # anything else (mixed objects that need str()) takes the generic path below
+        try:
+            import pyarrow as pa
+            arr = pa.array(series.to_numpy(dtype=object, na_value=None) if series.dtype != object else series.to_numpy(),
+                           type=pa.string(), from_pandas=True)
+            return _encode_arrow_strings(name, arr)
+        except Exception:  # noqa: BLE001  (non-string objects, no pyarrow)
+            pass
     obj = series.astype(object)
     isn = pd.isna(obj).to_numpy()
     strs = np.array([None if n else str(v) for v, n in zip(obj.tolist(), isn.tolist())], dtype=object)
@@ -263,24 +292,7 @@ class EncodedTable:
                 vals = pc.cast(arr, pa.float64()).to_numpy(zero_copy_only=False)
                 cols.append(_encode_numeric(f.name, kinds[f.name], np.asarray(vals, dtype=np.float64)))
                 continue
-            if not pa.types.is_dictionary(arr.type):
-                arr = pc.dictionary_encode(arr)
-            idx = arr.indices
-            valid = np.asarray(idx.is_valid())
-            raw = np.asarray(idx.fill_null(0).to_numpy(zero_copy_only=False), dtype=np.int64)
-            entries = np.array(arr.dictionary.to_pylist(), dtype=object)
-            # a Parquet dictionary page may list values the rows never use: keep what occurs, sorted
-            used = np.zeros(len(entries), dtype=bool)
-            used[raw[valid]] = True
-            used &= np.array([e is not None for e in entries], dtype=bool) if len(entries) else used
-            keep = np.nonzero(used)[0]
-            order = keep[np.argsort(np.array([str(entries[i]) for i in keep], dtype=object), kind="stable")] \
-                if len(keep) else keep
-            rank = np.full(len(entries), -1, dtype=np.int32)
-            rank[order] = np.arange(len(order), dtype=np.int32)
-            codes = np.where(valid, rank[raw], -1).astype(np.int32) if len(entries) else \
-                np.full(len(raw), -1, dtype=np.int32)
-            cols.append(Column(f.name, "str", np.array([str(entries[i]) for i in order], dtype=object), codes, None))
+            cols.append(_encode_arrow_strings(f.name, arr))
         ids = plain(tbl[row_id])
         if pa.types.is_dictionary(ids.type):
             ids = ids.dictionary_decode()
@@ -325,6 +337,7 @@ class EncodedTable:
             raise AnalysisException(
                 "Uniqueness does not hold in column '{}' of table '{}' (# of distinct '{}': {}, # of rows: {})".format(
                     row_id, name, row_id, n_distinct, n))
+        t_ids = time.perf_counter() - t0
         # ---- attribute columns: what has to travel ---------------------------------------------------
         plan = []   # per attribute: (entries, width, [(idx address, validity address or 0, bit offset, rows)])
         for a in attrs:
@@ -360,6 +373,7 @@ class EncodedTable:
         side = torch.cuda.Stream(device=device)
         t_copy = t_remap = 0.0
         keep_alive = []
+        phases = {"wait_presence_s": 0.0, "sort_dictionaries_s": 0.0, "lut_upload_s": 0.0, "final_sync_s": 0.0}
 
         def launch_presence(g0, g1, where):
             uoff = [0]
@@ -383,7 +397,10 @@ class EncodedTable:
         def finish(g0, g1, where, pres):
             """Sorted dictionaries of the group (host, one entry per distinct value) -> LUTs -> re-encode."""
             uoff, used, used_h, done = pres
+            t_w = time.perf_counter()
             done.synchronize()
+            phases["wait_presence_s"] += time.perf_counter() - t_w
+            t_w = time.perf_counter()
             bits_all = used_h.numpy().view(np.uint32)
             luts, loff = [], [0]
             for i in range(g0, g1):
@@ -394,8 +411,11 @@ class EncodedTable:
                 luts.append(lut)
                 loff.append(loff[-1] + len(lut))
                 table_cols[i] = Column(attrs[i], "str", dictionary, None, None)
+            phases["sort_dictionaries_s"] += time.perf_counter() - t_w
+            t_w = time.perf_counter()
             with torch.cuda.stream(side):
                 d_lut = torch.from_numpy(np.concatenate(luts + [np.zeros(1, dtype=np.int32)])).to(device)
+                phases["lut_upload_s"] += time.perf_counter() - t_w
                 for i in range(g0, g1):
                     entries, width, parts = plan[i]
                     row = 0
@@ -447,8 +467,10 @@ class EncodedTable:
         t1 = time.perf_counter()
         if pending is not None:
             finish(*pending)
+        t_w = time.perf_counter()
         torch.cuda.current_stream().wait_stream(side)
         side.synchronize()
+        phases["final_sync_s"] += time.perf_counter() - t_w
         keep_alive.clear()
         t_remap += time.perf_counter() - t1
 
@@ -461,7 +483,8 @@ class EncodedTable:
             c._codes = (lambda i=i: dt.codes[i][:n].cpu().numpy())
         if timings is not None:
             timings.update({"ingest_copy_s": t_copy, "ingest_encode_s": t_remap,
-                            "ingest_total_s": time.perf_counter() - t0})
+                            "ingest_total_s": time.perf_counter() - t0, "ingest_ids_s": t_ids,
+                            "ingest_encode_phases": dict(phases)})
         return t, dt
 
     @classmethod
