@@ -332,12 +332,6 @@ class RepairModel():
             raise ValueError("Cannot enable the maximal likelihood repair mode when continous attributes found")
         if self.targets and len(set(self.targets) & (set(table.names) | {table.row_id})) == 0:
             raise ValueError("Target attributes not found in {}: {}".format(input_name, to_list_str(self.targets)))
-        if self.training_data_rebalancing_enabled:
-            # train.py:242-290 over/under-samples with imbalanced-learn's SMOTEN, which this build does not
-            # carry; silently training on unbalanced data would not be what was asked for
-            raise NotImplementedError("training data rebalancing needs imbalanced-learn (SMOTEN), which is not "
-                                      "available; `class_weight=balanced` (model.lgb.class_weight) is applied "
-                                      "by default instead")
         err_opts = ErrorModelOptions.resolve(self.opts)
         validate_options(self.opts)
         for key in _MODEL_OPT:
@@ -555,6 +549,24 @@ def _train_model(rm, engine, table, res, y, continuous, tile_col, fdeps=None):
         if kind != "cont":
             e["categories"] = first_seen(codes[:, tile_col[f]])
         encoders.append(e)
+    if rm.training_data_rebalancing_enabled and is_discrete:
+        # train.py:901-903: the classes of a discrete target are brought to the median class size before
+        # training; like SMOTEN, every feature is taken as nominal (numeric ones by their distinct values)
+        from .rebalance import rebalance
+        fcols = [tile_col[f] for f in features]
+        src, fcodes, y_new = rebalance(codes[:, fcols], codes[:, tile_col[y]])
+        codes2 = np.full((len(src), codes.shape[1]), -1, dtype=codes.dtype)
+        codes2[:, fcols] = fcodes
+        codes2[:, tile_col[y]] = y_new
+        if vals is not None:
+            vals2 = np.full((len(src), vals.shape[1]), np.nan, dtype=np.float64)
+            for f in features:
+                if f in cont_idx:
+                    d = np.r_[np.asarray(table.by_name[f].dictionary, dtype=np.float64), np.nan]
+                    vals2[:, cont_idx[f]] = d[codes2[:, tile_col[f]]]      # code -1 -> NaN (last slot)
+            vals = vals2
+        codes = codes2
+        rows = np.where(src >= 0, np.asarray(rows)[np.maximum(src, 0)], -1)   # -1 = synthetic row
     X = encode_matrix(encoders, {f: codes[:, tile_col[f]] for f in features},
                       {f: vals[:, cont_idx[f]] for f in features if f in cont_idx} if vals is not None else {},
                       dict_sizes)

@@ -455,3 +455,19 @@ def test_domain_pruning_in_one_call_equals_the_per_cell_kernel():
     assert got[False][2] > 0 and got[False][1] != got[False][3]          # something was pruned
     for a in got[True][0]:
         assert np.array_equal(got[False][0][a], got[True][0][a]), a
+
+
+def test_training_data_rebalancing_reference_kat():
+    # tests/test_model.py:1197-1215: mixed_input with setTrainingDataRebalancingEnabled(True) repairs its four cells
+    from repair import RepairModel
+    rows = [(1, 0, 1.0, 1.0, "a"), (2, 1, 1.5, 1.5, "b"), (3, 0, 1.4, None, "b"), (4, 1, 1.3, 1.3, "b"),
+            (5, 1, 1.2, 1.1, "b"), (6, 1, 1.1, 1.2, "b"), (7, 0, None, 1.4, "b"), (8, 1, 1.4, 1.0, "b"),
+            (9, 0, 1.2, 1.1, "b"), (10, None, 1.3, 1.2, "b"), (11, 0, 1.0, 1.9, "b"), (12, 0, 1.9, 1.2, "b"),
+            (13, 0, 1.2, 1.3, "b"), (14, 0, 1.8, 1.2, None), (15, 0, 1.3, 1.1, "b"), (16, 1, 1.3, 1.0, "b"),
+            (17, 0, 1.3, 1.0, "b")]
+    df = pd.DataFrame(rows, columns=["tid", "v1", "v2", "v3", "v4"])
+    out = RepairModel().setInput(df).setRowId("tid").setTrainingDataRebalancingEnabled(True) \
+        .option("model.hp.max_evals", "1").option("model.lgb.n_estimators", "30").run()
+    got = sorted((int(r["tid"]), r["attribute"], r["current_value"]) for r in out.to_dict("records"))
+    assert got == [(3, "v3", None), (7, "v2", None), (10, "v1", None), (14, "v4", None)]
+    assert all(r is not None and r == r for r in out["repaired"].tolist())

@@ -718,5 +718,34 @@ def test_invalid_running_modes_are_refused_before_any_gpu_work():
                  "compute_repair_score"):
         with pytest.raises(ValueError, match=msg):
             m.run(**{mode: True})
-    with pytest.raises(NotImplementedError, match="rebalancing needs imbalanced-learn"):
-        RepairModel().setInput(adult).setRowId("tid").setTrainingDataRebalancingEnabled(True).run()
+
+
+
+def test_training_data_rebalancing_restates_smoten_and_random_under_sampling():
+    """repair/rebalance.py (train.py:242-293): every class ends at the median class size -- larger classes keep
+    a subset of their rows, smaller ones (with more than k = 5 rows) get synthetic rows whose every feature
+    value is the mode of the k nearest class members under the value difference metric."""
+    from repair.rebalance import K_NEIGHBORS, rebalance
+    rng = np.random.default_rng(4)
+    n = 600
+    y = rng.choice([0, 1, 2, 3, 4], size=n, p=[0.55, 0.25, 0.12, 0.075, 0.005])
+    y[:3] = 4                                        # a class too small to over-sample
+    codes = np.stack([(y * 2 + rng.integers(0, 2, n)) % 7, rng.integers(-1, 5, n), (y + rng.integers(0, 3, n)) % 4],
+                     axis=1).astype(np.int32)
+    src, out_codes, out_y = rebalance(codes, y)
+    counts = np.bincount(y, minlength=5)
+    median = int(np.median(counts))
+    got = np.bincount(out_y, minlength=5)
+    for c in range(5):
+        want = median if counts[c] > K_NEIGHBORS else counts[c]
+        assert got[c] == want, (c, counts[c], got[c])
+    real = src >= 0
+    assert np.array_equal(out_codes[real], codes[src[real]]) and np.array_equal(out_y[real], y[src[real]])
+    assert len(np.unique(src[real])) == real.sum()                      # under-sampling draws without replacement
+    for c in range(5):                                                  # synthetic rows only use the class's own values
+        synth = out_codes[(~real) & (out_y == c)]
+        for j in range(codes.shape[1]):
+            assert set(synth[:, j].tolist()) <= set(codes[y == c][:, j].tolist())
+    # deterministic (seeded)
+    again = rebalance(codes, y)
+    assert all(np.array_equal(a, b) for a, b in zip(again, (src, out_codes, out_y)))
