@@ -326,6 +326,8 @@ def verify_step(engine, table, res, out, models, k, n_sample, dist, seed=12345):
     dev = engine.device
     names = table.names
     n = engine.n_rows
+    if ckernels.available():
+        ckernels.use_all_cores()   # (torchrun exports OMP_NUM_THREADS=1; the rank is bound to its GPU's NUMA node)
     info = {"hist_columns_checked": 0, "hist_mismatches": 0, "cell_count_attrs_checked": 0,
             "cell_count_mismatches": 0, "cells_checked": 0, "mismatches": 0}
     # ---- histograms ----
