@@ -466,8 +466,11 @@ def test_training_data_rebalancing_reference_kat():
             (13, 0, 1.2, 1.3, "b"), (14, 0, 1.8, 1.2, None), (15, 0, 1.3, 1.1, "b"), (16, 1, 1.3, 1.0, "b"),
             (17, 0, 1.3, 1.0, "b")]
     df = pd.DataFrame(rows, columns=["tid", "v1", "v2", "v3", "v4"])
-    out = RepairModel().setInput(df).setRowId("tid").setTrainingDataRebalancingEnabled(True) \
+    from repair import NullErrorDetector
+    out = RepairModel().setInput(df).setRowId("tid").setErrorDetectors([NullErrorDetector()]) \
+        .setTrainingDataRebalancingEnabled(True) \
         .option("model.hp.max_evals", "1").option("model.lgb.n_estimators", "30").run()
-    got = sorted((int(r["tid"]), r["attribute"], r["current_value"]) for r in out.to_dict("records"))
+    none = lambda v: None if v is None or v != v else v  # noqa: E731
+    got = sorted((int(r["tid"]), r["attribute"], none(r["current_value"])) for r in out.to_dict("records"))
     assert got == [(3, "v3", None), (7, "v2", None), (10, "v1", None), (14, "v4", None)]
-    assert all(r is not None and r == r for r in out["repaired"].tolist())
+    assert all(none(r) is not None for r in out["repaired"].tolist())
