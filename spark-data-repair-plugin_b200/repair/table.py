@@ -458,9 +458,11 @@ class EncodedTable:
             ctx.h2d_copy(src, dst, size, threads)        # blocks; the previous group's kernels run meanwhile
             t_copy += time.perf_counter() - t1
             t1 = time.perf_counter()
-            pres = launch_presence(g0, g1, where)
+            # (the previous group first: its LUT upload is a synchronous copy on the side stream and would
+            # otherwise wait for this group's presence kernels, holding back the next group's copy)
             if pending is not None:
                 finish(*pending)
+            pres = launch_presence(g0, g1, where)
             pending = (g0, g1, where, pres)
             t_remap += time.perf_counter() - t1
             g0 = g1
