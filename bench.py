@@ -777,8 +777,10 @@ def b200_arm(args):
     n_disc = k
     alg = {
         "scan_hist": 4.0 * n_disc * n,                               # every code read once
-        "forest_predict": stats["cells"] * (4.0 * (k - 1) + 4.0),     # feature gather + fill per cell
-        "forest_predict_ranked": stats["cells"] * (4.0 * (k - 1) + 4.0),
+        # per error cell 4*F bytes of feature gather (F = K - 1) + 4 bytes written + 16 bytes of
+        # output record = 144 B/cell at K = 32
+        "forest_predict": stats["cells"] * (4.0 * (k - 1) + 4.0 + 16.0),
+        "forest_predict_ranked": stats["cells"] * (4.0 * (k - 1) + 4.0 + 16.0),
         "gather_rows_masked": stats["dirty"] * 4.0 * k * 2,          # dirty rows in, tile out
         "cooc": None, "dc_fd_build": None, "dc_fd_flag": None, "domain_score": None,
     }
