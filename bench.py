@@ -808,8 +808,8 @@ def b200_arm(args):
     if fp:
         # forest inference is bounded by the shared-memory pipe, not HBM (profiles/r1_ncu_forest_*.md): the
         # roofline that explains it counts shared-memory wavefronts.  Algorithmic minimum per warp: two
-        # loads per tree level (rank byte, node word) + per tree one header broadcast and a 64-bit leaf
-        # value (two wavefronts); peak = one wavefront per cycle per SM.
+        # loads per tree level (rank, node word; the last level only the rank) + per tree one header
+        # broadcast and the leaf value (two 32-bit loads); peak = one wavefront per cycle per SM.
         f_ms = sum(v[1] for v in fp)
         levels = sum((m[1].n_trees * (m[1].ranked.max_depth if m[1].ranked is not None else 5)) *
                      res_cells.get(y, 0) for y, m in models if m[0] == "forest")
@@ -825,15 +825,18 @@ def b200_arm(args):
             "max_depth_by_model": {y: shape[y]["max_depth"] for y in shape}}
         sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         sm_count = torch.cuda.get_device_properties(device).multi_processor_count
-        wf = (2.0 * levels + 3.0 * tree_cells) / 32.0
+        # per warp and tree: 2 loads per level except the last (rank only) + header broadcast (1) + leaf value
+        # (two 32-bit loads) = 2 * depth + 2
+        wf = (2.0 * levels + 2.0 * tree_cells) / 32.0
         e = ncu_for("k_forest_predict_ranked")
         line["roofline_forest"] = {
             "kernel": "k_forest_predict_ranked", "bound": "shared-memory wavefronts",
             "achieved": wf / (f_ms / 1e3) / 1e9, "peak": sm_count * sm_hz / 1e9, "unit": "Gwavefront/s",
             "frac": wf / (f_ms / 1e3) / (sm_count * sm_hz),
             "measured_pipe_utilisation": e.get("smem_wavefronts_per_cycle_per_sm") if e else None,
-            "note": "achieved = algorithmic wavefronts (2 per warp-level + 3 per warp-tree) / kernel time; "
-                    "measured_pipe_utilisation counts bank-conflict replays too (ncu)"}
+            "note": "achieved = algorithmic wavefronts (2 per warp-level + 2 per warp-tree) / kernel time; "
+                    "measured_pipe_utilisation is ncu's wavefront count (conflict replays and the tile fill "
+                    "included) per cycle and SM"}
     if dominant:
         d = kernels[dominant]
         ach = d.get("achieved_gbs")
