@@ -749,3 +749,72 @@ def test_training_data_rebalancing_restates_smoten_and_random_under_sampling():
     # deterministic (seeded)
     again = rebalance(codes, y)
     assert all(np.array_equal(a, b) for a, b in zip(again, (src, out_codes, out_y)))
+
+
+def test_row_id_joins_are_vectorised_and_string_compatible():
+    """utils.row_positions (setErrorCells / misc.repair / maximal-likelihood repair_data): ids are compared like
+    the reference's CAST(.. AS STRING) joins, without a Python dict over the table."""
+    from repair.utils import row_positions
+    pos, found = row_positions(np.array([3, 5, 9, 12]), ["5", "12", "7", 9, "x"])
+    assert list(found) == [True, True, False, True, False] and list(pos[found]) == [1, 3, 2]
+    pos, found = row_positions(np.array([9, 3, 12, 5]), [5, 12, 7, 9])            # unordered integer ids
+    assert list(found) == [True, True, False, True] and list(pos[found]) == [3, 2, 0]
+    pos, found = row_positions(np.array(["a", "b", "c"], dtype=object), ["c", "z", "a"])
+    assert list(found) == [True, False, True] and list(pos[found]) == [2, 0]
+    pos, found = row_positions(np.zeros(0, dtype=np.int64), [1])
+    assert list(found) == [False]
+
+
+def test_search_keeps_the_defaults_unless_a_configuration_wins_by_one_standard_error():
+    """search.search: trial 0 = LightGBM's defaults; max_evals = 1 does not evaluate at all; a better mean CV
+    loss only wins when it beats the defaults by more than the standard error of the defaults' folds."""
+    from repair import search as HS
+    assert HS.search(lambda p: 1 / 0, 1, 50, 0) == (dict(HS.DEFAULTS), None, 0)
+    calls = []
+
+    def noisy(p):          # every configuration 2 % better than the defaults, whose folds scatter by 10 %
+        calls.append(p)
+        return (1.0, [0.9, 1.0, 1.1]) if p == HS.DEFAULTS else (0.98, [0.98] * 3)
+    best, loss, n = HS.search(noisy, 6, 50, 0)
+    assert calls[0] == HS.DEFAULTS and n == 6 and best == HS.DEFAULTS and loss == 1.0
+
+    def clear(p):          # a clear win is taken
+        return (1.0, [0.99, 1.0, 1.01]) if p == HS.DEFAULTS else (0.5, [0.5] * 3)
+    best, loss, n = HS.search(clear, 4, 50, 0)
+    assert best != HS.DEFAULTS and loss == 0.5
+    # plain floats (no fold losses) fall back to hyperopt's argmin; exceptions count as loss 0.0 (train.py:176-180)
+    best, loss, _ = HS.search(lambda p: 1.0 if p == HS.DEFAULTS else 0.9, 3, 50, 0)
+    assert best != HS.DEFAULTS and loss == 0.9
+    # early stop after `no_progress_loss` evaluations without improvement
+    assert HS.search(lambda p: 1.0, 100, 5, 0)[2] == 6
+
+
+def test_gpu_trainer_bins_high_cardinality_features_like_max_bin():
+    """gbdt.bin_sample: more than 254 distinct encoded values -> adjacent values share a bin (about equal sample
+    counts), every row's value lies inside its bin, thresholds fall between bins (train.py:106 max_bin = 255)."""
+    from repair import gbdt as G
+    from repair.forest import encoder_lut, first_seen
+    rng = np.random.default_rng(0)
+    k = 600
+    codes = rng.integers(-1, k, size=5000)
+    enc = [{"attr": "a", "type": "ordinal", "categories": first_seen(codes)},
+           {"attr": "b", "type": "ordinal", "categories": list(range(10))}]
+    small = rng.integers(0, 10, size=5000)
+    bins, n_bins, values = G.bin_sample(enc, {"a": codes, "b": small}, {"a": k, "b": 10})
+    assert bins.dtype == np.uint8 and n_bins[0] <= G.MAX_BINS + 1 and n_bins[1] in (11, 12)   # 10 values (+ "unseen") + missing
+    hi, lo = values[0]
+    assert np.all(lo <= hi) and np.all(hi[:-1] < lo[1:])                 # disjoint, ordered value ranges
+    e = encoder_lut(enc[0], k)[:, 0][codes + 1]
+    ok = ~np.isnan(e)
+    b = bins[:, 0].astype(np.int64)
+    assert np.all(b[~ok] == n_bins[0] - 1)                               # missing bin
+    assert np.all((e[ok] >= lo[b[ok]]) & (e[ok] <= hi[b[ok]]))
+    assert np.bincount(b[ok]).max() <= 3 * len(e) // G.MAX_BINS + 3      # roughly equal-count bins
+    assert np.ndim(values[1]) == 1                                       # the small feature keeps one bin per value
+    # thresholds: midway between the split bin's largest and the next bin's smallest value
+    nodes = np.zeros((1, 1, G.MAX_NODES), dtype=G.NODE_DTYPE)
+    nodes[0, 0, 0] = (0, 3, 0, 1, 2, (0, 0), 0.0)
+    nodes[0, 0, 1] = (-1, 0, 0, 0, 0, (0, 0), -1.0)
+    nodes[0, 0, 2] = (-1, 0, 0, 0, 0, (0, 0), 1.0)
+    f = G.flatten(nodes, np.array([[3]]), np.zeros(1), values, 2, 1)
+    assert f["threshold"][0] == (hi[3] + lo[4]) / 2.0
