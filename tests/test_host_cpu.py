@@ -818,3 +818,53 @@ def test_gpu_trainer_bins_high_cardinality_features_like_max_bin():
     nodes[0, 0, 2] = (-1, 0, 0, 0, 0, (0, 0), 1.0)
     f = G.flatten(nodes, np.array([[3]]), np.zeros(1), values, 2, 1)
     assert f["threshold"][0] == (hi[3] + lo[4]) / 2.0
+
+
+def test_presence_map_decodes_pairs_on_demand():
+    """engine._PresenceMap: the packed presence bits of a pair launch, unpacked per pair only when asked."""
+    from repair.engine import _PresenceMap
+    dom = {"x": 3, "y": 5, "z": 2}
+    pairs = [("x", "y"), ("z", "x")]
+    rng = np.random.default_rng(1)
+    mats = [rng.random((dom[a] + 1, dom[b] + 1)) < 0.4 for a, b in pairs]
+    words, offs = [], [0]
+    for m in mats:
+        bits = np.zeros((m.size + 31) // 32 * 32, dtype=np.uint8)
+        bits[:m.size] = m.reshape(-1)
+        words.append(np.packbits(bits, bitorder="little").view(np.uint32))
+        offs.append(offs[-1] + len(words[-1]))
+    pm = _PresenceMap(pairs, offs, np.concatenate(words), dom)
+    assert ("x", "y") in pm and ("y", "x") not in pm and pm.get(("y", "x")) is None
+    assert np.array_equal(pm[("x", "y")], mats[0]) and np.array_equal(pm.get(("z", "x")), mats[1])
+
+
+def test_bench_frame_comparison_catches_differences():
+    """bench.frames_equal (the e2e leg's check of the API's Arrow frame against the resident pass)."""
+    import sys
+    import pyarrow as pa
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    from repair.table import EncodedTable
+    names = ["a", "b", "c"]
+    table = EncodedTable.from_codes("tid", names, [np.zeros(4, dtype=np.int32)] * 3, [3, 2, 2])
+    out = [("a", np.array([1, 3], dtype=np.int32), np.array([-1, 2], dtype=np.int32), np.array([0, 1], dtype=np.int32)),
+           ("c", np.array([0], dtype=np.int32), np.array([1], dtype=np.int32), np.array([-1], dtype=np.int32))]
+
+    def frame(rep_a=(0, 1), ids_a=(101, 103)):
+        def dic(codes, attr):
+            strs = pa.array(table.by_name[attr].strings(), type=pa.string())
+            codes = np.asarray(codes, dtype=np.int32)
+            return pa.DictionaryArray.from_arrays(pa.array(codes, mask=codes < 0), strs)
+        attr_names = pa.array(["a", "b", "c"], type=pa.string())
+        att = [pa.DictionaryArray.from_arrays(pa.array(np.array([0, 0], dtype=np.int32)), attr_names),
+               pa.DictionaryArray.from_arrays(pa.array(np.array([2], dtype=np.int32)), attr_names)]
+        return pa.table({"tid": pa.chunked_array([pa.array(np.array(ids_a, dtype=np.int64)), pa.array(np.array([100], dtype=np.int64))]),
+                         "attribute": pa.chunked_array(att),
+                         "current_value": pa.chunked_array([dic([-1, 2], "a"), dic([1], "c")]),
+                         "repaired": pa.chunked_array([dic(list(rep_a), "a"), dic([-1], "c")])})
+    assert bench.frames_equal(frame(), out, 100, names, table)
+    assert not bench.frames_equal(frame(rep_a=(0, 2)), out, 100, names, table)        # a repaired value differs
+    assert not bench.frames_equal(frame(ids_a=(101, 102)), out, 100, names, table)    # a row id differs
+    assert not bench.frames_equal(frame(), out[:1], 100, names, table)                # an attribute is missing
