@@ -65,8 +65,10 @@ def _worker(rank, world, port, out_dir):
     local_bits = np.zeros(((doms[0] + 1) * (doms[1] + 1) + 31) // 32, dtype=np.uint32)
     np.bitwise_or.at(local_bits, idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
     tbits = torch.from_numpy(local_bits.view(np.int32).copy())
-    dist.exchange(None, [(flat, "sum"), (tlo, "min"), (thi, "max"), (tbits, "or")])   # THE exchange step
-    assert dist.n_exchanges == 1
+    # ... and so does the one-element "did the presence sample cover every shard" flag (MIN)
+    cover = torch.tensor([1 if rank == 0 else 0], dtype=torch.int64)
+    dist.exchange(None, [(flat, "sum"), (tlo, "min"), (thi, "max"), (tbits, "or"), (cover, "min")])   # THE exchange step
+    assert dist.n_exchanges == 1 and int(cover.item()) == 0
     g = flat.numpy()
     ghist, off = {}, 0
     for nm, d in zip(names, doms):
@@ -94,6 +96,19 @@ def _worker(rank, world, port, out_dir):
     fbits = np.zeros_like(local_bits)
     np.bitwise_or.at(fbits, fidx >> 5, np.uint32(1) << (fidx & 31).astype(np.uint32))
     assert np.array_equal(tbits.numpy().view(np.uint32), fbits)       # OR segment
+    # every rank ingested its own rows with its own dictionaries: unify() makes the codes global
+    import pandas as pd
+    lo_r, hi_r = shard.row_offset, shard.row_offset + shard.n_rows
+    strs = {nm: np.array(["v%03d" % v if v >= 0 else None for v in full[i][lo_r:hi_r]], dtype=object)
+            for i, nm in enumerate(names[:3])}
+    local = EncodedTable.from_pandas(pd.DataFrame({"tid": np.arange(lo_r, hi_r), **strs}), "tid")
+    whole = EncodedTable.from_pandas(pd.DataFrame(
+        {"tid": np.arange(n), **{nm: np.array(["v%03d" % v if v >= 0 else None for v in full[i]], dtype=object)
+                                 for i, nm in enumerate(names[:3])}}), "tid")
+    uni = local.unify(dist)
+    assert uni.row_offset == lo_r and uni.n_rows_global == n
+    for cu, cw in zip(uni.columns, whole.columns):
+        assert list(cu.dictionary) == list(cw.dictionary) and np.array_equal(cu.codes, cw.codes[lo_r:hi_r])
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     td.destroy_process_group()
 
