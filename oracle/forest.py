@@ -140,11 +140,12 @@ def encode_rows(encoders, columns):
         if w == 0:
             continue
         col = columns[e["attr"]]
-        cache = {}
-        for r, v in enumerate(col):
-            key = ("__null__",) if v is None else v
-            if key not in cache:
-                cache[key] = encode_value(e, v)
-            X[r, j:j + w] = cache[key]
+        # one encode_value per DISTINCT cell value (hashed in C), then a table look-up for the whole column
+        if n:
+            import pandas as pd
+            where, uniques = pd.factorize(np.asarray(col, dtype=object), use_na_sentinel=True)   # None -> -1
+            table = [encode_value(e, v) for v in uniques.tolist()] + [encode_value(e, None)]
+            where = np.where(where < 0, len(table) - 1, where)
+            X[:, j:j + w] = np.asarray(table, dtype=np.float64).reshape(len(table), w)[where]
         j += w
     return X
